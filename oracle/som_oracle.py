@@ -1,0 +1,516 @@
+"""CPU oracle for the batch-SOM training epoch of XPySom-Dask.
+
+TEST INFRASTRUCTURE ONLY.  This module is a numpy restatement of the
+reference's hot path (``/root/reference/xpysom_dask``), used as the checker in
+``tests/``, in ``__graft_entry__.smoke()`` and as the ``cpu_baseline`` /
+``--impl reference`` leg of ``bench.py``.  Nothing under ``xpysom_dask_b200/``
+imports it; the product path is CUDA only.
+
+Parity status: PINNED.  ``tests/test_oracle_golden.py`` checks every function
+here against fixtures in ``tests/golden/`` that were produced by importing the
+real reference (``oracle/make_golden.py``, run in the build container where
+``/root/reference`` exists), and against the scalar known answers of the
+reference's own ``test_distances.py:92-154`` and ``tests.py``.  The one
+exception is the Chebyshev distance, which the reference does not have
+(``distances.py:162-170``): its oracle is the scalar definition ``max|x-w|`` and
+is marked "no reference pin".
+
+The restatement keeps the reference's numpy operation order wherever that
+order is observable in the result (dtype promotion of sigma, product of two
+exponentials vs exponential of a sum, the strict windows, the compact-support
+quirk of the mexican hat, first-index argmin), so that on the same numpy build
+it is bit-identical to the reference.  Each function cites the lines it
+restates.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Optional, Tuple
+
+import numpy as np
+
+DISTANCES = ("euclidean", "cosine", "manhattan", "chebyshev", "norm_p")
+NEIGHBORHOODS = ("gaussian", "mexican_hat", "bubble", "triangle")
+TOPOLOGIES = ("rectangular", "hexagonal")
+DECAYS = ("exponential", "asymptotic", "linear")
+
+
+# --------------------------------------------------------------------------
+# S: decay schedules                                   (decays.py:4-65)
+# --------------------------------------------------------------------------
+def decay_value(kind: str, v0, vN, t: int, T: int):
+    """Scalar schedule shared by sigma and the learning rate (xpysom.py:541-543).
+
+    asymptotic  decays.py:20   v0 / (1 + 2t/T)
+    exponential decays.py:39-43  v0 * exp(-t * (-log(vN/v0)/T)); vN == 0 -> log(0.1)
+    linear      decays.py:62-65  v0 + (vN-v0) * t/(T-1); T == 1 -> v0
+
+    The exponential rule returns ``np.float64`` (it goes through numpy's
+    exp/log); the other two return Python floats.  That difference is
+    observable: a numpy-float sigma promotes the whole neighbourhood to fp64.
+    """
+    if kind == "asymptotic":
+        return v0 / (1 + 2 * t / T)
+    if kind == "exponential":
+        rate = -np.log(0.1) / T if vN == 0 else -np.log(vN / v0) / T
+        return v0 * np.exp(-t * rate)
+    if kind == "linear":
+        return v0 if T == 1 else v0 + (vN - v0) * t / (T - 1)
+    raise ValueError("%s not supported. Functions available: %s" % (kind, ", ".join(DECAYS)))
+
+
+# --------------------------------------------------------------------------
+# D: distances, all return an (n, K) matrix            (distances.py)
+# --------------------------------------------------------------------------
+def row_sq(a):
+    """sum of squares per row, keepdims            (distances.py:21,30,54)."""
+    return np.power(a, 2).sum(axis=1, keepdims=True)
+
+
+def dist_euclidean_part(x, w, w_sq=None):
+    """-2 x.w^T + |w|^2, the row-constant |x|^2 dropped (distances.py:11-23)."""
+    if w_sq is None:
+        w_sq = row_sq(w)
+    return -2 * np.dot(x, w.T) + w_sq.T
+
+
+def dist_euclidean_sq(x, w, w_sq=None):
+    """full squared L2                               (distances.py:25-31)."""
+    return dist_euclidean_part(x, w, w_sq) + row_sq(x)
+
+
+def dist_euclidean(x, w, w_sq=None):
+    """L2 with negative round-off -> NaN -> 0        (distances.py:33-43)."""
+    return np.nan_to_num(np.sqrt(dist_euclidean_sq(x, w, w_sq)))
+
+
+def dist_cosine(x, w, w_sq=None):
+    """1 - nan_to_num(x.w / sqrt(|x|^2 |w|^2))       (distances.py:45-59)."""
+    if w_sq is None:
+        w_sq = row_sq(w)
+    x_sq = row_sq(x)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        sim = np.nan_to_num(np.dot(x, w.T) / np.sqrt(x_sq * w_sq.T))
+    return 1 - sim
+
+
+def dist_norm_p_generic(x, w, p=2):
+    """sum |x-w|^p through an (n,K,D) broadcast       (distances.py:61-75)."""
+    return np.sum(np.power(np.abs(x[:, None, :] - w[None, :, :]), p), axis=2)
+
+
+def dist_norm_p_even(x, w, p=2):
+    """binomial expansion, p+1 GEMMs, fp64 accumulator (distances.py:77-96)."""
+    if p % 2 != 0:
+        raise ValueError("p must be even")
+    acc = np.zeros((len(x), len(w)))
+    coef = 1
+    for e in range(p + 1):
+        acc += (-1 if e % 2 == 1 else 1) * coef * np.dot(x ** (p - e), (w ** e).T)
+        coef = (coef * (p - e)) // (e + 1)
+    return acc
+
+
+def dist_norm_p(x, w, p=2):
+    """dispatch on the parity of p                    (distances.py:98-107)."""
+    return dist_norm_p_even(x, w, p) if p % 2 == 0 else dist_norm_p_generic(x, w, p)
+
+
+def dist_manhattan(x, w):
+    """numpy path of manhattan = generic p=1          (distances.py:137-158)."""
+    return dist_norm_p_generic(x, w, p=1)
+
+
+def dist_chebyshev(x, w):
+    """max_d |x_d - w_d|.  NOT in the reference (distances.py:162-170 has no
+    such entry); named by BASELINE.json's north_star.  No reference pin."""
+    out = np.empty((len(x), len(w)), dtype=np.result_type(x, w))
+    step = max(1, (1 << 24) // max(1, w.size))
+    for s in range(0, len(x), step):
+        out[s:s + step] = np.abs(x[s:s + step, None, :] - w[None, :, :]).max(axis=2)
+    return out
+
+
+def activation_distance(name, x, w_flat, w_sq=None, p=2):
+    """DistanceFunction.__call__ on a flattened codebook (distances.py:184-191);
+    w_sq is only forwarded for the two cacheable kinds (distances.py:179-182)."""
+    if name == "euclidean":
+        return dist_euclidean_part(x, w_flat, w_sq)
+    if name == "euclidean_no_opt":
+        return dist_euclidean_sq(x, w_flat, w_sq)
+    if name == "cosine":
+        return dist_cosine(x, w_flat, w_sq)
+    if name in ("manhattan", "manhattan_no_opt"):
+        return dist_manhattan(x, w_flat)
+    if name == "norm_p":
+        return dist_norm_p(x, w_flat, p)
+    if name == "norm_p_no_opt":
+        return dist_norm_p_generic(x, w_flat, p)
+    if name == "chebyshev":
+        return dist_chebyshev(x, w_flat)
+    raise ValueError("%s not supported." % name)
+
+
+# --------------------------------------------------------------------------
+# N: neighbourhoods, (bi, bj) int vectors -> (n, gx, gy)   (neighborhoods.py)
+# --------------------------------------------------------------------------
+def hex_coords(gx: int, gy: int, topology: str):
+    """Real-valued neuron coordinates, shape (gy, gx)  (xpysom.py:201-206).
+
+    hexagonal: every second ROW counted from the last one is shifted by -0.5,
+    i.e. neuron (i, j) sits at (i - 0.5*[(gy-1-j) even], j); yy is not scaled.
+    """
+    xx, yy = np.meshgrid(np.arange(gx), np.arange(gy))
+    xx = xx.astype(float)
+    yy = yy.astype(float)
+    if topology == "hexagonal":
+        xx[::-2] -= 0.5
+    return xx, yy
+
+
+def _window(n, c, sigma):
+    """strict |n - c| < sigma window                   (neighborhoods.py:30,108)."""
+    return np.logical_and(n > c - sigma, n < c + sigma)
+
+
+def neigh_gaussian_rect(gx, gy, std_coeff, compact, bi, bj, sigma):
+    """outer product of two 1-D Gaussians              (neighborhoods.py:14-33)."""
+    d = 2 * std_coeff ** 2 * sigma ** 2
+    nx, ny = np.arange(gx)[None, :], np.arange(gy)[None, :]
+    cx, cy = bi[:, None], bj[:, None]
+    ax = np.exp(-np.power(nx - cx, 2, dtype=np.float32) / d)
+    ay = np.exp(-np.power(ny - cy, 2, dtype=np.float32) / d)
+    if compact:
+        ax *= _window(nx, cx, sigma)
+        ay *= _window(ny, cy, sigma)
+    return ax[:, :, None] * ay[:, None, :]
+
+
+def neigh_gaussian_generic(xx, yy, std_coeff, compact, bi, bj, sigma):
+    """same on real coordinates, result transposed to (n,gx,gy) (neighborhoods.py:35-55)."""
+    d = 2 * std_coeff ** 2 * sigma ** 2
+    nx, ny = xx[None, :, :], yy[None, :, :]
+    cx = xx.T[(bi, bj)][:, None, None]
+    cy = yy.T[(bi, bj)][:, None, None]
+    ax = np.exp(-np.power(nx - cx, 2, dtype=np.float32) / d)
+    ay = np.exp(-np.power(ny - cy, 2, dtype=np.float32) / d)
+    if compact:
+        ax *= _window(nx, cx, sigma)
+        ay *= _window(ny, cy, sigma)
+    return (ax * ay).transpose((0, 2, 1))
+
+
+def neigh_mexican_rect(gx, gy, std_coeff, compact, bi, bj, sigma):
+    """exp(-p/d)(1-2p/d), p = dx^2+dy^2               (neighborhoods.py:57-74).
+
+    compact support multiplies px by BOTH windows and never touches py
+    (neighborhoods.py:69-71); the second product broadcasts an (n,gx) array with
+    an (n,gy) mask, so it raises unless gx == gy.  Kept as is."""
+    d = 2 * std_coeff ** 2 * sigma ** 2
+    nx, ny = np.arange(gx)[None, :], np.arange(gy)[None, :]
+    cx, cy = bi[:, None], bj[:, None]
+    px = np.power(nx - cx, 2, dtype=np.float32)
+    py = np.power(ny - cy, 2, dtype=np.float32)
+    if compact:
+        px *= _window(nx, cx, sigma)
+        px *= _window(ny, cy, sigma)
+    p = px[:, :, None] + py[:, None, :]
+    return np.exp(-p / d) * (1 - 2 / d * p)
+
+
+def neigh_mexican_generic(xx, yy, std_coeff, compact, bi, bj, sigma):
+    """real-coordinate mexican hat                    (neighborhoods.py:76-97)."""
+    d = 2 * std_coeff ** 2 * sigma ** 2
+    nx, ny = xx[None, :, :], yy[None, :, :]
+    cx = xx.T[(bi, bj)][:, None, None]
+    cy = yy.T[(bi, bj)][:, None, None]
+    px = np.power(nx - cx, 2, dtype=np.float32)
+    py = np.power(ny - cy, 2, dtype=np.float32)
+    if compact:
+        px *= _window(nx, cx, sigma)
+        px *= _window(ny, cy, sigma)
+    p = px + py
+    return (np.exp(-p / d) * (1 - 2 / d * p)).transpose((0, 2, 1))
+
+
+def neigh_bubble(gx, gy, bi, bj, sigma):
+    """strict box indicator, fp32, integer coords for both topologies
+    (neighborhoods.py:99-112, xpysom.py:266-267,277-278)."""
+    nx, ny = np.arange(gx)[None, :], np.arange(gy)[None, :]
+    ax = _window(nx, bi[:, None], sigma)
+    ay = _window(ny, bj[:, None], sigma)
+    return (ax[:, :, None] * ay[:, None, :]).astype(np.float32)
+
+
+def neigh_triangle(gx, gy, compact, bi, bj, sigma):
+    """outer product of two clipped tents             (neighborhoods.py:114-130)."""
+    nx, ny = np.arange(gx)[None, :], np.arange(gy)[None, :]
+    cx, cy = bi[:, None], bj[:, None]
+    tx = (-np.abs(cx - nx)) + sigma
+    ty = (-np.abs(cy - ny)) + sigma
+    tx[tx < 0] = 0.0
+    ty[ty < 0] = 0.0
+    if compact:
+        tx *= _window(nx, cx, sigma)
+        ty *= _window(ny, cy, sigma)
+    return tx[:, :, None] * ty[:, None, :]
+
+
+# --------------------------------------------------------------------------
+# the model state the hot path needs
+# --------------------------------------------------------------------------
+@dataclass
+class SomSpec:
+    """Constructor arguments of XPySom that reach the hot path (xpysom.py:73-82)."""
+    gx: int
+    gy: int
+    dim: int
+    sigma: float = 0
+    sigmaN: float = 1
+    learning_rate: float = 0.5
+    learning_rateN: float = 0.01
+    decay_function: str = "exponential"
+    neighborhood_function: str = "gaussian"
+    std_coeff: float = 0.5
+    topology: str = "rectangular"
+    activation_distance: str = "euclidean"
+    p: float = 2
+    compact_support: bool = False
+    n_parallel: int = 4000
+    random_seed: Optional[int] = None
+    _coords: tuple = field(default=None, repr=False)
+
+    def __post_init__(self):
+        if self.topology not in TOPOLOGIES:
+            raise ValueError("%s not supported only hexagonal and rectangular available" % self.topology)
+        if self.decay_function not in DECAYS:
+            raise ValueError("%s not supported." % self.decay_function)
+        if self.neighborhood_function not in NEIGHBORHOODS or (
+                self.topology == "hexagonal" and self.neighborhood_function == "triangle"):
+            raise ValueError("%s not supported." % self.neighborhood_function)
+        if self.sigma == 0:                      # xpysom.py:178-181
+            self.sigma = min(self.gx, self.gy) / 2
+        self._coords = hex_coords(self.gx, self.gy, self.topology)
+
+    @property
+    def K(self):
+        return self.gx * self.gy
+
+
+def init_weights(spec: SomSpec):
+    """RandomState(seed).rand(gx,gy,D)*2-1, L2-normalised per neuron, fp64
+    (xpysom.py:167,189-190)."""
+    rng = np.random.RandomState(spec.random_seed)
+    w = rng.rand(spec.gx, spec.gy, spec.dim) * 2 - 1
+    w /= np.linalg.norm(w, axis=-1, keepdims=True)
+    return w
+
+
+def neighborhood(spec: SomSpec, bi, bj, sigma):
+    """function table of xpysom.py:255-283."""
+    f = spec.neighborhood_function
+    if f == "bubble":
+        return neigh_bubble(spec.gx, spec.gy, bi, bj, sigma)
+    if spec.topology == "rectangular":
+        if f == "gaussian":
+            return neigh_gaussian_rect(spec.gx, spec.gy, spec.std_coeff, spec.compact_support, bi, bj, sigma)
+        if f == "mexican_hat":
+            return neigh_mexican_rect(spec.gx, spec.gy, spec.std_coeff, spec.compact_support, bi, bj, sigma)
+        return neigh_triangle(spec.gx, spec.gy, spec.compact_support, bi, bj, sigma)
+    xx, yy = spec._coords
+    if f == "gaussian":
+        return neigh_gaussian_generic(xx, yy, spec.std_coeff, spec.compact_support, bi, bj, sigma)
+    return neigh_mexican_generic(xx, yy, spec.std_coeff, spec.compact_support, bi, bj, sigma)
+
+
+def bmu_flat(spec: SomSpec, x, w, w_sq=None):
+    """W: distance matrix -> first-minimum argmin     (xpysom.py:410-417)."""
+    d = activation_distance(spec.activation_distance, x, w.reshape(-1, w.shape[2]), w_sq, spec.p)
+    return d.argmin(axis=1)
+
+
+def update_block(spec: SomSpec, x, w, eta, sig, w_sq=None):
+    """U: one block of samples -> (num (gx,gy,D), den (gx,gy,1))  (xpysom.py:420-443)."""
+    flat = bmu_flat(spec, x, w, w_sq)
+    bi, bj = np.unravel_index(flat, (spec.gx, spec.gy))
+    g = neighborhood(spec, bi, bj, sig) * eta
+    den = np.sum(g, axis=0)[:, :, None]
+    num = np.dot(g.reshape(g.shape[0], -1).T, x).reshape(w.shape)
+    return num, den
+
+
+def merge(w, num, den):
+    """M: W <- where(den != 0, num/den, W)            (xpysom.py:446-455)."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return np.where(den != 0, num / den, w)
+
+
+def epoch(spec: SomSpec, data32, w32, t: int, T: int, return_bmu=False):
+    """T: one pass over all samples                    (xpysom.py:515-577).
+
+    fp32 accumulators, |w|^2 cached for euclidean/cosine (xpysom.py:529-539),
+    chunks of n_parallel rows (xpysom.py:560-569)."""
+    num = np.zeros(w32.shape, dtype=np.float32)
+    den = np.zeros((spec.gx, spec.gy, 1), dtype=np.float32)
+    w_sq = None
+    if spec.activation_distance in ("euclidean", "cosine"):
+        w_sq = np.power(w32.reshape(-1, w32.shape[2]), 2).sum(axis=1, keepdims=True)
+    eta = decay_value(spec.decay_function, spec.learning_rate, spec.learning_rateN, t, T)
+    sig = decay_value(spec.decay_function, spec.sigma, spec.sigmaN, t, T)
+    bmus = []
+    for s in range(0, len(data32), spec.n_parallel):
+        blk = data32[s:s + spec.n_parallel]
+        if return_bmu:
+            bmus.append(bmu_flat(spec, blk, w32, w_sq))
+        a, b = update_block(spec, blk, w32, eta, sig, w_sq)
+        num += a
+        den += b
+    w_new = merge(w32, num, den)
+    if return_bmu:
+        return w_new, np.concatenate(bmus)
+    return w_new
+
+
+def train(spec: SomSpec, data, w, num_epochs, iter_beg=0, iter_end=None):
+    """xpysom.py:458-594 without dask: returns the fp32 codebook."""
+    if iter_end is None:
+        iter_end = num_epochs
+    w32 = np.asarray(w, dtype=np.float32)
+    d32 = np.asarray(data, dtype=np.float32)
+    for t in range(iter_beg, iter_end):
+        w32 = epoch(spec, d32, w32, t, num_epochs)
+    return w32
+
+
+def block_partials(spec: SomSpec, data32, w32, t, T, n_blocks):
+    """G: the Dask graph of xpysom.py:545-558 — one `_update` per row block
+    (whole block at once, no n_parallel sub-chunking), partials summed with
+    Python's sum, merged on the client."""
+    eta = decay_value(spec.decay_function, spec.learning_rate, spec.learning_rateN, t, T)
+    sig = decay_value(spec.decay_function, spec.sigma, spec.sigmaN, t, T)
+    w_sq = None
+    if spec.activation_distance in ("euclidean", "cosine"):
+        w_sq = np.power(w32.reshape(-1, w32.shape[2]), 2).sum(axis=1, keepdims=True)
+    rows = -(-len(data32) // n_blocks)
+    parts = [update_block(spec, data32[s:s + rows], w32, eta, sig, w_sq)
+             for s in range(0, len(data32), rows)]
+    num = sum(p[0] for p in parts)
+    den = sum(p[1] for p in parts)
+    return merge(w32, num, den)
+
+
+# --------------------------------------------------------------------------
+# inference API the path's callers use right after train   
+# --------------------------------------------------------------------------
+def winner(spec: SomSpec, x, w):
+    """xpysom.py:370-408: list of (i, j) for 2-D input (weights NOT cast)."""
+    x = np.array(x)
+    w = np.array(w)
+    out = []
+    for s in range(0, len(x), spec.n_parallel):
+        flat = bmu_flat(spec, x[s:s + spec.n_parallel], w)
+        out.append(np.vstack(np.unravel_index(flat, (spec.gx, spec.gy))))
+    win = np.hstack(out)
+    return list(map(tuple, win.T))
+
+
+def quantization(spec: SomSpec, data, w):
+    """xpysom.py:620-645: always Euclidean (sqrt form), whatever the activation distance."""
+    data = np.array(data)
+    w = np.array(w)
+    wf = w.reshape(-1, w.shape[2])
+    q = []
+    for s in range(0, len(data), spec.n_parallel):
+        idx = np.argmin(dist_euclidean(data[s:s + spec.n_parallel], wf), axis=1)
+        q.append(wf[idx])
+    return np.vstack(q)
+
+
+def quantization_error(spec: SomSpec, data, w):
+    """xpysom.py:673-707 (local branch): mean ||x - q(x)|| with x cast to fp32."""
+    d = np.array(data, dtype=np.float32)
+    d -= quantization(spec, d, np.array(w))
+    return np.linalg.norm(d, axis=1).mean().item()
+
+
+def distance_map(spec: SomSpec, w):
+    """U-matrix: sum of Euclidean distances to the (8 | 6) grid neighbours,
+    divided by its maximum                          (xpysom.py:788-817)."""
+    w = np.asarray(w)
+    gx, gy = w.shape[:2]
+    um = np.zeros((gx, gy, 8))
+    if spec.topology == "hexagonal":
+        ii = [[1, 1, 1, 0, -1, 0], [0, 1, 0, -1, -1, -1]]
+        jj = [[1, 0, -1, -1, 0, 1], [1, 0, -1, -1, 0, 1]]
+    else:
+        ii = [[0, -1, -1, -1, 0, 1, 1, 1]] * 2
+        jj = [[-1, -1, 0, 1, 1, 1, 0, -1]] * 2
+    for x in range(gx):
+        for y in range(gy):
+            e = y % 2 == 0
+            for k, (i, j) in enumerate(zip(ii[e], jj[e])):
+                if 0 <= x + i < gx and 0 <= y + j < gy:
+                    um[x, y, k] = np.linalg.norm(w[x, y] - w[x + i, y + j])
+    um = um.sum(axis=2)
+    return um / um.max()
+
+
+def topographic_error(spec: SomSpec, data, w):
+    """xpysom.py:709-746."""
+    d = np.array(data, dtype=np.float32)
+    w = np.array(w)
+    dist = dist_euclidean(d, w.reshape(-1, w.shape[2]))
+    b2 = np.argsort(dist, axis=1)[:, :2]
+    bx, by = np.unravel_index(b2, (spec.gx, spec.gy))
+    if spec.topology == "rectangular":
+        return ((np.abs(np.diff(bx)) > 1) | (np.abs(np.diff(by)) > 1)).mean().item()
+    xx, yy = spec._coords
+    # NOTE xpysom.py:742-743 indexes the (gy, gx) meshgrids with (i, j) directly.
+    ex, ey = xx[bx, by], yy[bx, by]
+    dxdy = np.hstack([np.diff(ex), np.diff(ey)])
+    return (np.linalg.norm(dxdy, axis=1) > 1.5).mean().item()
+
+
+# --------------------------------------------------------------------------
+# helpers for the parity criterion of BASELINE.json's north_star
+# --------------------------------------------------------------------------
+def top2_gap(spec: SomSpec, x, w, chunk=4096):
+    """Per row: (bmu, d1, d2 - d1, scale) on the reference's own fp32 distances.
+
+    `scale` is what the stated epsilon multiplies: |x|^2 + |d1| for the
+    Euclidean partial distance (whose |x|^2 term was dropped), 1 for cosine
+    (values live in [0,2]) and |d1| + tiny for the L1/Linf/Lp sums."""
+    wf = w.reshape(-1, w.shape[2])
+    w_sq = row_sq(wf) if spec.activation_distance in ("euclidean", "cosine") else None
+    bm, d1s, gaps, scales = [], [], [], []
+    for s in range(0, len(x), chunk):
+        xb = x[s:s + chunk]
+        d = activation_distance(spec.activation_distance, xb, wf, w_sq, spec.p)
+        b = d.argmin(axis=1)
+        r = np.arange(len(xb))
+        d1 = d[r, b].astype(np.float64)
+        d[r, b] = np.inf
+        d2 = d.min(axis=1).astype(np.float64)
+        if spec.activation_distance == "euclidean":
+            sc = (xb.astype(np.float64) ** 2).sum(axis=1) + np.abs(d1)
+        elif spec.activation_distance == "cosine":
+            sc = np.ones(len(xb))
+        else:
+            sc = np.abs(d1) + 1e-30
+        bm.append(b); d1s.append(d1); gaps.append(d2 - d1); scales.append(sc)
+    return (np.concatenate(bm), np.concatenate(d1s), np.concatenate(gaps), np.concatenate(scales))
+
+
+def sums_by_bmu(bmu, x, K):
+    """S[b] = sum of samples whose BMU is b, c[b] = their count (fp64).  Used to
+    check the identity num = H^T S, den = H^T c that the CUDA path relies on."""
+    S = np.zeros((K, x.shape[1]))
+    np.add.at(S, bmu, x.astype(np.float64))
+    c = np.bincount(bmu, minlength=K).astype(np.float64)
+    return S, c
+
+
+def neighborhood_table(spec: SomSpec, sigma):
+    """H[b, k] = h(bmu=b, neuron=k) for every pair, (K, K)."""
+    bi, bj = np.unravel_index(np.arange(spec.K), (spec.gx, spec.gy))
+    return neighborhood(spec, bi, bj, sigma).reshape(spec.K, spec.K)
