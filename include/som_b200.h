@@ -1,0 +1,168 @@
+/*
+ * som_b200.h — C ABI of the B200-native batch-SOM epoch (libsom_b200.so).
+ *
+ * Drop-in boundary for ONE hot path of XPySom-Dask: the training epoch
+ *   XPySom.train -> XPySom._update -> DistanceFunction + argmin + neighborhood
+ *   + dot -> XPySom._merge_updates       (reference xpysom_dask/xpysom.py:420-577)
+ * and the inference calls that reuse its BMU search (winner / quantization /
+ * quantization_error / distance_map, xpysom.py:370-408, 620-707, 788-817).
+ *
+ * Conventions
+ *   - plain C, no torch / C++ types; every function returns 0 on success, a
+ *     positive cudaError_t value on a CUDA failure, or a negative SOM_E_* code
+ *     for a rejected argument.  No exceptions cross the boundary.
+ *     som_b200_last_error() returns a thread-local message for the last failure.
+ *   - "dev" pointers are device pointers owned by the caller (torch tensors in
+ *     the Python host class); "host" pointers are ordinary host memory.
+ *   - every device entry point takes the CUDA stream to enqueue on
+ *     (`void*` == cudaStream_t; NULL is the legacy default stream) and does not
+ *     synchronise.
+ *   - codebook W is (K, D) fp32 row-major, K = gx*gy, neuron (i,j) at flat
+ *     index k = i*gy + j (C-order reshape of the reference's (x, y, D) tensor,
+ *     distances.py:185, xpysom.py:240).  Samples X are (n, D) fp32 with a row
+ *     stride of ldx floats.
+ *   - accumulators: S (K, D) = per-BMU sample sums, c (K) = per-BMU counts.
+ *     The reference's numerator/denominator (xpysom.py:436-441) are
+ *     num = eta * H^T S, den = eta * H^T c with H[b,k] = h(bmu=b, neuron=k);
+ *     the identity is checked in tests/test_oracle_golden.py.
+ */
+#ifndef SOM_B200_H
+#define SOM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOM_B200_ABI_VERSION 1
+
+/* activation distances: DistanceFunction table, distances.py:162-170 */
+enum som_dist {
+    SOM_DIST_EUCLIDEAN = 0, /* 'euclidean'  -2 x.w + |w|^2   distances.py:11-23 */
+    SOM_DIST_COSINE    = 1, /* 'cosine'     1 - x.w/(|x||w|) distances.py:45-59 */
+    SOM_DIST_MANHATTAN = 2, /* 'manhattan'  sum|x-w|         distances.py:109-158 */
+    SOM_DIST_CHEBYSHEV = 3, /* max|x-w| — extension named by north_star, not in the reference */
+    SOM_DIST_NORM_P    = 4  /* 'norm_p'     sum|x-w|^p       distances.py:61-107 */
+};
+
+/* neighbourhood functions: xpysom.py:255-283, neighborhoods.py:14-130 */
+enum som_neigh {
+    SOM_NEIGH_GAUSSIAN    = 0,
+    SOM_NEIGH_MEXICAN_HAT = 1,
+    SOM_NEIGH_BUBBLE      = 2,
+    SOM_NEIGH_TRIANGLE    = 3  /* rectangular only, xpysom.py:268-279 */
+};
+
+enum som_topology { SOM_TOPO_RECTANGULAR = 0, SOM_TOPO_HEXAGONAL = 1 }; /* xpysom.py:196-206 */
+
+/* which BMU kernel to run */
+enum som_algo {
+    SOM_ALGO_AUTO      = 0, /* tensor-core kernel when the shape allows, else SIMT */
+    SOM_ALGO_SIMT_FP32 = 1, /* shared-memory tiled SIMT, plain fp32 FMA chains */
+    SOM_ALGO_TC_3XTF32 = 2  /* tcgen05 TF32 MMA, 3-term split (fp32-accurate), TMA staged */
+};
+
+/* negative return codes */
+#define SOM_E_BADARG   (-1)  /* NULL pointer, non-positive size, unknown enum */
+#define SOM_E_SHAPE    (-2)  /* shape not supported by the requested algo */
+#define SOM_E_WORKSPACE (-3) /* workspace too small */
+#define SOM_E_NODEVICE (-4)  /* no CUDA device / wrong architecture */
+
+int         som_b200_abi_version(void);
+const char *som_b200_last_error(void);
+
+/* Device properties the host class needs (SM count, cc major*10+minor). */
+int som_b200_device_info(int *sm_count, int *cc, size_t *smem_per_block_optin);
+
+/* Bytes of scratch som_b200_prepare_codebook / _bmu / _epoch_accumulate need
+ * for a codebook of K neurons x D features (prepared operand copies, |w|^2). */
+size_t som_b200_workspace_bytes(int k, int d);
+
+/* Q: per-epoch codebook preparation.  Replaces the |w|^2 cache of
+ * xpysom.py:529-539 and, for the tensor-core kernel, writes the split
+ * (hi/lo TF32) operand copies of W into the workspace.  Must be called after
+ * every change of W and before _bmu / _epoch_accumulate with the same ws. */
+int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, float p,
+                              void *ws_dev, size_t ws_bytes, void *stream);
+
+/* W: BMU search.  Replaces XPySom._winner (xpysom.py:410-417): activation
+ * distance + first-minimum argmin over the K neurons, fused, the (n,K) matrix
+ * is never materialised.  bmu_dev (n) receives flat indices.  best_dev may be
+ * NULL; otherwise it receives the kernel's winning score (distance up to the
+ * row-constant terms the argmin does not need). */
+int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx,
+                 const float *w_dev, int k, int dist_kind, float p, int algo,
+                 int32_t *bmu_dev, float *best_dev,
+                 void *ws_dev, size_t ws_bytes, void *stream);
+
+/* U (first half): S[bmu[r], :] += X[r, :], c[bmu[r]] += 1 for the n rows.
+ * Replaces the sample side of g^T X and sum(g) in XPySom._update
+ * (xpysom.py:434-441).  S and c are accumulated into (zero them per epoch). */
+int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
+                        const int32_t *bmu_dev, int k,
+                        float *s_dev, float *c_dev, void *stream);
+
+/* W+U fused: som_b200_bmu followed by som_b200_accumulate on one shard of rows
+ * — the unit of distributed work (`_update` on one Dask block, xpysom.py:551).
+ * bmu_dev may be NULL if the caller does not want the indices; then
+ * ws must also hold n int32 (see som_b200_shard_workspace_bytes). */
+int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
+                              const float *w_dev, int k, int dist_kind, float p, int algo,
+                              float *s_dev, float *c_dev, int32_t *bmu_dev,
+                              void *ws_dev, size_t ws_bytes, void *stream);
+size_t som_b200_shard_workspace_bytes(int64_t n, int k, int d);
+
+/* U (second half) + N: num = eta * H^T S, den = eta * H^T c with the
+ * neighbourhood evaluated on the fly for every (bmu, neuron) pair.  Replaces
+ * neighborhoods.py:14-130 and xpysom.py:434-441.  num (K,D) and den (K) are
+ * overwritten.  tables_dev is scratch of som_b200_neigh_table_floats(gx,gy)
+ * floats.  Returns SOM_E_SHAPE for the combinations the reference rejects
+ * (triangle on a hexagonal map; mexican_hat + compact_support on a rectangular
+ * map with gx != gy, whose broadcast raises in neighborhoods.py:69-71). */
+int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy, int d,
+                         int topology, int neigh_kind, double sigma, double eta,
+                         double std_coeff, int compact_support,
+                         float *num_dev, float *den_dev, float *tables_dev, void *stream);
+size_t som_b200_neigh_table_floats(int gx, int gy);
+
+/* M: W <- den != 0 ? num/den : W   (XPySom._merge_updates, xpysom.py:446-455). */
+int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev,
+                   int k, int d, void *stream);
+
+/* quantization / quantization_error support (xpysom.py:620-707): for each row,
+ * q_dev (n,D) <- W[bmu[r]] if q_dev != NULL, and err_dev (n) <- ||x_r - W[bmu[r]]||_2
+ * if err_dev != NULL. */
+int som_b200_quantize(const float *x_dev, int64_t n, int d, int64_t ldx,
+                      const float *w_dev, int k, const int32_t *bmu_dev,
+                      float *q_dev, float *err_dev, void *stream);
+
+/* distance_map (xpysom.py:788-817): um (gx*gy) <- sum of Euclidean distances
+ * to the 8 (rectangular) or 6 (hexagonal) grid neighbours, NOT normalised;
+ * the host divides by the maximum. */
+int som_b200_distance_map(const float *w_dev, int gx, int gy, int d, int topology,
+                          float *um_dev, void *stream);
+
+/* Whole-job entry with HOST buffers: what a maintainer of the reference would
+ * bind from XPySom.train (xpysom.py:458-594) with numpy arrays — uploads the
+ * samples once, runs epochs [iter_beg, iter_end) with the given per-epoch
+ * sigma / learning-rate schedule (length iter_end - iter_beg, computed by the
+ * reference's own decays.py on the host), downloads the codebook.  Single GPU
+ * (the current device).  Synchronous. */
+typedef struct som_b200_train_config {
+    int    gx, gy, d;
+    int    topology, neigh_kind, dist_kind, algo, compact_support;
+    float  p;
+    double std_coeff;
+} som_b200_train_config;
+
+int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx,
+                        float *w_host, const som_b200_train_config *cfg,
+                        const double *sigma_per_epoch, const double *eta_per_epoch,
+                        int n_epochs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOM_B200_H */

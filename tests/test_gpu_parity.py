@@ -1,0 +1,304 @@
+"""Parity of the CUDA path (through the C ABI) against the oracle and the golden fixtures.
+
+BMU indices: bit-exact wherever the reference's own top-2 gap exceeds EPS*scale
+(tests/som_testutil.py); the near-tie rate is printed.  Codebooks: teacher-forced, one
+epoch from the same W_t, max-abs error / max-abs value <= 1e-4 (fp32).
+"""
+import ctypes
+
+import numpy as np
+import pytest
+
+from oracle import som_oracle as so
+import som_testutil as U
+
+torch = pytest.importorskip("torch")
+pytestmark = pytest.mark.gpu
+
+CODEBOOK_TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from xpysom_dask_b200.engine import CudaEngine
+    return CudaEngine("cuda:0")
+
+
+def _gpu_bmu(eng, x, w, dist, p, algo):
+    from xpysom_dask_b200 import _lib
+    xd = torch.from_numpy(x).cuda()
+    wd = torch.from_numpy(np.ascontiguousarray(w.reshape(-1, w.shape[-1]), dtype=np.float32)).cuda()
+    ws = eng.workspace(0, wd.shape[0], wd.shape[1])
+    eng.prepare_codebook(wd, _lib.DIST[dist], p, ws)
+    bmu = eng.bmu(xd, wd, _lib.DIST[dist], p, _lib.ALGO[algo], ws)
+    torch.cuda.synchronize()
+    return bmu.cpu().numpy()
+
+
+BMU_SHAPES = [
+    # n, d, gx, gy
+    (150, 4, 7, 7),          # Iris shape (config 1)
+    (3000, 16, 8, 8),
+    (5000, 64, 32, 32),      # config-2 map
+    (2500, 100, 20, 15),     # K, D not multiples of the tile sizes
+    (1000, 784, 25, 20),     # config-4 feature count
+    (4097, 128, 50, 50),     # config-5 map, ragged n
+    (1, 16, 5, 5),           # single sample
+]
+
+
+@pytest.mark.parametrize("n,d,gx,gy", BMU_SHAPES)
+@pytest.mark.parametrize("dist", ["euclidean", "cosine"])
+@pytest.mark.parametrize("algo", ["simt", "tc"])
+def test_bmu_contraction_distances(eng, n, d, gx, gy, dist, algo):
+    if algo == "tc" and d < 4:
+        pytest.skip("tensor-core kernel needs d >= 4")
+    x = U.blobs(n, d, seed=n + d)
+    spec = so.SomSpec(gx=gx, gy=gy, dim=d, activation_distance=dist, random_seed=d)
+    w = so.init_weights(spec).astype(np.float32) * 0.5 + 0.5 * U.uniform(gx * gy, d, 3).reshape(gx, gy, d)
+    bmu = _gpu_bmu(eng, x, w, dist, 2.0, algo)
+    r = U.bmu_parity(spec, x, w, bmu)
+    print("\n[bmu %s/%s n=%d d=%d K=%d] near-tie rate %.2e, raw mismatch %.2e, worst mismatching rel gap %.2e"
+          % (dist, algo, n, d, gx * gy, r["near_tie_rate"], r["mismatch_rate"], r["worst_rel_gap"]))
+    assert r["bad"] == 0, r
+
+
+@pytest.mark.parametrize("n,d,gx,gy", [(2000, 7, 8, 8), (1500, 33, 12, 10), (3000, 64, 16, 16)])
+@pytest.mark.parametrize("dist,p", [("manhattan", 1.0), ("chebyshev", 0.0), ("norm_p", 3.0), ("norm_p", 2.0),
+                                    ("norm_p", 4.0), ("norm_p", 2.5), ("euclidean", 2.0), ("cosine", 2.0)])
+def test_bmu_simt_all_distances(eng, n, d, gx, gy, dist, p):
+    x = U.blobs(n, d, seed=11 * n + d)
+    spec = so.SomSpec(gx=gx, gy=gy, dim=d, activation_distance=dist, p=p, random_seed=1)
+    w = U.uniform(gx * gy, d, 5).reshape(gx, gy, d)
+    if dist == "norm_p" and p % 2 == 0:
+        # the reference's even-p path is a binomial expansion with cancellation
+        # (distances.py:77-96); compare against the direct definition instead
+        spec_direct = so.SomSpec(gx=gx, gy=gy, dim=d, activation_distance="norm_p_no_opt", p=p, random_seed=1)
+        spec_direct.activation_distance = "norm_p_no_opt"
+        ref_spec = spec_direct
+    else:
+        ref_spec = spec
+    bmu = _gpu_bmu(eng, x, w, dist, p, "simt")
+    r = U.bmu_parity(ref_spec, x.astype(np.float64) if dist == "norm_p" and p == 2.5 else x, w if p != 2.5 else w.astype(np.float64), bmu)
+    print("\n[bmu %s p=%g n=%d d=%d] near-tie %.2e mismatch %.2e" % (dist, p, n, d, r["near_tie_rate"], r["mismatch_rate"]))
+    assert r["bad"] == 0, r
+
+
+def test_unaligned_rows_fall_back_to_simt(eng):
+    """AUTO must pick the SIMT kernel when TMA cannot address X (row stride not a multiple of 16 B)."""
+    from xpysom_dask_b200 import _lib
+    x = U.blobs(1000, 30, seed=1)
+    spec = so.SomSpec(gx=9, gy=9, dim=30, random_seed=2)
+    w = so.init_weights(spec).astype(np.float32)
+    bmu = _gpu_bmu(eng, x, w, "euclidean", 2.0, "auto")
+    assert U.bmu_parity(spec, x, w, bmu)["bad"] == 0
+    xd = torch.from_numpy(x).cuda()
+    wd = torch.from_numpy(w.reshape(81, 30)).cuda()
+    ws = eng.workspace(0, 81, 30)
+    eng.prepare_codebook(wd, 0, 2.0, ws)
+    with pytest.raises(_lib.SomB200Error):
+        eng.bmu(xd, wd, 0, 2.0, _lib.ALGO["tc"], ws)
+
+
+def test_accumulate_matches_oracle_sums(eng):
+    for n, d, K in [(5000, 16, 64), (3001, 30, 50), (20000, 64, 1024), (777, 5, 13000)]:
+        x = U.blobs(n, d, seed=n)
+        bmu = np.random.RandomState(n).randint(K, size=n).astype(np.int32)
+        S_ref, c_ref = so.sums_by_bmu(bmu, x, K)
+        xd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(bmu).cuda()
+        S, c = eng.zeros(K, d), eng.zeros(K)
+        from xpysom_dask_b200 import _lib
+        _lib.check(eng.lib.som_b200_accumulate(eng._p(xd), n, d, d, eng._p(bd), K, eng._p(S), eng._p(c), eng._stream()),
+                   "accumulate")
+        torch.cuda.synchronize()
+        np.testing.assert_array_equal(c.cpu().numpy(), c_ref)
+        np.testing.assert_allclose(S.cpu().numpy(), S_ref, rtol=2e-5, atol=1e-5)
+
+
+def _apply_neigh(eng, case, sigma, S, c, eta=0.37):
+    from xpysom_dask_b200 import _lib
+    gx, gy = case["gx"], case["gy"]
+    K, d = gx * gy, S.shape[1]
+    Sd, cd = torch.from_numpy(S).cuda(), torch.from_numpy(c).cuda()
+    num, den = eng.empty(K, d), eng.empty(K)
+    eng.neigh_apply(Sd, cd, gx, gy, d, _lib.TOPO[case["topology"]], _lib.NEIGH[case["fn"]], sigma, eta, 0.5,
+                    case["compact"], num, den, eng.neigh_tables(gx, gy))
+    torch.cuda.synchronize()
+    return num.cpu().numpy(), den.cpu().numpy()
+
+
+def test_neigh_apply_matches_reference_tables(eng):
+    """num = eta H^T S, den = eta H^T c with H taken from the reference's own neighbourhood
+    functions (golden tables for every BMU of 5x5, 9x6, 6x9, 7x7 maps, both topologies,
+    compact support on/off, Python-float and numpy-float sigma)."""
+    from xpysom_dask_b200 import _lib
+    g = U.load("neighborhoods.npz")
+    cases = U.load_json("neighborhoods.json")
+    rng = np.random.RandomState(0)
+    worst = 0.0
+    for case in cases:
+        K = case["gx"] * case["gy"]
+        S = rng.randn(K, 9).astype(np.float32)
+        c = rng.randint(1, 50, size=K).astype(np.float32)
+        if case["error"]:
+            with pytest.raises(_lib.SomB200Error):
+                _apply_neigh(eng, case, case["sigma"], S, c)
+            continue
+        H = g[case["key"]].reshape(K, K).astype(np.float64)
+        num, den = _apply_neigh(eng, case, case["sigma"], S, c)
+        num_ref, den_ref = 0.37 * H.T @ S.astype(np.float64), 0.37 * H.T @ c.astype(np.float64)
+        e1 = np.abs(num - num_ref).max() / max(np.abs(num_ref).max(), 1e-30)
+        e2 = np.abs(den - den_ref).max() / max(np.abs(den_ref).max(), 1e-30)
+        worst = max(worst, e1, e2)
+        assert e1 < 5e-6 and e2 < 5e-6, (case["key"], e1, e2)
+    print("\n[neigh_apply] %d reference tables, worst rel err %.2e" % (len(cases), worst))
+
+
+def test_neigh_apply_skips_empty_bmus(eng):
+    case = dict(gx=6, gy=5, topology="rectangular", fn="gaussian", compact=False)
+    S = np.zeros((30, 4), np.float32); c = np.zeros(30, np.float32)
+    S[7] = [1, 2, 3, 4]; c[7] = 2
+    num, den = _apply_neigh(eng, case, 1.3, S, c, eta=1.0)
+    spec = so.SomSpec(gx=6, gy=5, dim=4)
+    H = so.neighborhood_table(spec, 1.3)
+    np.testing.assert_allclose(num, H.T @ S, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(den, H.T @ c, rtol=1e-5, atol=1e-7)
+
+
+EPOCHS = U.load_json("epochs.json")
+
+
+@pytest.mark.parametrize("algo", ["simt", "tc", "auto"])
+@pytest.mark.parametrize("case", EPOCHS, ids=[c["name"] for c in EPOCHS])
+def test_epoch_teacher_forced_vs_reference(case, algo):
+    """W_t from the reference -> one epoch on the GPU -> compare with the reference's W_{t+1}."""
+    from xpysom_dask_b200 import XPySom
+    g = U.load("epochs.npz")
+    name = case["name"]
+    spec = U.spec_from_case(case)
+    dist = case["kwargs"].get("activation_distance", "euclidean")
+    if algo == "tc" and dist not in ("euclidean", "cosine"):
+        pytest.skip("tensor-core kernel: contraction distances only")
+    data = g[name + "_data"]
+    som = XPySom(case["gx"], case["gy"], case["D"], random_seed=case["seed"], algo=algo, **case["kwargs"])
+    np.testing.assert_array_equal(som._weights, g[name + "_w_init"])      # bit-compatible init (xpysom.py:189-190)
+    for t in case["steps"]:
+        w_in = g["%s_t%d_w_in" % (name, t)]
+        som._weights = w_in.copy()
+        bmu = som.predict(data)
+        r = U.bmu_parity(spec, data, w_in, bmu)
+        assert r["bad"] == 0, (name, t, r)
+        som.train(data, case["T"], iter_beg=t, iter_end=t + 1)
+        assert som._weights.dtype == np.float32 and som._weights.shape == w_in.shape
+        want = g["%s_t%d_w_out" % (name, t)]
+        if "mex" in name:
+            # the mexican hat's denominators cross zero: compare where |den| is not tiny
+            sig = so.decay_value(spec.decay_function, spec.sigma, spec.sigmaN, t, case["T"])
+            H = so.neighborhood_table(spec, float(sig)).astype(np.float64)
+            _, c = so.sums_by_bmu(g["%s_t%d_bmu" % (name, t)], data, spec.K)
+            den = H.T @ c
+            ok = (np.abs(den) > 1e-3 * np.abs(den).max()).reshape(case["gx"], case["gy"])
+            err = np.abs(som._weights - want)[ok].max() / np.abs(want).max()
+        else:
+            err = U.codebook_rel_err(som._weights, want)
+        assert err <= CODEBOOK_TOL, (name, t, err, r)
+
+
+def test_iris_config1_free_run():
+    """Config 1 of BASELINE.json end to end: 100 epochs free-running on Iris, compared through the
+    aggregate the reference's own tests use (quantization error), plus teacher-forced epochs."""
+    from xpysom_dask_b200 import XPySom
+    g = U.load("iris.npz")
+    data = g["data"]
+    som = XPySom(7, 7, 4, sigma=3, learning_rate=0.5, neighborhood_function="gaussian", random_seed=10)
+    np.testing.assert_array_equal(som._weights, g["w_init"])
+    for t in (0, 50, 99):
+        som._weights = g["t%d_w_in" % t].copy()
+        som.train(data, 100, iter_beg=t, iter_end=t + 1)
+        assert U.codebook_rel_err(som._weights, g["t%d_w_out" % t]) <= CODEBOOK_TOL
+    som = XPySom(7, 7, 4, sigma=3, learning_rate=0.5, neighborhood_function="gaussian", random_seed=10)
+    som.train(data, 100)
+    qe = som.quantization_error(data)
+    print("\n[iris] QE gpu %.6f  reference %.6f  codebook rel err after 100 free epochs %.2e"
+          % (qe, float(g["qe_final"]), U.codebook_rel_err(som._weights, g["w_final"])))
+    assert qe == pytest.approx(float(g["qe_final"]), rel=2e-2)
+    som._weights = g["w_final"].copy()
+    assert som.quantization_error(data) == pytest.approx(float(g["qe_final"]), rel=1e-5)
+    np.testing.assert_allclose(som.distance_map(), g["distance_map_final"], rtol=1e-5, atol=1e-6)
+    q = som.quantization(data)
+    assert (np.abs(q - g["quantization_final"]).max(axis=1) == 0).mean() > 0.98
+    win = np.array(som.winner(data))
+    assert (win == g["winner_final"]).all(axis=1).mean() > 0.98
+
+
+def test_api_known_answers_from_reference_tests():
+    """tests.py:22-33,49-96 of the reference, on the GPU backend."""
+    from xpysom_dask_b200 import XPySom
+    g = U.load("api.npz")
+    som = XPySom(5, 5, 1, std_coeff=1)
+    for i in range(5):
+        for j in range(5):
+            np.testing.assert_almost_equal(1.0, np.linalg.norm(som._weights[i, j]))
+    som._weights = g["fake_w"].copy()
+    assert som.winner(np.array([5.0])) == (2, 3)
+    assert som.winner(np.array([[5.0], [2.0]])) == [(2, 3), (1, 1)]
+    wm = som.win_map([[5.0], [2.0]])
+    assert wm[(2, 3)][0] == [5.0] and wm[(1, 1)][0] == [2.0]
+    lm = som.labels_map([[5.0], [2.0]], ['a', 'b'])
+    assert lm[(2, 3)]['a'] == 1 and lm[(1, 1)]['b'] == 1
+    with pytest.raises(ValueError):
+        som.labels_map([[5.0]], ['a', 'b'])
+    resp = som.activation_response([[5.0], [2.0]])
+    assert resp[2, 3] == 1 and resp[1, 1] == 1
+    assert som.quantization_error([[5], [2]]) == 0.0
+    assert som.quantization_error([[4], [1]]) == 1.0
+    q = som.quantization(np.array([[4], [2]]))
+    assert q[0] == 5.0 and q[1] == 2.0
+    som2 = XPySom(2, 2, 2, random_seed=1)
+    som2._weights = np.array([[[1., 0.], [0., 1.]], [[1., 0.], [0., 1.]]])
+    np.testing.assert_array_equal(som2.distance_map(), np.array([[1., 1.], [1., 1.]]))
+    s1 = XPySom(5, 5, 2, sigma=1.0, learning_rate=0.5, random_seed=1)
+    np.testing.assert_array_equal(s1._weights, g["seed1_w_init"])
+    q1 = s1.quantization_error(g["seed1_data"])
+    s1.train(g["seed1_data"], 10)
+    assert q1 > s1.quantization_error(g["seed1_data"])                      # tests.py:111-121
+    s1b = XPySom(5, 5, 2, sigma=1.0, learning_rate=0.5, random_seed=1)
+    s1b.train_random(g["seed1_data"], 10)
+    np.testing.assert_array_almost_equal(s1._weights, s1b._weights, decimal=4)   # tests.py:98-109
+    s1._weights = g["seed1_w_trained"].copy()
+    np.testing.assert_allclose(s1.distance_map(), g["seed1_distance_map"], rtol=1e-5)
+    hexs = XPySom(6, 5, 3, topology="hexagonal", random_seed=3)
+    np.testing.assert_array_equal(hexs._weights, g["hex_w"])
+    np.testing.assert_allclose(hexs.distance_map(), g["hex_distance_map"], rtol=1e-5)
+    assert hexs.quantization_error(g["hex_data"]) == pytest.approx(float(g["hex_qe"]), rel=1e-5)
+
+
+def test_train_host_c_abi_matches_class():
+    """The whole-job C entry with HOST buffers (what the reference would bind) == the Python class."""
+    from xpysom_dask_b200 import XPySom, _lib
+    from xpysom_dask_b200.decays import exponential_decay
+    lib = _lib.load()
+    n, d, gx, gy, T = 6000, 24, 10, 9, 4
+    data = U.blobs(n, d, seed=9)
+    som = XPySom(gx, gy, d, random_seed=5, algo="simt")
+    w0 = np.ascontiguousarray(som._weights, dtype=np.float32)
+    som.train(data, T)
+    cfg = _lib.TrainConfig(gx, gy, d, 0, 0, 0, _lib.ALGO["simt"], 0, 2.0, 0.5)
+    sig = (ctypes.c_double * T)(*[float(exponential_decay(min(gx, gy) / 2, 1, t, T)) for t in range(T)])
+    eta = (ctypes.c_double * T)(*[float(exponential_decay(0.5, 0.01, t, T)) for t in range(T)])
+    w = w0.copy()
+    rc = lib.som_b200_train_host(data.ctypes.data_as(ctypes.c_void_p), n, d, w.ctypes.data_as(ctypes.c_void_p),
+                                 ctypes.byref(cfg), sig, eta, T)
+    _lib.check(rc, "som_b200_train_host")
+    assert U.codebook_rel_err(w, som._weights) < 1e-4
+
+
+def test_errors_cross_the_abi_as_codes(eng):
+    from xpysom_dask_b200 import _lib
+    lib = eng.lib
+    assert lib.som_b200_merge(None, None, None, 4, 4, None) == -1
+    assert b"merge" in lib.som_b200_last_error()
+    w = eng.zeros(16, 8)
+    small = torch.empty(16, dtype=torch.uint8, device="cuda")
+    assert lib.som_b200_prepare_codebook(eng._p(w), 16, 8, 0, 2.0, eng._p(small), 16, None) == -3
+    assert lib.som_b200_prepare_codebook(eng._p(w), 16, 8, 99, 2.0, eng._p(small), 16, None) == -1

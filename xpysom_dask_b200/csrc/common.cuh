@@ -1,0 +1,82 @@
+// Shared helpers for the B200 batch-SOM kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stddef.h>
+#include <math.h>
+#include "../../include/som_b200.h"
+
+#if defined(__CUDA_ARCH__) && (__CUDA_ARCH__ < 1000)
+#error "libsom_b200 is written for sm_100a (B200) only"
+#endif
+
+namespace somb200 {
+
+constexpr int kKPad = 256;   // neuron padding of the prepared codebook (one UMMA N tile)
+constexpr int kDPad = 32;    // feature padding: one 128-byte swizzle row of fp32
+
+__host__ __device__ inline int64_t round_up(int64_t v, int64_t m) { return (v + m - 1) / m * m; }
+__host__ __device__ inline int64_t ceil_div(int64_t v, int64_t m) { return (v + m - 1) / m; }
+
+// Workspace carved out of the caller's buffer by prepare_codebook and read by the BMU kernels.
+struct WsLayout {
+    int    k_pad, d_pad;
+    size_t aux_off;   // k_pad floats: |w|^2 (euclidean) / 1/|w| (cosine, SIMT) / bias (tensor-core path)
+    size_t bias_off;  // k_pad floats: additive bias of the tensor-core epilogue (+inf on padding)
+    size_t whi_off;   // k_pad x d_pad floats: TF32 "hi" part of the scaled codebook
+    size_t wlo_off;   // k_pad x d_pad floats: TF32 "lo" part
+    size_t total;
+};
+
+__host__ inline WsLayout ws_layout(int k, int d) {
+    WsLayout L;
+    L.k_pad = (int)round_up(k, kKPad);
+    L.d_pad = (int)round_up(d, kDPad);
+    size_t off = 0;
+    L.aux_off = off;  off += round_up((size_t)L.k_pad * 4, 1024);
+    L.bias_off = off; off += round_up((size_t)L.k_pad * 4, 1024);
+    L.whi_off = off;  off += round_up((size_t)L.k_pad * L.d_pad * 4, 1024);
+    L.wlo_off = off;  off += round_up((size_t)L.k_pad * L.d_pad * 4, 1024);
+    L.total = off;
+    return L;
+}
+
+// ---- error plumbing (host) -------------------------------------------------
+void set_error(const char *fmt, ...);
+int  check_cuda(cudaError_t e, const char *what);
+
+#define SOM_CUDA(call)                                                 \
+    do {                                                               \
+        int _rc = ::somb200::check_cuda((call), #call);                \
+        if (_rc) return _rc;                                           \
+    } while (0)
+
+#define SOM_REQUIRE(cond, code, ...)                                   \
+    do {                                                               \
+        if (!(cond)) { ::somb200::set_error(__VA_ARGS__); return (code); } \
+    } while (0)
+
+// ---- device helpers -------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// 16-byte vector reduction into global memory (sm_90+): one L2 atomic transaction for 4 floats.
+__device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
+                 :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// lexicographic (value, index) minimum: the first minimum wins, as numpy's argmin.
+__device__ __forceinline__ void argmin_merge(float &v, int &i, float ov, int oi) {
+    if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
+}
+
+}  // namespace somb200

@@ -1,0 +1,115 @@
+// Small kernels around the epoch: codebook preparation (Q), merge (M),
+// quantization error and the U-matrix.
+#pragma once
+#include "common.cuh"
+
+namespace somb200 {
+
+// round-to-nearest TF32 (10 explicit mantissa bits); result is an fp32 bit pattern with 13 zero low bits
+__device__ __forceinline__ float tf32_rna(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+
+// Q: one warp per (padded) neuron.
+//   aux[k]  = |w_k|^2 (euclidean; xpysom.py:529-537)  or 1/|w_k| (cosine; 0 for a zero neuron,
+//             which makes its similarity 0 like nan_to_num in distances.py:57)
+//   bias[k] = additive term of the tensor-core epilogue: |w|^2 / 0, +inf on padding neurons
+//   whi/wlo = TF32 split of the SCALED codebook row (-2 w for euclidean: exact; -w/|w| for cosine),
+//             zero on padding, so that score = x . w' + bias is what both kernels minimise.
+__global__ void prepare_codebook_kernel(const float *__restrict__ W, int k, int d, int dist_kind,
+                                        int k_pad, int d_pad, float *__restrict__ aux, float *__restrict__ bias,
+                                        float *__restrict__ whi, float *__restrict__ wlo) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= k_pad) return;
+    const bool real = warp < k;
+    double s = 0.0;
+    if (real)
+        for (int c = lane; c < d; c += 32) { const double v = W[(int64_t)warp * d + c]; s += v * v; }
+    s = warp_sum(s);
+    const float wsq = (float)s;
+    float scale = 0.f, a = 0.f, b = INFINITY;
+    if (real) {
+        if (dist_kind == SOM_DIST_EUCLIDEAN) { scale = -2.f; a = wsq; b = wsq; }
+        else if (dist_kind == SOM_DIST_COSINE) {
+            const float rn = s > 0.0 ? (float)(1.0 / sqrt(s)) : 0.f;
+            scale = -rn; a = rn; b = 0.f;
+        } else { a = wsq; b = 0.f; }
+    }
+    if (lane == 0) { aux[warp] = a; bias[warp] = b; }
+    if (whi != nullptr) {
+        for (int c = lane; c < d_pad; c += 32) {
+            float v = 0.f;
+            if (real && c < d) v = W[(int64_t)warp * d + c] * scale;
+            const float hi = tf32_rna(v);
+            const float lo = tf32_rna(v - hi);
+            whi[(int64_t)warp * d_pad + c] = hi;
+            wlo[(int64_t)warp * d_pad + c] = lo;
+        }
+    }
+}
+
+// M: W <- den != 0 ? num/den : W      (xpysom.py:451-455)
+__global__ void merge_kernel(float *__restrict__ W, const float *__restrict__ num, const float *__restrict__ den,
+                             int k, int d) {
+    const int64_t tot = (int64_t)k * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const float dn = __ldg(den + e / d);
+        if (dn != 0.f) W[e] = __fdiv_rn(num[e], dn);
+    }
+}
+
+// quantization support: one warp per row.  q[r] = W[bmu[r]];  err[r] = ||x_r - W[bmu[r]]||_2
+// (xpysom.py:632-645, 699-705: the quantization error subtracts the code vector and takes the norm).
+__global__ void quantize_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx,
+                                const float *__restrict__ W, const int32_t *__restrict__ bmu,
+                                float *__restrict__ q, float *__restrict__ err) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        const int b = __ldg(bmu + r);
+        float s = 0.f;
+        for (int c = lane; c < d; c += 32) {
+            const float w = __ldg(W + (int64_t)b * d + c);
+            if (q) q[r * d + c] = w;
+            const float t = __ldg(X + r * ldx + c) - w;     // data -= quantization (fp32, :703)
+            s = fmaf(t, t, s);
+        }
+        s = warp_sum(s);
+        if (err && lane == 0) err[r] = sqrtf(s);
+    }
+}
+
+// distance_map (xpysom.py:788-817): one warp per neuron, sum of ||w - w_neighbour|| over the
+// 8 (rectangular) or 6 (hexagonal, offsets depend on the parity of j) grid neighbours.
+__global__ void distance_map_kernel(const float *__restrict__ W, int gx, int gy, int d, int topology,
+                                    float *__restrict__ um) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= gx * gy) return;
+    const int x = warp / gy, y = warp % gy;
+    const int rect_i[8] = {0, -1, -1, -1, 0, 1, 1, 1}, rect_j[8] = {-1, -1, 0, 1, 1, 1, 0, -1};
+    const int hex_i_even[6] = {0, 1, 0, -1, -1, -1}, hex_i_odd[6] = {1, 1, 1, 0, -1, 0};
+    const int hex_j[6] = {1, 0, -1, -1, 0, 1};
+    const int nn = topology == SOM_TOPO_HEXAGONAL ? 6 : 8;
+    double tot = 0.0;
+    for (int e = 0; e < nn; ++e) {
+        int di, dj;
+        if (topology == SOM_TOPO_HEXAGONAL) { di = (y % 2 == 0) ? hex_i_even[e] : hex_i_odd[e]; dj = hex_j[e]; }
+        else { di = rect_i[e]; dj = rect_j[e]; }
+        const int xi = x + di, yj = y + dj;
+        if (xi < 0 || xi >= gx || yj < 0 || yj >= gy) continue;
+        double s = 0.0;
+        for (int c = lane; c < d; c += 32) {
+            const double t = (double)W[(int64_t)warp * d + c] - (double)W[((int64_t)xi * gy + yj) * d + c];
+            s += t * t;
+        }
+        s = warp_sum(s);
+        tot += sqrt(s);
+    }
+    if (lane == 0) um[warp] = (float)tot;
+}
+
+}  // namespace somb200

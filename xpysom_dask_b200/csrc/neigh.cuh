@@ -1,0 +1,196 @@
+// K4: neighbourhood apply.  num = eta * H^T S,  den = eta * H^T c  with
+// H[b, k] = h(bmu = b, neuron = k) evaluated on the fly (never a K x K matrix
+// in memory: 400 MB at K = 10^4).
+//
+// Replaces neighborhoods.py:14-130 (gaussian / mexican_hat / bubble / triangle
+// on rectangular and hexagonal maps, with compact_support) together with the
+// neighbourhood side of XPySom._update (xpysom.py:434-441).
+//
+// Every neighbourhood of the reference is built from per-axis factors, so a
+// tiny fp64 pre-kernel tabulates them once per epoch:
+//   TX[q][bi][i], TY[bj][j]     q = hexagonal row-parity shift index
+// and the apply kernel turns two L1-resident table reads into h:
+//   product form  h = TX * TY                 (gaussian, bubble, triangle)
+//   mexican hat   h = exp(-p/d) (1 - 2p/d),  p = PX * mask + PY
+// Work: 2 K^2 D flops, SIMT fp32, tiled 64 neurons x 64 features per CTA.
+#pragma once
+#include "common.cuh"
+
+namespace somb200 {
+
+struct NeighParams {
+    int    gx, gy, d;
+    int    topology, kind, compact;
+    int    shifted;       // 1: real (hexagonal) coordinates are used -> 3 parity planes
+    int    mex_rect_quirk;  // rectangular mexican_hat + compact: the y-window is applied at index i
+    float  inv_d;         // 1/d,   d = 2 std_coeff^2 sigma^2
+    float  two_over_d;    // 2/d
+    float  eta;
+    const float *tx, *ty;     // product factors or squared offsets
+    const float *mx, *my;     // compact-support windows (mexican hat only)
+};
+
+// hexagonal rule of xpysom.py:201-206: rows (gy-1-j) even are shifted by -0.5
+__host__ __device__ inline int hex_shift(int j, int gy) { return ((gy - 1 - j) & 1) == 0 ? 1 : 0; }
+
+// one thread per table entry; all arithmetic in fp64, stored as fp32
+__global__ void neigh_tables_kernel(int gx, int gy, int kind, int compact, int shifted,
+                                    double sigma, double dd, float *tx, float *ty, float *mx, float *my) {
+    const int nxe = 3 * gx * gx, nye = gy * gy;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nxe + nye; e += gridDim.x * blockDim.x) {
+        const bool isx = e < nxe;
+        int q = 1, c, nn;
+        if (isx) { q = e / (gx * gx); c = (e / gx) % gx; nn = e % gx; }
+        else     { int f = e - nxe; c = f / gy; nn = f % gy; }
+        // offset along the axis in the coordinates the reference uses for this function
+        const double shift = (isx && shifted) ? 0.5 * (double)(q - 1) : 0.0;
+        const double delta = (double)(nn - c) + shift;       // n - c  (neighborhoods.py:26,48)
+        const bool   inwin = (delta > -sigma) && (delta < sigma);  // strict window (:30, :108)
+        const float  sq = (float)(delta * delta);            // power(..., 2, dtype=float32), exact for .5 grids
+        float val = 0.f, msk = 1.f;
+        if (kind == SOM_NEIGH_GAUSSIAN) {
+            double v = exp(-(double)sq / dd);
+            if (compact && !inwin) v = 0.0;
+            val = (float)v;
+        } else if (kind == SOM_NEIGH_BUBBLE) {
+            val = inwin ? 1.f : 0.f;
+        } else if (kind == SOM_NEIGH_TRIANGLE) {
+            double v = sigma - fabs(delta);                   // (-|c - n|) + sigma  (:121)
+            if (v < 0.0) v = 0.0;
+            if (compact && !inwin) v = 0.0;
+            val = (float)v;
+        } else {  // mexican hat: tabulate the squared offset and the window
+            val = sq;
+            msk = inwin ? 1.f : 0.f;
+        }
+        if (isx) { tx[e] = val; mx[e] = msk; }
+        else     { ty[e - nxe] = val; my[e - nxe] = msk; }
+    }
+}
+
+__device__ __forceinline__ float neigh_eval(const NeighParams &P, int bi, int bj, int i, int j) {
+    const int q = P.shifted ? (hex_shift(bj, P.gy) - hex_shift(j, P.gy) + 1) : 1;
+    const int xe = (q * P.gx + bi) * P.gx + i;
+    const int ye = bj * P.gy + j;
+    const float fx = __ldg(P.tx + xe), fy = __ldg(P.ty + ye);
+    if (P.kind != SOM_NEIGH_MEXICAN_HAT) return fx * fy;
+    float px = fx;
+    if (P.compact) {
+        // neighborhoods.py:69-71 / 91-93: px is multiplied by both windows, py by none.
+        const float wy = P.mex_rect_quirk ? __ldg(P.my + bj * P.gy + i) : __ldg(P.my + ye);
+        px *= __ldg(P.mx + xe) * wy;
+    }
+    const float p = px + fy;
+    return expf(-p * P.inv_d) * (1.f - P.two_over_d * p);
+}
+
+constexpr int NB_M = 64, NB_N = 64, NB_K = 16, NB_THREADS = 256;
+
+__global__ void __launch_bounds__(NB_THREADS)
+neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__restrict__ c,
+                   float *__restrict__ num, float *__restrict__ den) {
+    __shared__ __align__(16) float Hs[NB_K][NB_M + 4];
+    __shared__ __align__(16) float Ss[NB_K][NB_N + 4];
+    __shared__ float cs[NB_K];
+    const int K = P.gx * P.gy, D = P.d;
+    const int k0 = blockIdx.x * NB_M, n0 = blockIdx.y * NB_N;
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+
+    // this thread generates H entries for b = b0 + (tid >> 4), k = k0 + (tid & 15) * 4 + {0..3}
+    const int hb = tid >> 4, hk = (tid & 15) * 4;
+    int ki[4], kj[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        int kk = k0 + hk + e; if (kk >= K) kk = K - 1;
+        ki[e] = kk / P.gy; kj[e] = kk % P.gy;
+    }
+    // and loads S entries for b = b0 + (tid >> 4), cols n0 + (tid & 15) * 4 + {0..3}
+    float acc[4][4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a)
+#pragma unroll
+        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
+    float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+
+    for (int b0 = 0; b0 < K; b0 += NB_K) {
+        const int b = b0 + hb;
+        float h4[4] = {0.f, 0.f, 0.f, 0.f}, s4[4] = {0.f, 0.f, 0.f, 0.f};
+        float cb = 0.f;
+        if (b < K) {
+            cb = __ldg(c + b);
+            if (cb != 0.f) {   // an empty BMU contributes nothing (S[b] = 0 as well)
+                const int bi = b / P.gy, bj = b % P.gy;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h4[e] = neigh_eval(P, bi, bj, ki[e], kj[e]);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int col = n0 + hk + e;
+                    s4[e] = col < D ? __ldg(S + (int64_t)b * D + col) : 0.f;
+                }
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { Hs[hb][hk + e] = h4[e]; Ss[hb][hk + e] = s4[e]; }
+        if (hk == 0) cs[hb] = cb;
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < NB_K; ++kk) {
+            const float4 hv = *reinterpret_cast<const float4 *>(&Hs[kk][ty * 4]);
+            const float4 sv = *reinterpret_cast<const float4 *>(&Ss[kk][tx * 4]);
+            const float h[4] = {hv.x, hv.y, hv.z, hv.w};
+            const float s[4] = {sv.x, sv.y, sv.z, sv.w};
+#pragma unroll
+            for (int a = 0; a < 4; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fmaf(h[a], s[bb], acc[a][bb]);
+            if (tx == 0) {
+                const float cv = cs[kk];
+#pragma unroll
+                for (int a = 0; a < 4; ++a) dacc[a] = fmaf(h[a], cv, dacc[a]);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+        const int kk = k0 + ty * 4 + a;
+        if (kk >= K) continue;
+#pragma unroll
+        for (int bb = 0; bb < 4; ++bb) {
+            const int col = n0 + tx * 4 + bb;
+            if (col < D) num[(int64_t)kk * D + col] = acc[a][bb] * P.eta;   // g = h * eta (xpysom.py:434)
+        }
+        if (tx == 0 && blockIdx.y == 0) den[kk] = dacc[a] * P.eta;
+    }
+}
+
+inline size_t neigh_table_floats(int gx, int gy) {
+    return (size_t)2 * ((size_t)3 * gx * gx + (size_t)gy * gy) + 64;
+}
+
+inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, int d, int topology, int kind,
+                              double sigma, double eta, double std_coeff, int compact,
+                              float *num, float *den, float *tables, cudaStream_t st) {
+    NeighParams P;
+    P.gx = gx; P.gy = gy; P.d = d; P.topology = topology; P.kind = kind; P.compact = compact ? 1 : 0;
+    // bubble and triangle use integer grid indices on both topologies (xpysom.py:266-269, 277-278)
+    P.shifted = (topology == SOM_TOPO_HEXAGONAL && (kind == SOM_NEIGH_GAUSSIAN || kind == SOM_NEIGH_MEXICAN_HAT)) ? 1 : 0;
+    P.mex_rect_quirk = (kind == SOM_NEIGH_MEXICAN_HAT && compact && topology == SOM_TOPO_RECTANGULAR) ? 1 : 0;
+    const double dd = 2.0 * std_coeff * std_coeff * sigma * sigma;   // neighborhoods.py:19
+    P.inv_d = (float)(1.0 / dd);
+    P.two_over_d = (float)(2.0 / dd);
+    P.eta = (float)eta;
+    const size_t nxe = (size_t)3 * gx * gx, nye = (size_t)gy * gy;
+    float *tx = tables, *ty = tx + nxe, *mx = ty + nye, *my = mx + nxe;
+    P.tx = tx; P.ty = ty; P.mx = mx; P.my = my;
+    const int tot = (int)(nxe + nye);
+    neigh_tables_kernel<<<(tot + 255) / 256, 256, 0, st>>>(gx, gy, kind, P.compact, P.shifted, sigma, dd, tx, ty, mx, my);
+    int rc = check_cuda(cudaGetLastError(), "neigh_tables_kernel launch");
+    if (rc) return rc;
+    const int K = gx * gy;
+    dim3 grid((unsigned)ceil_div(K, NB_M), (unsigned)ceil_div(d, NB_N));
+    neigh_apply_kernel<<<grid, NB_THREADS, 0, st>>>(P, S, c, num, den);
+    return check_cuda(cudaGetLastError(), "neigh_apply_kernel launch");
+}
+
+}  // namespace somb200

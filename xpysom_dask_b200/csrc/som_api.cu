@@ -1,0 +1,253 @@
+// C ABI of libsom_b200.so — see include/som_b200.h for the contract and the
+// reference lines each entry point replaces.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <vector>
+
+#include "common.cuh"
+#include "bmu_simt.cuh"
+#include "bmu_tc.cuh"
+#include "accumulate.cuh"
+#include "neigh.cuh"
+#include "misc.cuh"
+
+namespace somb200 {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int check_cuda(cudaError_t e, const char *what) {
+    if (e == cudaSuccess) return 0;
+    set_error("%s: %s (%s)", what, cudaGetErrorString(e), cudaGetErrorName(e));
+    return (int)e;
+}
+
+struct DevInfo { int ok = 0, sm = 0, cc = 0; size_t smem_optin = 0; };
+
+static int device_info(DevInfo &out) {
+    static thread_local DevInfo cache[64];
+    int dev = 0;
+    SOM_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) dev = 0;
+    if (!cache[dev].ok) {
+        cudaDeviceProp p;
+        SOM_CUDA(cudaGetDeviceProperties(&p, dev));
+        cache[dev].sm = p.multiProcessorCount;
+        cache[dev].cc = p.major * 10 + p.minor;
+        cache[dev].smem_optin = p.sharedMemPerBlockOptin;
+        cache[dev].ok = 1;
+    }
+    out = cache[dev];
+    SOM_REQUIRE(out.cc >= 100, SOM_E_NODEVICE, "libsom_b200 needs an sm_100a device, found cc %d", out.cc);
+    return 0;
+}
+
+static bool known_dist(int k) { return k >= SOM_DIST_EUCLIDEAN && k <= SOM_DIST_NORM_P; }
+
+// AUTO: the tensor-core kernel for the two contraction distances whenever TMA can address X.
+static int pick_algo(int algo, int dist_kind, const float *X, int64_t n, int d, int64_t ldx) {
+    const bool contraction = dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE;
+    if (algo == SOM_ALGO_AUTO)
+        return (contraction && tc::shape_ok(X, n, d, ldx) && d >= 8) ? SOM_ALGO_TC_3XTF32 : SOM_ALGO_SIMT_FP32;
+    return algo;
+}
+
+}  // namespace somb200
+
+using namespace somb200;
+
+extern "C" {
+
+int som_b200_abi_version(void) { return SOM_B200_ABI_VERSION; }
+
+const char *som_b200_last_error(void) { return g_err; }
+
+int som_b200_device_info(int *sm_count, int *cc, size_t *smem_per_block_optin) {
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    if (sm_count) *sm_count = di.sm;
+    if (cc) *cc = di.cc;
+    if (smem_per_block_optin) *smem_per_block_optin = di.smem_optin;
+    return 0;
+}
+
+size_t som_b200_workspace_bytes(int k, int d) {
+    if (k <= 0 || d <= 0) return 0;
+    return ws_layout(k, d).total;
+}
+
+size_t som_b200_shard_workspace_bytes(int64_t n, int k, int d) {
+    if (k <= 0 || d <= 0 || n < 0) return 0;
+    return ws_layout(k, d).total + (size_t)round_up(n * 4, 1024);
+}
+
+size_t som_b200_neigh_table_floats(int gx, int gy) {
+    if (gx <= 0 || gy <= 0) return 0;
+    return neigh_table_floats(gx, gy);
+}
+
+int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, float p,
+                              void *ws_dev, size_t ws_bytes, void *stream) {
+    (void)p;
+    SOM_REQUIRE(w_dev && ws_dev && k > 0 && d > 0, SOM_E_BADARG, "prepare_codebook: bad argument");
+    SOM_REQUIRE(known_dist(dist_kind), SOM_E_BADARG, "prepare_codebook: unknown distance kind %d", dist_kind);
+    const WsLayout L = ws_layout(k, d);
+    SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "prepare_codebook: workspace %zu < %zu bytes", ws_bytes, L.total);
+    uint8_t *ws = static_cast<uint8_t *>(ws_dev);
+    const bool split = dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE;
+    const int threads = 256, warps_per_block = threads / 32;
+    const int blocks = (int)ceil_div(L.k_pad, warps_per_block);
+    prepare_codebook_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        w_dev, k, d, dist_kind, L.k_pad, L.d_pad, reinterpret_cast<float *>(ws + L.aux_off),
+        reinterpret_cast<float *>(ws + L.bias_off), split ? reinterpret_cast<float *>(ws + L.whi_off) : nullptr,
+        split ? reinterpret_cast<float *>(ws + L.wlo_off) : nullptr);
+    return check_cuda(cudaGetLastError(), "prepare_codebook_kernel launch");
+}
+
+int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int dist_kind,
+                 float p, int algo, int32_t *bmu_dev, float *best_dev, void *ws_dev, size_t ws_bytes, void *stream) {
+    SOM_REQUIRE(w_dev && ws_dev && bmu_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "bmu: bad argument");
+    SOM_REQUIRE(known_dist(dist_kind), SOM_E_BADARG, "bmu: unknown distance kind %d", dist_kind);
+    if (n == 0) return 0;
+    SOM_REQUIRE(x_dev, SOM_E_BADARG, "bmu: x is NULL");
+    const WsLayout L = ws_layout(k, d);
+    SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "bmu: workspace %zu < %zu bytes", ws_bytes, L.total);
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    uint8_t *ws = static_cast<uint8_t *>(ws_dev);
+    const int use = pick_algo(algo, dist_kind, x_dev, n, d, ldx);
+    if (use == SOM_ALGO_TC_3XTF32) {
+        SOM_REQUIRE(dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE, SOM_E_SHAPE,
+                    "the tensor-core kernel computes contraction distances only (euclidean, cosine)");
+        return tc::launch_bmu_tc(x_dev, n, d, ldx, k, L, ws, bmu_dev, best_dev, di.sm, (cudaStream_t)stream);
+    }
+    SOM_REQUIRE(use == SOM_ALGO_SIMT_FP32, SOM_E_BADARG, "bmu: unknown algo %d", algo);
+    return launch_bmu_simt(x_dev, n, d, ldx, w_dev, k, dist_kind, p, reinterpret_cast<const float *>(ws + L.aux_off),
+                           bmu_dev, best_dev, di.sm, (cudaStream_t)stream);
+}
+
+int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const int32_t *bmu_dev, int k,
+                        float *s_dev, float *c_dev, void *stream) {
+    SOM_REQUIRE(s_dev && c_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "accumulate: bad argument");
+    if (n == 0) return 0;
+    SOM_REQUIRE(x_dev && bmu_dev, SOM_E_BADARG, "accumulate: NULL input");
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    return launch_accumulate(x_dev, n, d, ldx, bmu_dev, k, s_dev, c_dev, di.sm, (cudaStream_t)stream);
+}
+
+int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k,
+                              int dist_kind, float p, int algo, float *s_dev, float *c_dev, int32_t *bmu_dev,
+                              void *ws_dev, size_t ws_bytes, void *stream) {
+    SOM_REQUIRE(n >= 0 && k > 0 && d > 0, SOM_E_BADARG, "epoch_accumulate: bad argument");
+    if (n == 0) return 0;
+    const WsLayout L = ws_layout(k, d);
+    int32_t *bmu = bmu_dev;
+    if (!bmu) {
+        const size_t need = L.total + (size_t)round_up(n * 4, 1024);
+        SOM_REQUIRE(ws_dev && ws_bytes >= need, SOM_E_WORKSPACE,
+                    "epoch_accumulate: workspace %zu < %zu bytes (no bmu buffer given)", ws_bytes, need);
+        bmu = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(ws_dev) + L.total);
+    }
+    int rc = som_b200_bmu(x_dev, n, d, ldx, w_dev, k, dist_kind, p, algo, bmu, nullptr, ws_dev, ws_bytes, stream);
+    if (rc) return rc;
+    return som_b200_accumulate(x_dev, n, d, ldx, bmu, k, s_dev, c_dev, stream);
+}
+
+int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy, int d, int topology,
+                         int neigh_kind, double sigma, double eta, double std_coeff, int compact_support,
+                         float *num_dev, float *den_dev, float *tables_dev, void *stream) {
+    SOM_REQUIRE(s_dev && c_dev && num_dev && den_dev && tables_dev && gx > 0 && gy > 0 && d > 0, SOM_E_BADARG,
+                "neigh_apply: bad argument");
+    SOM_REQUIRE(topology == SOM_TOPO_RECTANGULAR || topology == SOM_TOPO_HEXAGONAL, SOM_E_BADARG,
+                "neigh_apply: unknown topology %d", topology);
+    SOM_REQUIRE(neigh_kind >= SOM_NEIGH_GAUSSIAN && neigh_kind <= SOM_NEIGH_TRIANGLE, SOM_E_BADARG,
+                "neigh_apply: unknown neighbourhood %d", neigh_kind);
+    // combinations the reference itself rejects
+    SOM_REQUIRE(!(neigh_kind == SOM_NEIGH_TRIANGLE && topology == SOM_TOPO_HEXAGONAL), SOM_E_SHAPE,
+                "triangle is not available on a hexagonal map (xpysom.py:272-279)");
+    SOM_REQUIRE(!(neigh_kind == SOM_NEIGH_MEXICAN_HAT && compact_support && topology == SOM_TOPO_RECTANGULAR && gx != gy),
+                SOM_E_SHAPE, "mexican_hat with compact_support broadcasts (n,gx)*(n,gy) in the reference "
+                "(neighborhoods.py:69-71): needs gx == gy");
+    SOM_REQUIRE(sigma != 0.0 && std_coeff != 0.0, SOM_E_BADARG, "neigh_apply: sigma and std_coeff must be non-zero");
+    return launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support,
+                              num_dev, den_dev, tables_dev, (cudaStream_t)stream);
+}
+
+int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev, int k, int d, void *stream) {
+    SOM_REQUIRE(w_dev && num_dev && den_dev && k > 0 && d > 0, SOM_E_BADARG, "merge: bad argument");
+    const int64_t tot = (int64_t)k * d;
+    int blocks = (int)ceil_div(tot, 256);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    merge_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_dev, num_dev, den_dev, k, d);
+    return check_cuda(cudaGetLastError(), "merge_kernel launch");
+}
+
+int som_b200_quantize(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k,
+                      const int32_t *bmu_dev, float *q_dev, float *err_dev, void *stream) {
+    SOM_REQUIRE(w_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "quantize: bad argument");
+    if (n == 0) return 0;
+    SOM_REQUIRE(x_dev && bmu_dev, SOM_E_BADARG, "quantize: NULL input");
+    int64_t blocks = ceil_div(n, 8);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    quantize_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, n, d, ldx, w_dev, bmu_dev, q_dev, err_dev);
+    return check_cuda(cudaGetLastError(), "quantize_kernel launch");
+}
+
+int som_b200_distance_map(const float *w_dev, int gx, int gy, int d, int topology, float *um_dev, void *stream) {
+    SOM_REQUIRE(w_dev && um_dev && gx > 0 && gy > 0 && d > 0, SOM_E_BADARG, "distance_map: bad argument");
+    const int K = gx * gy;
+    distance_map_kernel<<<(int)ceil_div(K, 8), 256, 0, (cudaStream_t)stream>>>(w_dev, gx, gy, d, topology, um_dev);
+    return check_cuda(cudaGetLastError(), "distance_map_kernel launch");
+}
+
+int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_host, const som_b200_train_config *cfg,
+                        const double *sigma_per_epoch, const double *eta_per_epoch, int n_epochs) {
+    SOM_REQUIRE(x_host && w_host && cfg && sigma_per_epoch && eta_per_epoch && n > 0 && n_epochs >= 0, SOM_E_BADARG,
+                "train_host: bad argument");
+    const int d = cfg->d, K = cfg->gx * cfg->gy;
+    SOM_REQUIRE(d > 0 && K > 0 && ldx >= d, SOM_E_BADARG, "train_host: bad shape");
+    struct Bufs {
+        float *x = nullptr, *w = nullptr, *sc = nullptr, *nd = nullptr, *tab = nullptr;
+        uint8_t *ws = nullptr; cudaStream_t st = nullptr;
+        ~Bufs() { cudaFree(x); cudaFree(w); cudaFree(sc); cudaFree(nd); cudaFree(tab); cudaFree(ws); if (st) cudaStreamDestroy(st); }
+    } b;
+    const int64_t dld = round_up(d, 4);                 // device row stride: 16-byte aligned rows for TMA / float4
+    const size_t ws_bytes = som_b200_shard_workspace_bytes(n, K, d);
+    SOM_CUDA(cudaStreamCreateWithFlags(&b.st, cudaStreamNonBlocking));
+    SOM_CUDA(cudaMalloc(&b.x, (size_t)n * dld * 4));
+    SOM_CUDA(cudaMalloc(&b.w, (size_t)K * d * 4));
+    SOM_CUDA(cudaMalloc(&b.sc, ((size_t)K * d + K) * 4));
+    SOM_CUDA(cudaMalloc(&b.nd, ((size_t)K * d + K) * 4));
+    SOM_CUDA(cudaMalloc(&b.tab, som_b200_neigh_table_floats(cfg->gx, cfg->gy) * 4));
+    SOM_CUDA(cudaMalloc(&b.ws, ws_bytes));
+    if (dld != d) SOM_CUDA(cudaMemsetAsync(b.x, 0, (size_t)n * dld * 4, b.st));
+    SOM_CUDA(cudaMemcpy2DAsync(b.x, dld * 4, x_host, ldx * 4, (size_t)d * 4, (size_t)n, cudaMemcpyHostToDevice, b.st));
+    SOM_CUDA(cudaMemcpyAsync(b.w, w_host, (size_t)K * d * 4, cudaMemcpyHostToDevice, b.st));
+    float *S = b.sc, *c = b.sc + (size_t)K * d, *num = b.nd, *den = b.nd + (size_t)K * d;
+    for (int e = 0; e < n_epochs; ++e) {
+        int rc;
+        SOM_CUDA(cudaMemsetAsync(b.sc, 0, ((size_t)K * d + K) * 4, b.st));
+        if ((rc = som_b200_prepare_codebook(b.w, K, d, cfg->dist_kind, cfg->p, b.ws, ws_bytes, b.st))) return rc;
+        if ((rc = som_b200_epoch_accumulate(b.x, n, d, dld, b.w, K, cfg->dist_kind, cfg->p, cfg->algo, S, c, nullptr,
+                                            b.ws, ws_bytes, b.st))) return rc;
+        if ((rc = som_b200_neigh_apply(S, c, cfg->gx, cfg->gy, d, cfg->topology, cfg->neigh_kind, sigma_per_epoch[e],
+                                       eta_per_epoch[e], cfg->std_coeff, cfg->compact_support, num, den, b.tab, b.st))) return rc;
+        if ((rc = som_b200_merge(b.w, num, den, K, d, b.st))) return rc;
+    }
+    SOM_CUDA(cudaMemcpyAsync(w_host, b.w, (size_t)K * d * 4, cudaMemcpyDeviceToHost, b.st));
+    SOM_CUDA(cudaStreamSynchronize(b.st));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,128 @@
+"""Device engine: torch tensors for memory and streams, libsom_b200 for every kernel.
+
+One engine instance drives one GPU.  All methods enqueue on torch's current
+CUDA stream and take / return torch tensors living on that GPU; nothing here
+computes with torch ops on the hot path.  Without a CUDA device or without the
+shared object the constructor raises — there is no CPU fallback.
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+
+class CudaEngine:
+    name = "cuda"
+
+    def __init__(self, device=None):
+        if not torch.cuda.is_available():
+            raise _lib.SomB200Error(
+                "xpysom_dask_b200 needs a CUDA device (B200, sm_100a); torch.cuda.is_available() is False. "
+                "There is no CPU fallback.")
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device())
+        self.device = torch.device(device)
+        with torch.cuda.device(self.device):
+            sm, cc = ctypes.c_int(), ctypes.c_int()
+            smem = ctypes.c_size_t()
+            _lib.check(self.lib.som_b200_device_info(ctypes.byref(sm), ctypes.byref(cc), ctypes.byref(smem)),
+                       "som_b200_device_info")
+        self.sm_count, self.cc = sm.value, cc.value
+        self.launches = 0          # kernels enqueued through this engine (bench.py reports it)
+
+    # -- helpers ---------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @staticmethod
+    def _p(t):
+        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+    def empty(self, *shape, dtype=torch.float32):
+        return torch.empty(*shape, dtype=dtype, device=self.device)
+
+    def zeros(self, *shape, dtype=torch.float32):
+        return torch.zeros(*shape, dtype=dtype, device=self.device)
+
+    def to_device(self, host_tensor):
+        """Host (pinned if possible) -> device copy on the current stream."""
+        return host_tensor.to(self.device, non_blocking=True)
+
+    def workspace(self, n, k, d):
+        nbytes = self.lib.som_b200_shard_workspace_bytes(int(n), int(k), int(d))
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+
+    def neigh_tables(self, gx, gy):
+        return self.empty(self.lib.som_b200_neigh_table_floats(int(gx), int(gy)))
+
+    # -- kernels -----------------------------------------------------------------
+    def prepare_codebook(self, w, dist_kind, p, ws):
+        k, d = w.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_prepare_codebook(self._p(w), k, d, dist_kind, float(p), self._p(ws),
+                                                          ws.numel(), self._stream()), "som_b200_prepare_codebook")
+        self.launches += 1
+
+    def bmu(self, x, w, dist_kind, p, algo, ws, bmu_out=None, best_out=None):
+        n, d = x.shape
+        k = w.shape[0]
+        if bmu_out is None:
+            bmu_out = self.empty(n, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_bmu(self._p(x), n, d, x.stride(0), self._p(w), k, dist_kind, float(p), algo,
+                                             self._p(bmu_out), self._p(best_out), self._p(ws), ws.numel(),
+                                             self._stream()), "som_b200_bmu")
+        self.launches += 1
+        return bmu_out
+
+    def accumulate(self, x, bmu, k, s, c):
+        n, d = x.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_accumulate(self._p(x), n, d, x.stride(0), self._p(bmu), k, self._p(s),
+                                                    self._p(c), self._stream()), "som_b200_accumulate")
+        self.launches += 1
+
+    def epoch_accumulate(self, x, w, dist_kind, p, algo, s, c, ws, bmu_out=None):
+        n, d = x.shape
+        k = w.shape[0]
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_epoch_accumulate(self._p(x), n, d, x.stride(0), self._p(w), k, dist_kind,
+                                                          float(p), algo, self._p(s), self._p(c), self._p(bmu_out),
+                                                          self._p(ws), ws.numel(), self._stream()),
+                       "som_b200_epoch_accumulate")
+        self.launches += 2
+
+    def neigh_apply(self, s, c, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, num, den, tables):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_neigh_apply(self._p(s), self._p(c), gx, gy, d, topology, neigh_kind,
+                                                     float(sigma), float(eta), float(std_coeff), int(bool(compact)),
+                                                     self._p(num), self._p(den), self._p(tables), self._stream()),
+                       "som_b200_neigh_apply")
+        self.launches += 2
+
+    def merge(self, w, num, den):
+        k, d = w.shape
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_merge(self._p(w), self._p(num), self._p(den), k, d, self._stream()),
+                       "som_b200_merge")
+        self.launches += 1
+
+    def quantize(self, x, w, bmu, want_q=False, want_err=True):
+        n, d = x.shape
+        q = self.empty(n, d) if want_q else None
+        err = self.empty(n) if want_err else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_quantize(self._p(x), n, d, x.stride(0), self._p(w), w.shape[0], self._p(bmu),
+                                                  self._p(q), self._p(err), self._stream()), "som_b200_quantize")
+        self.launches += 1
+        return q, err
+
+    def distance_map(self, w, gx, gy, topology):
+        um = self.empty(gx * gy)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_distance_map(self._p(w), gx, gy, w.shape[1], topology, self._p(um),
+                                                      self._stream()), "som_b200_distance_map")
+        self.launches += 1
+        return um

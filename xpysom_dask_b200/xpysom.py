@@ -1,0 +1,371 @@
+"""`XPySom` — the reference's model API, with the batch-SOM epoch on B200 kernels.
+
+Host-side mirror of ``xpysom_dask/xpysom.py:72-892``: same constructor
+arguments, defaults, validation errors and method names, so it drops in as the
+compute backend for the training path (``train`` -> ``_update`` ->
+``_merge_updates``) and for the inference calls that reuse its BMU search.
+What changed underneath:
+
+* numpy/CuPy dispatch (``xp``) and Dask scheduling (``use_dask``,
+  ``dask_chunks``) are accepted and ignored; every array operation of the epoch
+  runs in ``libsom_b200.so`` (hand-written sm_100a CUDA) through a C ABI;
+* ``n_parallel`` chunking (xpysom.py:560-569) becomes kernel tiling;
+* Dask row-blocks (xpysom.py:545-558) become shards: one process per GPU, each
+  calling ``train`` on its own rows with ``process_group`` set, and ONE
+  all-reduce of the (K*D + K) per-BMU sums per epoch; the codebook stays
+  replicated.
+
+``self._weights`` stays a host numpy array of shape (x, y, input_len) that
+callers may assign to between calls, exactly as with the reference
+(tests.py:31-33); it is re-uploaded at every public call.
+"""
+from collections import Counter, defaultdict
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _lib
+from .decays import DECAY_FUNCTIONS
+
+_NEIGHBORHOODS = {
+    "rectangular": ("gaussian", "mexican_hat", "bubble", "triangle"),
+    "hexagonal": ("gaussian", "mexican_hat", "bubble"),          # xpysom.py:271-279
+}
+_DISTANCES = ("euclidean", "euclidean_no_opt", "manhattan", "manhattan_no_opt", "cosine", "norm_p",
+              "norm_p_no_opt", "chebyshev")                       # distances.py:162-170 + chebyshev
+_DEFAULT_N_PARALLEL = 148 * 2048     # SMs x max threads/SM on B200: the rule of utils.py:4-11
+
+
+def _as_f32_matrix(data):
+    """Any array-like / torch tensor -> 2-D float32 torch tensor (no copy when possible)."""
+    if isinstance(data, torch.Tensor):
+        t = data
+        if t.dtype != torch.float32:
+            t = t.to(torch.float32)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(data, dtype=np.float32)))
+    if t.dim() == 1:
+        t = t.unsqueeze(0)
+    if t.dim() != 2:
+        raise ValueError("data must be a 2-D (samples, features) matrix")
+    return t
+
+
+class XPySom:
+    def __init__(self, x, y, input_len, sigma=0, sigmaN=1, learning_rate=0.5, learning_rateN=0.01,
+                 decay_function='exponential', neighborhood_function='gaussian', std_coeff=0.5,
+                 topology='rectangular', activation_distance='euclidean', activation_distance_kwargs={},
+                 random_seed=None, n_parallel=0, compact_support=False, xp=None, use_dask=False,
+                 dask_chunks='auto', *, device=None, algo='auto', process_group=None, engine=None):
+        """Same arguments as the reference constructor (xpysom.py:73-82).
+
+        Keyword-only additions: ``device`` (CUDA device of this process),
+        ``algo`` ('auto' | 'tc' | 'simt': which BMU kernel), ``process_group``
+        (a torch.distributed group, or True for the default group: this process
+        holds one shard of the samples) and ``engine`` (test hook).
+        """
+        if sigma >= x or sigma >= y:
+            warn('Warning: sigma is too high for the dimension of the map.')
+        self._random_generator = np.random.RandomState(random_seed)
+        self.xp = xp                       # accepted for signature compatibility, unused
+        self.use_dask = False              # Dask scheduling is replaced by GPU shards
+        self.dask_chunks = dask_chunks
+        self._learning_rate = learning_rate
+        self._learning_rateN = learning_rateN
+        self._sigma = min(x, y) / 2 if sigma == 0 else sigma
+        self._std_coeff = std_coeff
+        self._sigmaN = sigmaN
+        self._input_len = input_len
+
+        # bit-compatible initial codebook: same generator, same call order (xpysom.py:167,189-190)
+        self._weights = self._random_generator.rand(x, y, input_len) * 2 - 1
+        self._weights /= np.linalg.norm(self._weights, axis=-1, keepdims=True)
+
+        self._neigx = np.arange(x)
+        self._neigy = np.arange(y)
+        if topology not in _NEIGHBORHOODS:
+            raise ValueError('%s not supported only hexagonal and rectangular available' % topology)
+        self.topology = topology
+        self._xx, self._yy = np.meshgrid(self._neigx, self._neigy)
+        self._xx = self._xx.astype(float)
+        self._yy = self._yy.astype(float)
+        if topology == 'hexagonal':
+            self._xx[::-2] -= 0.5          # xpysom.py:206
+            if neighborhood_function in ['triangle']:
+                warn('triangle neighborhood function does not take in account hexagonal topology')
+
+        if decay_function not in DECAY_FUNCTIONS:
+            raise ValueError('%s not supported. Functions available: %s'
+                             % (decay_function, ', '.join(DECAY_FUNCTIONS.keys())))
+        self._decay_function_name = decay_function
+        self.compact_support = compact_support
+        if neighborhood_function not in _NEIGHBORHOODS[topology]:
+            raise ValueError('%s not supported. Functions available: %s'
+                             % (neighborhood_function, ', '.join(_NEIGHBORHOODS[topology])))
+        self.neighborhood_func_name = neighborhood_function
+        if activation_distance not in _DISTANCES:
+            raise ValueError('%s not supported. Distances available: %s'
+                             % (activation_distance, ', '.join(_DISTANCES)))
+        self._activation_distance_name = activation_distance
+        self._activation_distance_kwargs = dict(activation_distance_kwargs)
+        if n_parallel == 0:
+            n_parallel = _DEFAULT_N_PARALLEL
+        self._n_parallel = n_parallel      # kept for API parity; tiling is internal to the kernels
+
+        if algo not in _lib.ALGO:
+            raise ValueError("algo must be one of %s" % ', '.join(_lib.ALGO))
+        self._algo = algo
+        self._device = device
+        self._process_group = process_group
+        self._engine = engine
+        self._profile = False              # bench.py: record CUDA events around the BMU / accumulate kernels
+        self._profile_events = []
+        self.stats = {}
+
+    # ------------------------------------------------------------------ plumbing
+    @property
+    def _decay_function(self):
+        return DECAY_FUNCTIONS[self._decay_function_name]
+
+    def _get_engine(self):
+        if self._engine is None:
+            from .engine import CudaEngine
+            self._engine = CudaEngine(self._device)
+        return self._engine
+
+    def _dist_kind(self, euclidean_only=False):
+        if euclidean_only:
+            return _lib.DIST['euclidean'], 2.0
+        name = self._activation_distance_name
+        p = float(self._activation_distance_kwargs.get('p', 2))
+        return _lib.DIST[name], p
+
+    def _group(self):
+        pg = self._process_group
+        if pg is None or pg is False:
+            return None
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise RuntimeError("process_group given but torch.distributed is not initialised")
+        return dist.group.WORLD if pg is True else pg
+
+    def _shape(self):
+        gx, gy, d = self._weights.shape
+        return gx, gy, d
+
+    def _weights_to_device(self, eng):
+        gx, gy, d = self._shape()
+        w = torch.from_numpy(np.ascontiguousarray(self._weights, dtype=np.float32).reshape(gx * gy, d))
+        return eng.to_device(w)
+
+    def _data_to_device(self, eng, data):
+        t = _as_f32_matrix(data)
+        if t.device != eng.device:
+            t = eng.to_device(t)
+        if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+            t = t.contiguous()
+        return t
+
+    def _check_input_len(self, data):
+        """xpysom.py:361-367"""
+        data_len = len(data[0])
+        if self._input_len != data_len:
+            raise ValueError('Received %d features, expected %d.' % (data_len, self._input_len))
+
+    def _check_iteration_number(self, num_iteration):
+        if num_iteration < 1:
+            raise ValueError('num_iteration must be > 1')
+
+    # ------------------------------------------------------------------ training
+    def train(self, data, num_epochs, iter_beg=0, iter_end=None, verbose=False):
+        """Batch-SOM training, epochs [iter_beg, iter_end) of a num_epochs schedule
+        (xpysom.py:458-594).  With ``process_group`` set, ``data`` is this
+        process's shard of the samples."""
+        if iter_end is None:
+            iter_end = num_epochs
+        eng = self._get_engine()
+        gx, gy, d = self._shape()
+        K = gx * gy
+        dist_kind, p = self._dist_kind()
+        algo = _lib.ALGO[self._algo]
+        topo = _lib.TOPO[self.topology]
+        neigh = _lib.NEIGH[self.neighborhood_func_name]
+        group = self._group()
+
+        w = self._weights_to_device(eng)
+        x = self._data_to_device(eng, data)
+        if x.shape[1] != d:
+            raise ValueError('Received %d features, expected %d.' % (x.shape[1], d))
+        n = x.shape[0]
+
+        sc = eng.zeros(K * d + K)            # [S | c], one buffer -> one all-reduce
+        nd = eng.empty(K * d + K)            # [num | den]
+        S, c = sc[:K * d], sc[K * d:]
+        num, den = nd[:K * d], nd[K * d:]
+        ws = eng.workspace(0, K, d)
+        bmu = eng.empty(n, dtype=torch.int32)
+        tables = eng.neigh_tables(gx, gy)
+        prof = self._profile_events if getattr(self, '_profile', False) else None
+
+        for t in range(iter_beg, iter_end):
+            eta = self._decay_function(self._learning_rate, self._learning_rateN, t, num_epochs)
+            sig = self._decay_function(self._sigma, self._sigmaN, t, num_epochs)   # same rule (xpysom.py:541-543)
+            sc.zero_()
+            eng.prepare_codebook(w, dist_kind, p, ws)
+            if prof is not None:
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev[0].record()
+            eng.bmu(x, w, dist_kind, p, algo, ws, bmu_out=bmu)          # K1/K2: distance + argmin
+            if prof is not None:
+                ev[1].record()
+            eng.accumulate(x, bmu, K, S, c)                             # K3: S[bmu] += x, c[bmu] += 1
+            if prof is not None:
+                ev[2].record()
+                prof.append(ev)
+            if group is not None:
+                import torch.distributed as dist
+                dist.all_reduce(sc, op=dist.ReduceOp.SUM, group=group)
+            eng.neigh_apply(S, c, gx, gy, d, topo, neigh, sig, eta, self._std_coeff, self.compact_support,
+                            num, den, tables)
+            eng.merge(w, num, den)
+            if verbose:
+                print('\r [ %d / %d ]' % (t + 1, num_epochs), end='')
+
+        self._weights = w.cpu().numpy().reshape(gx, gy, d)      # synchronises; fp32 like xpysom.py:580-583
+        if verbose:
+            print('\n quantization error:', self.quantization_error(data))
+        return self
+
+    def train_batch(self, data, num_iteration, verbose=False):
+        """Compatibility with MiniSom, alias for train (xpysom.py:597-599)."""
+        return self.train(data, num_iteration, verbose=verbose)
+
+    def train_random(self, data, num_iteration, verbose=False):
+        """Compatibility with MiniSom (xpysom.py:602-605): batch SOM has no sample order."""
+        print("WARNING: due to batch SOM algorithm, random order is not supported. Falling back to train_batch.")
+        return self.train(data, num_iteration, verbose=verbose)
+
+    # ------------------------------------------------------------------ inference
+    def _bmu_flat(self, data, euclidean_only=False):
+        """Device BMU search -> (flat int32 indices on device, x, w, engine)."""
+        eng = self._get_engine()
+        gx, gy, d = self._shape()
+        dist_kind, p = self._dist_kind(euclidean_only)
+        w = self._weights_to_device(eng)
+        x = self._data_to_device(eng, data)
+        ws = eng.workspace(0, gx * gy, d)
+        eng.prepare_codebook(w, dist_kind, p, ws)
+        bmu = eng.bmu(x, w, dist_kind, p, _lib.ALGO[self._algo], ws)
+        return bmu, x, w, eng
+
+    def winner(self, x):
+        """Coordinates of the winning neuron(s) (xpysom.py:370-408): a tuple for a
+        1-D sample, a list of tuples for a 2-D batch."""
+        single = (np.ndim(x) == 1) if not isinstance(x, torch.Tensor) else (x.dim() == 1)
+        bmu, _, _, _ = self._bmu_flat(x)
+        flat = bmu.cpu().numpy().astype(np.int64)
+        gy = self._weights.shape[1]
+        wi, wj = flat // gy, flat % gy
+        if single:
+            return (wi[0].item(), wj[0].item())
+        return list(zip(wi, wj))
+
+    def predict(self, data):
+        """Flat index of the winner of every sample (xpysom.py:608-617)."""
+        bmu, _, _, _ = self._bmu_flat(data)
+        return bmu.cpu().numpy().astype(np.int64)
+
+    def quantization(self, data):
+        """Code-book vector of every sample's Euclidean BMU (xpysom.py:620-645)."""
+        self._check_input_len(data)
+        bmu, _, _, _ = self._bmu_flat(data, euclidean_only=True)
+        flat = bmu.cpu().numpy().astype(np.int64)
+        gx, gy, d = self._shape()
+        return np.array(self._weights).reshape(gx * gy, d)[flat]
+
+    def quantization_error(self, data):
+        """Mean Euclidean distance between each sample and its BMU (xpysom.py:673-707)."""
+        self._check_input_len(data)
+        bmu, x, w, eng = self._bmu_flat(data, euclidean_only=True)
+        _, err = eng.quantize(x, w, bmu, want_q=False, want_err=True)
+        return (err.sum(dtype=torch.float64) / err.numel()).item()
+
+    def distance_map(self):
+        """Normalised sum of distances to the grid neighbours (xpysom.py:788-817)."""
+        eng = self._get_engine()
+        gx, gy, _ = self._shape()
+        w = self._weights_to_device(eng)
+        um = eng.distance_map(w, gx, gy, _lib.TOPO[self.topology]).cpu().numpy().astype(np.float64)
+        return (um / um.max()).reshape(gx, gy)
+
+    def activation_response(self, data):
+        """How many times each neuron wins (xpysom.py:819-829)."""
+        self._check_input_len(data)
+        gx, gy, _ = self._shape()
+        flat = self.predict(data)
+        return np.bincount(flat, minlength=gx * gy).astype(float).reshape(gx, gy)
+
+    def win_map(self, data):
+        """(i,j) -> list of the samples mapped there (xpysom.py:831-840)."""
+        self._check_input_len(data)
+        winmap = defaultdict(list)
+        for sample, win in zip(data, self.winner(data)):
+            winmap[win].append(sample)
+        return winmap
+
+    def labels_map(self, data, labels):
+        """(i,j) -> Counter of the labels mapped there (xpysom.py:842-865)."""
+        self._check_input_len(data)
+        if not len(data) == len(labels):
+            raise ValueError('data and labels must have the same length.')
+        winmap = defaultdict(list)
+        for win, lab in zip(self.winner(data), labels):
+            winmap[win].append(lab)
+        return {pos: Counter(v) for pos, v in winmap.items()}
+
+    # ------------------------------------------------------------------ host-side conveniences
+    def get_weights(self):
+        """xpysom.py:286-288"""
+        return self._weights
+
+    def get_euclidean_coordinates(self):
+        """xpysom.py:291-305"""
+        return self._xx.T, self._yy.T
+
+    def convert_map_to_euclidean(self, xy):
+        """xpysom.py:308-320"""
+        return self._xx.T[xy], self._yy.T[xy]
+
+    def random_weights_init(self, data):
+        """Codebook <- random samples, same generator draws as xpysom.py:749-759."""
+        self._check_input_len(data)
+        gx, gy, _ = self._shape()
+        for i in range(gx):
+            for j in range(gy):
+                self._weights[i, j] = data[self._random_generator.randint(len(data))]
+
+    def pca_weights_init(self, data):
+        """Codebook spans the first two principal components (xpysom.py:762-785)."""
+        if self._input_len == 1:
+            raise ValueError('The data needs at least 2 features for pca initialization')
+        self._check_input_len(data)
+        if len(self._neigx) == 1 or len(self._neigy) == 1:
+            warn('PCA initialization inappropriate:One of the dimensions of the map is 1.')
+        pc_length, pc = np.linalg.eig(np.cov(np.transpose(data)))
+        order = np.argsort(-pc_length)
+        for i, c1 in enumerate(np.linspace(-1, 1, len(self._neigx))):
+            for j, c2 in enumerate(np.linspace(-1, 1, len(self._neigy))):
+                self._weights[i, j] = c1 * pc[order[0]] + c2 * pc[order[1]]
+
+    # ------------------------------------------------------------------ pickling (xpysom.py:868-892)
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state['_engine'] = None            # device handles are rebuilt on demand
+        state['_process_group'] = None
+        state['_profile_events'] = []
+        state['xp'] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
