@@ -51,8 +51,6 @@ BMU_SHAPES = [
 @pytest.mark.parametrize("dist", ["euclidean", "cosine"])
 @pytest.mark.parametrize("algo", ["simt", "tc"])
 def test_bmu_contraction_distances(eng, n, d, gx, gy, dist, algo):
-    if algo == "tc" and d < 4:
-        pytest.skip("tensor-core kernel needs d >= 4")
     x = U.blobs(n, d, seed=n + d)
     spec = so.SomSpec(gx=gx, gy=gy, dim=d, activation_distance=dist, random_seed=d)
     w = so.init_weights(spec).astype(np.float32) * 0.5 + 0.5 * U.uniform(gx * gy, d, 3).reshape(gx, gy, d)
@@ -92,7 +90,7 @@ def test_unaligned_rows_fall_back_to_simt(eng):
     w = so.init_weights(spec).astype(np.float32)
     bmu = _gpu_bmu(eng, x, w, "euclidean", 2.0, "auto")
     assert U.bmu_parity(spec, x, w, bmu)["bad"] == 0
-    xd = torch.from_numpy(x).cuda()
+    xd = torch.from_numpy(x).cuda()            # contiguous (1000, 30): rows not 16-byte aligned
     wd = torch.from_numpy(w.reshape(81, 30)).cuda()
     ws = eng.workspace(0, 81, 30)
     eng.prepare_codebook(wd, 0, 2.0, ws)

@@ -311,14 +311,14 @@ inline int make_map_2d(CUtensorMap *m, const void *base, uint64_t inner, uint64_
 }
 
 inline bool shape_ok(const float *X, int64_t n, int d, int64_t ldx) {
-    return n > 0 && d >= 4 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
+    return n > 0 && d >= 1 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
            n < ((int64_t)1 << 31) - BM;
 }
 
 inline int launch_bmu_tc(const float *X, int64_t n, int d, int64_t ldx, int k, const WsLayout &L, uint8_t *ws,
                          int32_t *bmu, float *best, int sm_count, cudaStream_t st) {
     SOM_REQUIRE(shape_ok(X, n, d, ldx), SOM_E_SHAPE,
-                "tensor-core BMU kernel needs d >= 4, ldx %% 4 == 0 and a 16-byte aligned X (d=%d ldx=%lld)", d, (long long)ldx);
+                "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
     CUtensorMap mx, mhi, mlo;
     int rc;
     if ((rc = make_map_2d(&mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)ldx * 4, BK, BM))) return rc;

@@ -160,12 +160,20 @@ class XPySom:
         return eng.to_device(w)
 
     def _data_to_device(self, eng, data):
+        """Samples -> fp32 device matrix whose rows start on 16-byte boundaries (row stride a
+        multiple of 4 floats), which is what TMA and the float4 paths need.  A CUDA tensor that
+        already satisfies this is used in place (no copy)."""
         t = _as_f32_matrix(data)
-        if t.device != eng.device:
-            t = eng.to_device(t)
-        if t.stride(1) != 1 or t.stride(0) < t.shape[1]:
-            t = t.contiguous()
-        return t
+        n, d = t.shape
+        ok = (t.device == eng.device and t.stride(1) == 1 and t.stride(0) >= d and t.stride(0) % 4 == 0
+              and t.data_ptr() % 16 == 0)
+        if ok:
+            return t
+        ld = (d + 3) // 4 * 4
+        buf = torch.empty((n, ld), dtype=torch.float32, device=eng.device)
+        view = buf[:, :d]
+        view.copy_(t, non_blocking=True)
+        return view
 
     def _check_input_len(self, data):
         """xpysom.py:361-367"""
