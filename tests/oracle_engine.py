@@ -52,6 +52,10 @@ class OracleEngine:
         s.view(k, -1).add_(torch.from_numpy(S.astype(np.float32)))
         c.add_(torch.from_numpy(cc.astype(np.float32)))
 
+    def epoch_accumulate(self, x, w, dist_kind, p, algo, s, c, ws, bmu_out=None):
+        bmu = self.bmu(x, w, dist_kind, p, algo, ws, bmu_out=bmu_out)
+        self.accumulate(x, bmu, w.shape[0], s, c)
+
     def neigh_apply(self, s, c, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, num, den, tables):
         spec = so.SomSpec(gx=gx, gy=gy, dim=d, sigma=1.0, neighborhood_function=_NEIGH[neigh_kind],
                           topology=_TOPO[topology], std_coeff=std_coeff, compact_support=bool(compact))

@@ -80,9 +80,8 @@ def stage_epoch(eng):
             torch.cuda.synchronize()
             dt = (time.perf_counter() - t0) / 3
             b = np.mean([e[0].elapsed_time(e[1]) for e in som._profile_events])
-            a = np.mean([e[1].elapsed_time(e[2]) for e in som._profile_events])
-            print("[epoch %s] n=%d d=%d K=%d %s: %.2f ms/epoch (bmu %.2f, accumulate %.2f) -> %.3e samples*epochs/s"
-                  % (algo, n, d, gx * gy, kw, dt * 1e3, b, a, n / dt), flush=True)
+            print("[epoch %s] n=%d d=%d K=%d %s: %.2f ms/epoch (bmu+accumulate %.2f) -> %.3e samples*epochs/s"
+                  % (algo, n, d, gx * gy, kw, dt * 1e3, b, n / dt), flush=True)
 
 
 if __name__ == "__main__":

@@ -17,8 +17,14 @@
 //   warp 0      TMA producer   X chunk [128 x 32] + W'hi/W'lo chunks [256 x 32], SWIZZLE_128B
 //   warp 1      MMA issuer     tcgen05.mma.kind::tf32, M=128 N=256 K=8, accumulators in TMEM (2 x 256 cols)
 //   warps 2-5   converter      X chunk -> hi (in place) and lo, generic->async proxy fence
-//   warps 6-9   epilogue       tcgen05.ld 32 columns at a time, + bias, running (min, argmin) per row
+//   warps 6-9   epilogue       tcgen05.ld 32 columns at a time, + bias, running (min, argmin) per row;
+//                              then (fused K3) S[bmu] += x for the tile's 128 rows, re-read from L2
 // The (n, K) score matrix lives only in TMEM.
+//
+// Fused accumulate (acc.S != nullptr): once a 128-row tile has its BMUs, the epilogue warps add the
+// tile's rows into the (K, D) accumulator with red.global.add.v4.f32 — the rows were just streamed
+// through L2 by TMA, so HBM sees X once per epoch — and bump exact int32 counts; the last CTA to
+// finish folds the counts into the fp32 c vector (fp32 increments of 1 are lost above 2^24).
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -129,11 +135,22 @@ __device__ __forceinline__ float tf32_rna_dev(float v) {
     return __uint_as_float(r);
 }
 
+// arguments of the fused accumulate; S == nullptr turns it off
+struct FusedAcc {
+    const float *X;      // samples (row stride ldx), the same matrix map_x describes
+    int64_t ldx;
+    int d, k;
+    float *S, *c;        // (K, D) sums and (K) counts, accumulated into
+    int *cnt;            // k ints, zero on entry, zero again on exit
+    unsigned int *done;  // ticket counter, zero on entry and exit
+    int vec;             // rows are 16-byte aligned and d % 4 == 0: 128-bit path
+};
+
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 bmu_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
               const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
               int64_t n, int num_m_tiles, int num_n_tiles, int num_k_blocks,
-              int32_t *__restrict__ bmu_out, float *__restrict__ best_out) {
+              int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -148,6 +165,8 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
     auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * STAGES + 4);
+    __shared__ int bmu_s[BM];          // BMUs of the current tile, shared among the epilogue warps
+    __shared__ unsigned int last_cta;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -267,8 +286,48 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
             }
             const int64_t row = (int64_t)mt * BM + row_in_tile;
             if (row < n) {
-                bmu_out[row] = bidx;
+                if (bmu_out) bmu_out[row] = bidx;
                 if (best_out) best_out[row] = best;
+            }
+            if (acc.S != nullptr) {
+                // ---- fused K3: S[bmu[r], :] += X[r, :] for the rows of this tile -----------------
+                bmu_s[row_in_tile] = (row < n) ? bidx : -1;
+                if (row < n) atomicAdd(acc.cnt + bidx, 1);
+                asm volatile("bar.sync 2, 128;" ::: "memory");
+                const int64_t row0 = (int64_t)mt * BM;
+                const int wq = warp - EPI_WARP0;                 // this warp takes rows wq, wq+4, ...
+                if (acc.vec) {
+                    const int d4 = acc.d >> 2;
+                    // 32 lanes cover `rows_per_pass` rows x d4 float4 at a time (d4 < 32), or one row in strips
+                    if (d4 <= 32) {
+                        const int lanes_per_row = d4 <= 1 ? 1 : d4 <= 2 ? 2 : d4 <= 4 ? 4 : d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
+                        const int rows_per_pass = 32 / lanes_per_row;
+                        const int sub = lane / lanes_per_row, c4 = lane % lanes_per_row;
+                        for (int r = wq * rows_per_pass + sub; r < BM; r += 4 * rows_per_pass) {
+                            const int b = bmu_s[r];
+                            if (b >= 0 && c4 < d4) {
+                                const float4 v = __ldg(reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx) + c4);
+                                red_add_v4(acc.S + (int64_t)b * acc.d + c4 * 4, v);
+                            }
+                        }
+                    } else {
+                        for (int r = wq; r < BM; r += 4) {
+                            const int b = bmu_s[r];
+                            if (b < 0) continue;
+                            const float4 *xr = reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx);
+                            float *sr = acc.S + (int64_t)b * acc.d;
+                            for (int c4 = lane; c4 < d4; c4 += 32) red_add_v4(sr + c4 * 4, __ldg(xr + c4));
+                        }
+                    }
+                } else {
+                    for (int r = wq; r < BM; r += 4) {
+                        const int b = bmu_s[r];
+                        if (b < 0) continue;
+                        for (int cc = lane; cc < acc.d; cc += 32)
+                            atomicAdd(acc.S + (int64_t)b * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
+                    }
+                }
+                asm volatile("bar.sync 2, 128;" ::: "memory");   // bmu_s is rewritten by the next tile
             }
         }
     }
@@ -276,6 +335,23 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
     tc_fence_before();
     __syncthreads();
     if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
+
+    if (acc.S != nullptr) {
+        // the last CTA to get here folds the exact integer counts into the fp32 vector c
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last_cta = (atomicAdd(acc.done, 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (last_cta) {
+            __threadfence();
+            for (int i = threadIdx.x; i < acc.k; i += blockDim.x) {
+                const int v = atomicExch(acc.cnt + i, 0);
+                if (v) atomicAdd(acc.c + i, (float)v);
+            }
+            if (threadIdx.x == 0) *acc.done = 0u;
+        }
+    }
 }
 
 // ---- host side -----------------------------------------------------------------
@@ -316,7 +392,7 @@ inline bool shape_ok(const float *X, int64_t n, int d, int64_t ldx) {
 }
 
 inline int launch_bmu_tc(const float *X, int64_t n, int d, int64_t ldx, int k, const WsLayout &L, uint8_t *ws,
-                         int32_t *bmu, float *best, int sm_count, cudaStream_t st) {
+                         int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
     SOM_REQUIRE(shape_ok(X, n, d, ldx), SOM_E_SHAPE,
                 "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
     CUtensorMap mx, mhi, mlo;
@@ -333,8 +409,13 @@ inline int launch_bmu_tc(const float *X, int64_t n, int d, int64_t ldx, int k, c
     const int num_n_tiles = L.k_pad / BN;
     const int num_k_blocks = L.d_pad / BK;
     const int grid = num_m_tiles < sm_count ? num_m_tiles : sm_count;
+    FusedAcc acc;
+    acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = S; acc.c = c;
+    acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
+    acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
+    acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
     bmu_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off),
-                                                         n, num_m_tiles, num_n_tiles, num_k_blocks, bmu, best);
+                                                         n, num_m_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
     return check_cuda(cudaGetLastError(), "bmu_tc_kernel launch");
 }
 

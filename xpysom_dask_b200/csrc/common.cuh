@@ -25,6 +25,8 @@ struct WsLayout {
     size_t bias_off;  // k_pad floats: additive bias of the tensor-core epilogue (+inf on padding)
     size_t whi_off;   // k_pad x d_pad floats: TF32 "hi" part of the scaled codebook
     size_t wlo_off;   // k_pad x d_pad floats: TF32 "lo" part
+    size_t cnt_off;   // k_pad int32: exact per-BMU counts of the fused kernel (zero between launches)
+    size_t done_off;  // one uint32: CTAs-finished ticket of the fused kernel (zero between launches)
     size_t total;
 };
 
@@ -37,6 +39,8 @@ __host__ inline WsLayout ws_layout(int k, int d) {
     L.bias_off = off; off += round_up((size_t)L.k_pad * 4, 1024);
     L.whi_off = off;  off += round_up((size_t)L.k_pad * L.d_pad * 4, 1024);
     L.wlo_off = off;  off += round_up((size_t)L.k_pad * L.d_pad * 4, 1024);
+    L.cnt_off = off;  off += round_up((size_t)L.k_pad * 4, 1024);
+    L.done_off = off; off += 1024;
     L.total = off;
     return L;
 }

@@ -88,7 +88,7 @@ constexpr int NB_M = 64, NB_N = 64, NB_K = 16, NB_THREADS = 256;
 
 __global__ void __launch_bounds__(NB_THREADS)
 neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__restrict__ c,
-                   float *__restrict__ num, float *__restrict__ den) {
+                   float *__restrict__ num, float *__restrict__ den, int b_per_slice) {
     __shared__ __align__(16) float Hs[NB_K][NB_M + 4];
     __shared__ __align__(16) float Ss[NB_K][NB_N + 4];
     __shared__ float cs[NB_K];
@@ -112,11 +112,14 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
         for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
     float dacc[4] = {0.f, 0.f, 0.f, 0.f};
 
-    for (int b0 = 0; b0 < K; b0 += NB_K) {
+    // gridDim.z slices the reduction over BMUs so that small maps still fill the GPU
+    const int b_begin = blockIdx.z * b_per_slice;
+    const int b_end = min(K, b_begin + b_per_slice);
+    for (int b0 = b_begin; b0 < b_end; b0 += NB_K) {
         const int b = b0 + hb;
         float h4[4] = {0.f, 0.f, 0.f, 0.f}, s4[4] = {0.f, 0.f, 0.f, 0.f};
         float cb = 0.f;
-        if (b < K) {
+        if (b < b_end) {
             cb = __ldg(c + b);
             if (cb != 0.f) {   // an empty BMU contributes nothing (S[b] = 0 as well)
                 const int bi = b / P.gy, bj = b % P.gy;
@@ -158,9 +161,15 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
 #pragma unroll
         for (int bb = 0; bb < 4; ++bb) {
             const int col = n0 + tx * 4 + bb;
-            if (col < D) num[(int64_t)kk * D + col] = acc[a][bb] * P.eta;   // g = h * eta (xpysom.py:434)
+            if (col < D) {                                                    // g = h * eta (xpysom.py:434)
+                if (gridDim.z == 1) num[(int64_t)kk * D + col] = acc[a][bb] * P.eta;
+                else                atomicAdd(num + (int64_t)kk * D + col, acc[a][bb] * P.eta);
+            }
         }
-        if (tx == 0 && blockIdx.y == 0) den[kk] = dacc[a] * P.eta;
+        if (tx == 0 && blockIdx.y == 0) {
+            if (gridDim.z == 1) den[kk] = dacc[a] * P.eta;
+            else                atomicAdd(den + kk, dacc[a] * P.eta);
+        }
     }
 }
 
@@ -170,7 +179,7 @@ inline size_t neigh_table_floats(int gx, int gy) {
 
 inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, int d, int topology, int kind,
                               double sigma, double eta, double std_coeff, int compact,
-                              float *num, float *den, float *tables, cudaStream_t st) {
+                              float *num, float *den, float *tables, int sm_count, cudaStream_t st) {
     NeighParams P;
     P.gx = gx; P.gy = gy; P.d = d; P.topology = topology; P.kind = kind; P.compact = compact ? 1 : 0;
     // bubble and triangle use integer grid indices on both topologies (xpysom.py:266-269, 277-278)
@@ -188,8 +197,23 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
     int rc = check_cuda(cudaGetLastError(), "neigh_tables_kernel launch");
     if (rc) return rc;
     const int K = gx * gy;
-    dim3 grid((unsigned)ceil_div(K, NB_M), (unsigned)ceil_div(d, NB_N));
-    neigh_apply_kernel<<<grid, NB_THREADS, 0, st>>>(P, S, c, num, den);
+    const int gxy = (int)(ceil_div(K, NB_M) * ceil_div(d, NB_N));
+    int slices = (2 * sm_count + gxy - 1) / gxy;                 // aim for >= 2 CTAs per SM
+    const int max_slices = (int)ceil_div(K, 4 * NB_K);           // at least 64 BMUs per slice
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    const int b_per_slice = (int)round_up(ceil_div(K, slices), NB_K);
+    slices = (int)ceil_div(K, b_per_slice);
+    if (slices > 1) {
+        // num and den are contiguous in the host class's [num | den] buffer, but the ABI does not
+        // require it: clear them separately
+        rc = check_cuda(cudaMemsetAsync(num, 0, (size_t)K * d * sizeof(float), st), "memset num");
+        if (rc) return rc;
+        rc = check_cuda(cudaMemsetAsync(den, 0, (size_t)K * sizeof(float), st), "memset den");
+        if (rc) return rc;
+    }
+    dim3 grid((unsigned)ceil_div(K, NB_M), (unsigned)ceil_div(d, NB_N), (unsigned)slices);
+    neigh_apply_kernel<<<grid, NB_THREADS, 0, st>>>(P, S, c, num, den, b_per_slice);
     return check_cuda(cudaGetLastError(), "neigh_apply_kernel launch");
 }
 

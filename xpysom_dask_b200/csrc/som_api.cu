@@ -103,6 +103,7 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
     SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "prepare_codebook: workspace %zu < %zu bytes", ws_bytes, L.total);
     uint8_t *ws = static_cast<uint8_t *>(ws_dev);
     const bool split = dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE;
+    SOM_CUDA(cudaMemsetAsync(ws + L.cnt_off, 0, L.total - L.cnt_off, (cudaStream_t)stream));   // counts + ticket
     const int threads = 256, warps_per_block = threads / 32;
     const int blocks = (int)ceil_div(L.k_pad, warps_per_block);
     prepare_codebook_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
@@ -128,7 +129,8 @@ int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float 
     if (use == SOM_ALGO_TC_3XTF32) {
         SOM_REQUIRE(dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE, SOM_E_SHAPE,
                     "the tensor-core kernel computes contraction distances only (euclidean, cosine)");
-        return tc::launch_bmu_tc(x_dev, n, d, ldx, k, L, ws, bmu_dev, best_dev, di.sm, (cudaStream_t)stream);
+        return tc::launch_bmu_tc(x_dev, n, d, ldx, k, L, ws, bmu_dev, best_dev, nullptr, nullptr, di.sm,
+                                 (cudaStream_t)stream);
     }
     SOM_REQUIRE(use == SOM_ALGO_SIMT_FP32, SOM_E_BADARG, "bmu: unknown algo %d", algo);
     return launch_bmu_simt(x_dev, n, d, ldx, w_dev, k, dist_kind, p, reinterpret_cast<const float *>(ws + L.aux_off),
@@ -149,9 +151,21 @@ int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const
 int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k,
                               int dist_kind, float p, int algo, float *s_dev, float *c_dev, int32_t *bmu_dev,
                               void *ws_dev, size_t ws_bytes, void *stream) {
-    SOM_REQUIRE(n >= 0 && k > 0 && d > 0, SOM_E_BADARG, "epoch_accumulate: bad argument");
+    SOM_REQUIRE(n >= 0 && k > 0 && d > 0 && ldx >= d, SOM_E_BADARG, "epoch_accumulate: bad argument");
     if (n == 0) return 0;
+    SOM_REQUIRE(x_dev && w_dev && s_dev && c_dev && ws_dev, SOM_E_BADARG, "epoch_accumulate: NULL pointer");
+    SOM_REQUIRE(known_dist(dist_kind), SOM_E_BADARG, "epoch_accumulate: unknown distance kind %d", dist_kind);
     const WsLayout L = ws_layout(k, d);
+    if (pick_algo(algo, dist_kind, x_dev, n, d, ldx) == SOM_ALGO_TC_3XTF32 &&
+        (dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE)) {
+        // one kernel: contraction + argmin + per-BMU sums (X read from HBM once)
+        SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "epoch_accumulate: workspace %zu < %zu bytes", ws_bytes, L.total);
+        DevInfo di;
+        int rc = device_info(di);
+        if (rc) return rc;
+        return tc::launch_bmu_tc(x_dev, n, d, ldx, k, L, static_cast<uint8_t *>(ws_dev), bmu_dev, nullptr, s_dev, c_dev,
+                                 di.sm, (cudaStream_t)stream);
+    }
     int32_t *bmu = bmu_dev;
     if (!bmu) {
         const size_t need = L.total + (size_t)round_up(n * 4, 1024);
@@ -180,8 +194,11 @@ int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy,
                 SOM_E_SHAPE, "mexican_hat with compact_support broadcasts (n,gx)*(n,gy) in the reference "
                 "(neighborhoods.py:69-71): needs gx == gy");
     SOM_REQUIRE(sigma != 0.0 && std_coeff != 0.0, SOM_E_BADARG, "neigh_apply: sigma and std_coeff must be non-zero");
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
     return launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support,
-                              num_dev, den_dev, tables_dev, (cudaStream_t)stream);
+                              num_dev, den_dev, tables_dev, di.sm, (cudaStream_t)stream);
 }
 
 int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev, int k, int d, void *stream) {

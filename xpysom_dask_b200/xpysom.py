@@ -222,14 +222,12 @@ class XPySom:
             sc.zero_()
             eng.prepare_codebook(w, dist_kind, p, ws)
             if prof is not None:
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                 ev[0].record()
-            eng.bmu(x, w, dist_kind, p, algo, ws, bmu_out=bmu)          # K1/K2: distance + argmin
+            # K1/K2 + K3: distance + argmin + per-BMU sums (one fused kernel on the tensor-core path)
+            eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu)
             if prof is not None:
                 ev[1].record()
-            eng.accumulate(x, bmu, K, S, c)                             # K3: S[bmu] += x, c[bmu] += 1
-            if prof is not None:
-                ev[2].record()
                 prof.append(ev)
             if group is not None:
                 import torch.distributed as dist
