@@ -1,0 +1,367 @@
+// K1 (v2): CTA-pair tensor-core distance contraction + fused BMU argmin + fused per-BMU accumulate.
+//
+// Same contract as bmu_tc.cuh (score = x . w' + bias minimised over neurons, 3xTF32 split, the
+// (n, K) score matrix lives only in TMEM) re-tiled for the two-SM tensor-core mode of sm_100a:
+//
+//   * thread-block cluster of 2 CTAs on one TPC, tcgen05.mma.cta_group::2, UMMA tile M=256 N=256
+//     K=8: each CTA owns 128 sample rows (its own TMEM accumulators, 2 x 256 columns) and stages
+//     only HALF of every W' tile (128 neurons), so the codebook traffic L2->SMEM and the SMEM reads
+//     of the B operand are halved with respect to the one-CTA kernel;
+//   * 3-stage ring of 64 KB stages (X chunk hi | lo, W'hi half, W'lo half), SWIZZLE_128B;
+//   * W' tiles arrive by TMA with the .cta_group::2 form: both CTAs' loads complete on the
+//     leader CTA's mbarrier; X chunks complete on a local mbarrier that the converter waits on;
+//   * tcgen05.commit ... .multicast::cluster releases the stage / publishes the accumulator in
+//     both CTAs at once;
+//   * four extra "scatter" warps per CTA take the finished BMUs of a 128-row tile and issue the
+//     S[bmu] += x reductions (red.global.add.v4.f32), so the ~1 element/clk/SM RED throughput
+//     overlaps with the MMA and the argmin epilogue instead of stalling them.
+//
+// Warp roles per CTA (448 threads): 0 TMA producer | 1 MMA issuer (leader CTA only) + TMEM alloc |
+// 2-5 converter (X -> TF32 hi/lo) | 6-9 epilogue (TMEM -> argmin) | 10-13 scatter (accumulate).
+#pragma once
+#include <cuda.h>
+#include "common.cuh"
+#include "bmu_tc.cuh"
+
+namespace somb200 {
+namespace tc2 {
+
+using tc::FusedAcc;
+using tc::smem_u32;
+
+constexpr int BM = 128;        // sample rows per CTA (256 per pair)
+constexpr int BN = 256;        // neurons per accumulator tile (UMMA N)
+constexpr int BNH = 128;       // neurons staged by each CTA
+constexpr int BK = 32, STAGES = 3, UMMA_K = 8;
+constexpr int A_BYTES = BM * BK * 4;     // 16 KB
+constexpr int BH_BYTES = BNH * BK * 4;   // 16 KB
+constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;   // 64 KB
+constexpr int NUM_THREADS = 448;
+constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6, SCAT_WARP0 = 10;
+constexpr int NUM_BARS = 4 * STAGES + 4 + 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 4 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
+
+// ---- cluster / 2-SM PTX wrappers -------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
+    return r;
+}
+// arrive on a barrier that may live in the peer CTA (shared::cluster address), release at cluster scope
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                 "selp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_cluster(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_cluster(bar, parity)) {
+        if (clock64() - t0 > 4000000000LL) {
+            printf("som_b200(tc2): mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
+                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+// TMA load whose completion bytes go to the LEADER CTA's mbarrier (peer bit cleared)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap *map, int c0, int c1, uint32_t bar) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+                 :: "r"(dst), "l"(map), "r"(c0), "r"(c1), "r"(bar & 0xFEFFFFFFu) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t slot_smem, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(bar), "h"((uint16_t)3) : "memory");
+}
+
+// UMMA tile of the pair: M = 256 (two CTAs x 128 lanes), N = 256
+constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+               const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
+               int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
+               int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+
+    float    *bias_s = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                       // [2][BN]
+    int      *bmu_s  = reinterpret_cast<int *>(smem + STAGES * STAGE_BYTES + 2 * BN * 4);            // [2][BM]
+    uint64_t *bars   = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + 2 * BN * 4 + 2 * BM * 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto xfull_bar  = [&](int s) { return bar0 + 8u * s; };                     // local: X chunk landed
+    auto bfull_bar  = [&](int s) { return bar0 + 8u * (STAGES + s); };          // leader: both W' halves landed
+    auto ready_bar  = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };      // leader: both converters done
+    auto empty_bar  = [&](int s) { return bar0 + 8u * (3 * STAGES + s); };      // local: stage consumed (multicast commit)
+    auto tfull_bar  = [&](int a) { return bar0 + 8u * (4 * STAGES + a); };      // local: accumulator complete (multicast commit)
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (4 * STAGES + 2 + a); };  // leader: both epilogues drained it
+    auto bfullq_bar = [&](int b) { return bar0 + 8u * (4 * STAGES + 4 + b); };  // local: BMUs of a tile published
+    auto bemptyq_bar = [&](int b) { return bar0 + 8u * (4 * STAGES + 6 + b); }; // local: scatter warps done with them
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + NUM_BARS);
+    __shared__ unsigned int last_cta;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const bool fused = acc.S != nullptr;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) {
+            tc::mbar_init(xfull_bar(s), 1); tc::mbar_init(bfull_bar(s), 1);
+            tc::mbar_init(ready_bar(s), 256); tc::mbar_init(empty_bar(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 256);
+            tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
+        }
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
+    }
+    if (warp == 1) tmem_alloc_2sm(smem_u32((const void *)tmem_slot), 512);
+    tc::tc_fence_before();
+    cluster_sync();                      // barriers of BOTH CTAs initialised before anyone signals the peer
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (each CTA loads its own rows and its half of W') ===========
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
+                for (int nt = 0; nt < num_n_tiles; ++nt)
+                    for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                        const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                        tc::mbar_wait(empty_bar(s), ph ^ 1);
+                        const uint32_t st = smem_base + s * STAGE_BYTES;
+                        if (leader) tc::mbar_expect_tx(bfull_bar(s), 4 * BH_BYTES);   // hi+lo halves of both CTAs
+                        tc::mbar_expect_tx(xfull_bar(s), A_BYTES);
+                        tc::tma_load_2d(st, &map_x, kb * BK, pt * (2 * BM) + (int)rank * BM, xfull_bar(s));
+                        tma_load_2d_2sm(st + 2 * A_BYTES,            &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                        tma_load_2d_2sm(st + 2 * A_BYTES + BH_BYTES, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                    }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer: one thread of the LEADER CTA drives both tensor cores ========
+        if (leader && lane == 0) {
+            uint32_t it = 0, acc_it = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
+                for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
+                    const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
+                    mbar_wait_cluster(tempty_bar(a), aph ^ 1);
+                    tc::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+                    for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                        const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                        mbar_wait_cluster(bfull_bar(s), ph);
+                        mbar_wait_cluster(ready_bar(s), ph);
+                        tc::tc_fence_after();
+                        const uint32_t st = smem_base + s * STAGE_BYTES;
+                        const uint64_t a_hi = tc::make_smem_desc(st), a_lo = tc::make_smem_desc(st + A_BYTES);
+                        const uint64_t b_hi = tc::make_smem_desc(st + 2 * A_BYTES);
+                        const uint64_t b_lo = tc::make_smem_desc(st + 2 * A_BYTES + BH_BYTES);
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            const uint64_t off = (uint64_t)((kk * UMMA_K * 4) >> 4);
+                            umma_tf32_2sm(tmem_d, a_lo + off, b_hi + off, kIdesc2, (kb | kk) != 0);
+                            umma_tf32_2sm(tmem_d, a_hi + off, b_lo + off, kIdesc2, 1);
+                            umma_tf32_2sm(tmem_d, a_hi + off, b_hi + off, kIdesc2, 1);
+                        }
+                        umma_commit_2sm(empty_bar(s));
+                    }
+                    umma_commit_2sm(tfull_bar(a));
+                }
+        }
+    } else if (warp < EPI_WARP0) {
+        // ===================== converter: split the local X chunk into TF32 hi / lo =====================
+        const int t = threadIdx.x - CONV_WARP0 * 32;
+        uint32_t it = 0;
+        for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
+            for (int nt = 0; nt < num_n_tiles; ++nt)
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                    const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                    tc::mbar_wait(xfull_bar(s), ph);
+                    float4 *ahi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
+                    float4 *alo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + A_BYTES);
+#pragma unroll
+                    for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
+                        const int e = t + 128 * i;
+                        const float4 v = ahi[e];
+                        float4 h, l;
+                        h.x = tc::tf32_rna_dev(v.x); h.y = tc::tf32_rna_dev(v.y); h.z = tc::tf32_rna_dev(v.z); h.w = tc::tf32_rna_dev(v.w);
+                        l.x = tc::tf32_rna_dev(v.x - h.x); l.y = tc::tf32_rna_dev(v.y - h.y);
+                        l.z = tc::tf32_rna_dev(v.z - h.z); l.w = tc::tf32_rna_dev(v.w - h.w);
+                        ahi[e] = h; alo[e] = l;
+                    }
+                    tc::fence_proxy_async();
+                    mbar_arrive_cluster(map_to_cta(ready_bar(s), 0));       // the leader's barrier counts both CTAs
+                }
+    } else if (warp < SCAT_WARP0) {
+        // ===================== epilogue: TMEM -> registers -> running argmin =====================
+        const int q = warp & 3;
+        const int e = threadIdx.x - EPI_WARP0 * 32;
+        const int row_in_tile = q * 32 + lane;
+        uint32_t acc_it = 0, tile_it = 0;
+        for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
+            float best = INFINITY; int bidx = 0;
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
+                const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
+                float *bs = bias_s + a * BN;
+                bs[e] = __ldg(bias + (int64_t)nt * BN + e);
+                bs[e + 128] = __ldg(bias + (int64_t)nt * BN + e + 128);
+                asm volatile("bar.sync 1, 128;" ::: "memory");
+                tc::mbar_wait(tfull_bar(a), aph);
+                tc::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
+#pragma unroll 1
+                for (int c = 0; c < BN / 32; ++c) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(taddr + c * 32, v);
+                    tc::tmem_ld_wait();
+                    const int colbase = nt * BN + c * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]) + bs[c * 32 + j];
+                        if (sc < best) { best = sc; bidx = colbase + j; }
+                    }
+                }
+                tc::tc_fence_before();
+                mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+            }
+            const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
+            if (row < n) {
+                if (bmu_out) bmu_out[row] = bidx;
+                if (best_out) best_out[row] = best;
+            }
+            if (fused) {          // hand the tile's BMUs to the scatter warps (double buffered)
+                const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
+                tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
+                bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
+                tc::mbar_arrive(bfullq_bar(b));
+            }
+        }
+    } else {
+        // ===================== scatter: S[bmu[r], :] += X[r, :], cnt[bmu[r]] += 1 =====================
+        if (fused) {
+            const int t = threadIdx.x - SCAT_WARP0 * 32;
+            const int wq = warp - SCAT_WARP0;
+            const int d4 = acc.d >> 2;
+            uint32_t tile_it = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
+                const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
+                tc::mbar_wait(bfullq_bar(b), bph);
+                const int *bm = bmu_s + b * BM;
+                const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
+                { const int mine = bm[t]; if (mine >= 0) atomicAdd(acc.cnt + mine, 1); }
+                if (acc.vec) {
+                    if (d4 <= 32) {
+                        const int lanes_per_row = d4 <= 1 ? 1 : d4 <= 2 ? 2 : d4 <= 4 ? 4 : d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
+                        const int rows_per_pass = 32 / lanes_per_row;
+                        const int sub = lane / lanes_per_row, c4 = lane % lanes_per_row;
+                        for (int r = wq * rows_per_pass + sub; r < BM; r += 4 * rows_per_pass) {
+                            const int bb = bm[r];
+                            if (bb >= 0 && c4 < d4) {
+                                const float4 v = __ldg(reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx) + c4);
+                                red_add_v4(acc.S + (int64_t)bb * acc.d + c4 * 4, v);
+                            }
+                        }
+                    } else {
+                        for (int r = wq; r < BM; r += 4) {
+                            const int bb = bm[r];
+                            if (bb < 0) continue;
+                            const float4 *xr = reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx);
+                            float *sr = acc.S + (int64_t)bb * acc.d;
+                            for (int c4 = lane; c4 < d4; c4 += 32) red_add_v4(sr + c4 * 4, __ldg(xr + c4));
+                        }
+                    }
+                } else {
+                    for (int r = wq; r < BM; r += 4) {
+                        const int bb = bm[r];
+                        if (bb < 0) continue;
+                        for (int cc = lane; cc < acc.d; cc += 32)
+                            atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
+                    }
+                }
+                tc::mbar_arrive(bemptyq_bar(b));
+            }
+        }
+    }
+
+    __syncwarp();
+    tc::tc_fence_before();
+    cluster_sync();                      // the peer may still be signalling this CTA's barriers / reading its SMEM
+    if (warp == 1) { tc::tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
+
+    if (fused) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last_cta = (atomicAdd(acc.done, 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (last_cta) {
+            __threadfence();
+            for (int i = threadIdx.x; i < acc.k; i += blockDim.x) {
+                const int v = atomicExch(acc.cnt + i, 0);
+                if (v) atomicAdd(acc.c + i, (float)v);
+            }
+            if (threadIdx.x == 0) *acc.done = 0u;
+        }
+    }
+}
+
+inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, const WsLayout &L, uint8_t *ws,
+                          int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
+    SOM_REQUIRE(tc::shape_ok(X, n, d, ldx), SOM_E_SHAPE,
+                "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
+    CUtensorMap mx, mhi, mlo;
+    int rc;
+    if ((rc = tc::make_map_2d(&mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)ldx * 4, BK, BM))) return rc;
+    if ((rc = tc::make_map_2d(&mhi, ws + L.whi_off, (uint64_t)L.d_pad, (uint64_t)L.k_pad, (uint64_t)L.d_pad * 4, BK, BNH))) return rc;
+    if ((rc = tc::make_map_2d(&mlo, ws + L.wlo_off, (uint64_t)L.d_pad, (uint64_t)L.k_pad, (uint64_t)L.d_pad * 4, BK, BNH))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int num_pair_tiles = (int)ceil_div(n, 2 * BM);
+    const int num_n_tiles = L.k_pad / BN;
+    const int num_k_blocks = L.d_pad / BK;
+    int pairs = sm_count / 2;
+    if (pairs > num_pair_tiles) pairs = num_pair_tiles;
+    if (pairs < 1) pairs = 1;
+    FusedAcc acc;
+    acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = S; acc.c = c;
+    acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
+    acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
+    acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+    bmu_tc2_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off),
+                                                               n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+    return check_cuda(cudaGetLastError(), "bmu_tc2_kernel launch");
+}
+
+}  // namespace tc2
+}  // namespace somb200

@@ -3,11 +3,13 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <cstdlib>
 #include <vector>
 
 #include "common.cuh"
 #include "bmu_simt.cuh"
 #include "bmu_tc.cuh"
+#include "bmu_tc2.cuh"
 #include "accumulate.cuh"
 #include "neigh.cuh"
 #include "misc.cuh"
@@ -47,6 +49,19 @@ static int device_info(DevInfo &out) {
     out = cache[dev];
     SOM_REQUIRE(out.cc >= 100, SOM_E_NODEVICE, "libsom_b200 needs an sm_100a device, found cc %d", out.cc);
     return 0;
+}
+
+// The CTA-pair kernel (bmu_tc2) is the product path; SOM_B200_TC_V1=1 selects the one-CTA kernel (A/B runs).
+static bool use_tc_v1() {
+    static int v = -1;
+    if (v < 0) { const char *e = getenv("SOM_B200_TC_V1"); v = (e && e[0] == '1') ? 1 : 0; }
+    return v == 1;
+}
+
+static int launch_tc(const float *X, int64_t n, int d, int64_t ldx, int k, const WsLayout &L, uint8_t *ws,
+                     int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
+    if (use_tc_v1()) return tc::launch_bmu_tc(X, n, d, ldx, k, L, ws, bmu, best, S, c, sm_count, st);
+    return tc2::launch_bmu_tc2(X, n, d, ldx, k, L, ws, bmu, best, S, c, sm_count, st);
 }
 
 static bool known_dist(int k) { return k >= SOM_DIST_EUCLIDEAN && k <= SOM_DIST_NORM_P; }
@@ -129,8 +144,7 @@ int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float 
     if (use == SOM_ALGO_TC_3XTF32) {
         SOM_REQUIRE(dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE, SOM_E_SHAPE,
                     "the tensor-core kernel computes contraction distances only (euclidean, cosine)");
-        return tc::launch_bmu_tc(x_dev, n, d, ldx, k, L, ws, bmu_dev, best_dev, nullptr, nullptr, di.sm,
-                                 (cudaStream_t)stream);
+        return launch_tc(x_dev, n, d, ldx, k, L, ws, bmu_dev, best_dev, nullptr, nullptr, di.sm, (cudaStream_t)stream);
     }
     SOM_REQUIRE(use == SOM_ALGO_SIMT_FP32, SOM_E_BADARG, "bmu: unknown algo %d", algo);
     return launch_bmu_simt(x_dev, n, d, ldx, w_dev, k, dist_kind, p, reinterpret_cast<const float *>(ws + L.aux_off),
@@ -163,8 +177,8 @@ int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
         DevInfo di;
         int rc = device_info(di);
         if (rc) return rc;
-        return tc::launch_bmu_tc(x_dev, n, d, ldx, k, L, static_cast<uint8_t *>(ws_dev), bmu_dev, nullptr, s_dev, c_dev,
-                                 di.sm, (cudaStream_t)stream);
+        return launch_tc(x_dev, n, d, ldx, k, L, static_cast<uint8_t *>(ws_dev), bmu_dev, nullptr, s_dev, c_dev, di.sm,
+                         (cudaStream_t)stream);
     }
     int32_t *bmu = bmu_dev;
     if (!bmu) {
