@@ -129,6 +129,43 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // instruction descriptor: D=f32 (bit4), A=B=tf32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
 constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
 
+// Running argmin of the epilogue.  A single (best, index) pair would make every one of the K compares
+// wait for the previous one (FSETP -> FSEL latency per element, ~2x the MMA time of a D=64 tile);
+// EPI_ACC independent pairs over interleaved columns keep the ALU pipe busy instead.  Each pair sees
+// its columns in increasing order with a strict <, the final lexicographic merge restores numpy's
+// first-minimum rule.
+constexpr int EPI_ACC = 8;
+struct RunMin {
+    float v[EPI_ACC];
+    int   i[EPI_ACC];
+    __device__ __forceinline__ void reset() {
+#pragma unroll
+        for (int a = 0; a < EPI_ACC; ++a) { v[a] = INFINITY; i[a] = 0x7fffffff; }
+    }
+    // 32 accumulator columns (TMEM registers) + their bias (shared memory, 16-byte aligned)
+    __device__ __forceinline__ void chunk(const uint32_t (&acc)[32], const float *bias32, int colbase) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = b4[j4];
+            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                const float sc = __uint_as_float(acc[j]) + bb[e];
+                const int a = j % EPI_ACC;
+                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
+            }
+        }
+    }
+    __device__ __forceinline__ void result(float &best, int &bidx) const {
+        best = v[0]; bidx = i[0];
+#pragma unroll
+        for (int a = 1; a < EPI_ACC; ++a) argmin_merge(best, bidx, v[a], i[a]);
+        if (bidx == 0x7fffffff) bidx = 0;      // every score was +inf / NaN: numpy's argmin would say 0
+    }
+};
+
 __device__ __forceinline__ float tf32_rna_dev(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -259,7 +296,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
         const int row_in_tile = q * 32 + lane;
         uint32_t acc_it = 0;
         for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
-            float best = INFINITY; int bidx = 0;
+            RunMin rm; rm.reset();
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                 const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
                 float *bs = bias_s + a * BN;
@@ -274,16 +311,13 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
                     tmem_ld_wait();
-                    const int colbase = nt * BN + c * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sc = __uint_as_float(v[j]) + bs[c * 32 + j];
-                        if (sc < best) { best = sc; bidx = colbase + j; }   // strict <, increasing k: first minimum wins
-                    }
+                    rm.chunk(v, bs + c * 32, nt * BN + c * 32);
                 }
                 tc_fence_before();
                 mbar_arrive(tempty_bar(a));
             }
+            float best; int bidx;
+            rm.result(best, bidx);
             const int64_t row = (int64_t)mt * BM + row_in_tile;
             if (row < n) {
                 if (bmu_out) bmu_out[row] = bidx;

@@ -227,7 +227,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int row_in_tile = q * 32 + lane;
         uint32_t acc_it = 0, tile_it = 0;
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
-            float best = INFINITY; int bidx = 0;
+            tc::RunMin rm; rm.reset();
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                 const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
                 float *bs = bias_s + a * BN;
@@ -242,16 +242,13 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait();
-                    const int colbase = nt * BN + c * 32;
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sc = __uint_as_float(v[j]) + bs[c * 32 + j];
-                        if (sc < best) { best = sc; bidx = colbase + j; }
-                    }
+                    rm.chunk(v, bs + c * 32, nt * BN + c * 32);
                 }
                 tc::tc_fence_before();
                 mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
             }
+            float best; int bidx;
+            rm.result(best, bidx);
             const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
             if (row < n) {
                 if (bmu_out) bmu_out[row] = bidx;
