@@ -112,6 +112,16 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                  : "r"(taddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait::ld that also "touches" the destination registers, so the compiler cannot schedule their
+// consumers above the wait
+__device__ __forceinline__ void tmem_ld_wait_dep(uint32_t (&v)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
+                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]),
+                   "+r"(v[16]), "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]),
+                   "+r"(v[24]), "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+                 :: "memory");
+}
 
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (sm_100 format):
 //   [0,14)  start address >> 4      [16,30) leading byte offset >> 4 (ignored for swizzled K-major; 1)
@@ -165,6 +175,23 @@ struct RunMin {
         if (bidx == 0x7fffffff) bidx = 0;      // every score was +inf / NaN: numpy's argmin would say 0
     }
 };
+
+// Drain one accumulator tile (NCHUNK x 32 columns) into the running argmin.  TMEM loads are double
+// buffered in registers: the load of chunk c+1 is in flight while chunk c is compared.
+template <int NCHUNK>
+__device__ __forceinline__ void drain_accumulator(RunMin &rm, uint32_t taddr, const float *bs, int colbase) {
+    uint32_t va[32], vb[32];
+    tmem_ld32(taddr, va);
+#pragma unroll 1
+    for (int c = 0; c < NCHUNK; c += 2) {
+        tmem_ld_wait_dep(va);
+        tmem_ld32(taddr + (c + 1) * 32, vb);
+        rm.chunk(va, bs + c * 32, colbase + c * 32);
+        tmem_ld_wait_dep(vb);
+        if (c + 2 < NCHUNK) tmem_ld32(taddr + (c + 2) * 32, va);
+        rm.chunk(vb, bs + (c + 1) * 32, colbase + (c + 1) * 32);
+    }
+}
 
 __device__ __forceinline__ float tf32_rna_dev(float v) {
     uint32_t r;
@@ -306,13 +333,7 @@ bmu_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__
                 mbar_wait(tfull_bar(a), aph);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c * 32, v);
-                    tmem_ld_wait();
-                    rm.chunk(v, bs + c * 32, nt * BN + c * 32);
-                }
+                drain_accumulator<BN / 32>(rm, taddr, bs, nt * BN);
                 tc_fence_before();
                 mbar_arrive(tempty_bar(a));
             }

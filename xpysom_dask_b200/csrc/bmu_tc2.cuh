@@ -237,13 +237,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 tc::mbar_wait(tfull_bar(a), aph);
                 tc::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-#pragma unroll 1
-                for (int c = 0; c < BN / 32; ++c) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(taddr + c * 32, v);
-                    tc::tmem_ld_wait();
-                    rm.chunk(v, bs + c * 32, nt * BN + c * 32);
-                }
+                tc::drain_accumulator<BN / 32>(rm, taddr, bs, nt * BN);
                 tc::tc_fence_before();
                 mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
             }
