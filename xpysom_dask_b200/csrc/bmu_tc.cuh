@@ -152,12 +152,15 @@ struct RunMin {
 #pragma unroll
         for (int a = 0; a < EPI_ACC; ++a) { v[a] = INFINITY; i[a] = 0x7fffffff; }
     }
-    // 32 accumulator columns (TMEM registers) + their bias (shared memory, 16-byte aligned)
+    // 32 accumulator columns (TMEM registers) + their bias (shared or global memory, 16-byte aligned)
     __device__ __forceinline__ void chunk(const uint32_t (&acc)[32], const float *bias32, int colbase) {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+        float4 bq[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) bq[j4] = b4[j4];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = b4[j4];
+            const float4 b = bq[j4];
             const float bb[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {

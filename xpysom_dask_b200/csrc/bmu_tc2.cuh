@@ -16,8 +16,9 @@
 //     S[bmu] += x reductions (red.global.add.v4.f32), so the ~1 element/clk/SM RED throughput
 //     overlaps with the MMA and the argmin epilogue instead of stalling them.
 //
-// Warp roles per CTA (448 threads): 0 TMA producer | 1 MMA issuer (leader CTA only) + TMEM alloc |
-// 2-5 converter (X -> TF32 hi/lo) | 6-9 epilogue (TMEM -> argmin) | 10-13 scatter (accumulate).
+// Warp roles per CTA (576 threads): 0 TMA producer | 1 MMA issuer (leader CTA only) + TMEM alloc |
+// 2-5 converter (X -> TF32 hi/lo) | 6-13 epilogue (TMEM -> argmin; two warps per TMEM lane quarter,
+// each taking half of the 256 columns, so one hides the other's TMEM/L1 latency) | 14-17 scatter.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -36,10 +37,12 @@ constexpr int BK = 32, STAGES = 3, UMMA_K = 8;
 constexpr int A_BYTES = BM * BK * 4;     // 16 KB
 constexpr int BH_BYTES = BNH * BK * 4;   // 16 KB
 constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;   // 64 KB
-constexpr int NUM_THREADS = 448;
-constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6, SCAT_WARP0 = 10;
+constexpr int NUM_THREADS = 576;
+constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6, SCAT_WARP0 = 14;
+constexpr int EPI_THREADS = 256;
 constexpr int NUM_BARS = 4 * STAGES + 4 + 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 4 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
+// stages | merge buffers [2][BM] (float + int) | bmu hand-off [2][BM] | barriers | tmem slot | align slack
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
 
 // ---- cluster / 2-SM PTX wrappers -------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -51,9 +54,10 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
     asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(saddr), "r"(rank));
     return r;
 }
-// arrive on a barrier that may live in the peer CTA (shared::cluster address), release at cluster scope
+// arrive on a barrier that may live in the peer CTA (shared::cluster address).  Default semantics, as
+// CUTLASS's ClusterBarrier::arrive(cta_id): an explicit .release.cluster compiles to MEMBAR.ALL.GPU.
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
@@ -109,9 +113,10 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-    float    *bias_s = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                       // [2][BN]
-    int      *bmu_s  = reinterpret_cast<int *>(smem + STAGES * STAGE_BYTES + 2 * BN * 4);            // [2][BM]
-    uint64_t *bars   = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + 2 * BN * 4 + 2 * BM * 4);
+    float    *mrg_v  = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                       // [2][BM]
+    int      *mrg_i  = reinterpret_cast<int *>(smem + STAGES * STAGE_BYTES + 2 * BM * 4);            // [2][BM]
+    int      *bmu_s  = reinterpret_cast<int *>(smem + STAGES * STAGE_BYTES + 2 * BM * 8);            // [2][BM]
+    uint64_t *bars   = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4);
     const uint32_t bar0 = smem_u32(bars);
     auto xfull_bar  = [&](int s) { return bar0 + 8u * s; };                     // local: X chunk landed
     auto bfull_bar  = [&](int s) { return bar0 + 8u * (STAGES + s); };          // leader: both W' halves landed
@@ -136,7 +141,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             tc::mbar_init(ready_bar(s), 256); tc::mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 256);
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS);
             tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
         }
         tc::fence_barrier_init();
@@ -222,37 +227,49 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 }
     } else if (warp < SCAT_WARP0) {
         // ===================== epilogue: TMEM -> registers -> running argmin =====================
+        // warp w: TMEM lane quarter q = w % 4 (hardware rule), column half h = (w - EPI_WARP0) / 4
         const int q = warp & 3;
-        const int e = threadIdx.x - EPI_WARP0 * 32;
+        const int h = (warp - EPI_WARP0) >> 2;
         const int row_in_tile = q * 32 + lane;
         uint32_t acc_it = 0, tile_it = 0;
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
             tc::RunMin rm; rm.reset();
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                 const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
-                float *bs = bias_s + a * BN;
-                bs[e] = __ldg(bias + (int64_t)nt * BN + e);
-                bs[e + 128] = __ldg(bias + (int64_t)nt * BN + e + 128);
-                asm volatile("bar.sync 1, 128;" ::: "memory");
+                const int col0 = nt * BN + h * (BN / 2);
+                const float *bs = bias + col0;            // read through L1 (uniform address per warp)
                 tc::mbar_wait(tfull_bar(a), aph);
                 tc::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-                tc::drain_accumulator<BN / 32>(rm, taddr, bs, nt * BN);
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
+#pragma unroll 1
+                for (int c = 0; c < BN / 2 / 32; ++c) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(taddr + c * 32, v);
+                    tc::tmem_ld_wait_dep(v);
+                    rm.chunk(v, bs + c * 32, col0 + c * 32);
+                }
                 tc::tc_fence_before();
                 mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
             }
             float best; int bidx;
             rm.result(best, bidx);
-            const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
-            if (row < n) {
-                if (bmu_out) bmu_out[row] = bidx;
-                if (best_out) best_out[row] = best;
-            }
-            if (fused) {          // hand the tile's BMUs to the scatter warps (double buffered)
-                const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
-                tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
-                bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
-                tc::mbar_arrive(bfullq_bar(b));
+            // merge the two column halves of each row (double-buffered hand-off through shared memory)
+            const int mb = (tile_it & 1) * BM;
+            if (h == 1) { mrg_v[mb + row_in_tile] = best; mrg_i[mb + row_in_tile] = bidx; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (h == 0) {
+                argmin_merge(best, bidx, mrg_v[mb + row_in_tile], mrg_i[mb + row_in_tile]);
+                const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
+                if (row < n) {
+                    if (bmu_out) bmu_out[row] = bidx;
+                    if (best_out) best_out[row] = best;
+                }
+                if (fused) {          // hand the tile's BMUs to the scatter warps (double buffered)
+                    const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
+                    tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
+                    bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
+                    tc::mbar_arrive(bfullq_bar(b));
+                }
             }
         }
     } else {
