@@ -61,7 +61,9 @@ enum som_topology { SOM_TOPO_RECTANGULAR = 0, SOM_TOPO_HEXAGONAL = 1 }; /* xpyso
 enum som_algo {
     SOM_ALGO_AUTO      = 0, /* tensor-core kernel when the shape allows, else SIMT */
     SOM_ALGO_SIMT_FP32 = 1, /* shared-memory tiled SIMT, plain fp32 FMA chains */
-    SOM_ALGO_TC_3XTF32 = 2  /* tcgen05 TF32 MMA, 3-term split (fp32-accurate), TMA staged */
+    SOM_ALGO_TC_3XTF32 = 2, /* tcgen05 kind::tf32 MMA, 3-term hi/lo split (fp32-accurate), TMA staged */
+    SOM_ALGO_TC_3XF16  = 3  /* tcgen05 kind::f16 MMA at twice the TF32 rate: fp16 hi/lo split of exactly
+                               power-of-two-scaled operands, same 22-bit accuracy; needs xscale_dev */
 };
 
 /* negative return codes */
@@ -80,6 +82,11 @@ int som_b200_device_info(int *sm_count, int *cc, size_t *smem_per_block_optin);
  * for a codebook of K neurons x D features (prepared operand copies, |w|^2). */
 size_t som_b200_workspace_bytes(int k, int d);
 
+/* Per-row power-of-two scales of the samples for SOM_ALGO_TC_3XF16: xscale_dev (n floats) receives
+ * 2^a_r with max_c |x[r,c]| * 2^a_r in [2^14, 2^15).  One pass over X; valid as long as X is
+ * unchanged (the host class computes it once per upload, not per epoch). */
+int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, void *stream);
+
 /* Q: per-epoch codebook preparation.  Replaces the |w|^2 cache of
  * xpysom.py:529-539 and, for the tensor-core kernel, writes the split
  * (hi/lo TF32) operand copies of W into the workspace.  Must be called after
@@ -92,7 +99,9 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
  * is never materialised.  bmu_dev (n) receives flat indices.  best_dev may be
  * NULL; otherwise it receives the kernel's winning score (distance up to the
  * row-constant terms the argmin does not need). */
-int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx,
+/* xscale_dev: output of som_b200_prepare_samples, or NULL (then SOM_ALGO_AUTO never picks the fp16
+ * kernel and SOM_ALGO_TC_3XF16 is rejected). */
+int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float *xscale_dev,
                  const float *w_dev, int k, int dist_kind, float p, int algo,
                  int32_t *bmu_dev, float *best_dev,
                  void *ws_dev, size_t ws_bytes, void *stream);
@@ -108,7 +117,7 @@ int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
  * — the unit of distributed work (`_update` on one Dask block, xpysom.py:551).
  * bmu_dev may be NULL if the caller does not want the indices; then
  * ws must also hold n int32 (see som_b200_shard_workspace_bytes). */
-int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
+int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const float *xscale_dev,
                               const float *w_dev, int k, int dist_kind, float p, int algo,
                               float *s_dev, float *c_dev, int32_t *bmu_dev,
                               void *ws_dev, size_t ws_bytes, void *stream);

@@ -36,7 +36,10 @@ class OracleEngine:
     def prepare_codebook(self, w, dist_kind, p, ws):
         pass
 
-    def bmu(self, x, w, dist_kind, p, algo, ws, bmu_out=None, best_out=None):
+    def prepare_samples(self, x):
+        return None
+
+    def bmu(self, x, w, dist_kind, p, algo, ws, bmu_out=None, best_out=None, xscale=None):
         k, d = w.shape
         spec = so.SomSpec(gx=k, gy=1, dim=d, activation_distance="euclidean", p=p)
         spec.activation_distance = _DIST[dist_kind]
@@ -52,7 +55,7 @@ class OracleEngine:
         s.view(k, -1).add_(torch.from_numpy(S.astype(np.float32)))
         c.add_(torch.from_numpy(cc.astype(np.float32)))
 
-    def epoch_accumulate(self, x, w, dist_kind, p, algo, s, c, ws, bmu_out=None):
+    def epoch_accumulate(self, x, w, dist_kind, p, algo, s, c, ws, bmu_out=None, xscale=None):
         bmu = self.bmu(x, w, dist_kind, p, algo, ws, bmu_out=bmu_out)
         self.accumulate(x, bmu, w.shape[0], s, c)
 

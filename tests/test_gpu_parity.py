@@ -30,7 +30,8 @@ def _gpu_bmu(eng, x, w, dist, p, algo):
     wd = torch.from_numpy(np.ascontiguousarray(w.reshape(-1, w.shape[-1]), dtype=np.float32)).cuda()
     ws = eng.workspace(0, wd.shape[0], wd.shape[1])
     eng.prepare_codebook(wd, _lib.DIST[dist], p, ws)
-    bmu = eng.bmu(xd, wd, _lib.DIST[dist], p, _lib.ALGO[algo], ws)
+    xs = eng.prepare_samples(xd) if algo in ("tc16", "auto") else None
+    bmu = eng.bmu(xd, wd, _lib.DIST[dist], p, _lib.ALGO[algo], ws, xscale=xs)
     torch.cuda.synchronize()
     return bmu.cpu().numpy()
 
@@ -49,7 +50,7 @@ BMU_SHAPES = [
 
 @pytest.mark.parametrize("n,d,gx,gy", BMU_SHAPES)
 @pytest.mark.parametrize("dist", ["euclidean", "cosine"])
-@pytest.mark.parametrize("algo", ["simt", "tc"])
+@pytest.mark.parametrize("algo", ["simt", "tc", "tc16"])
 def test_bmu_contraction_distances(eng, n, d, gx, gy, dist, algo):
     x = U.blobs(n, d, seed=n + d)
     spec = so.SomSpec(gx=gx, gy=gy, dim=d, activation_distance=dist, random_seed=d)
@@ -79,6 +80,25 @@ def test_bmu_simt_all_distances(eng, n, d, gx, gy, dist, p):
     bmu = _gpu_bmu(eng, x, w, dist, p, "simt")
     r = U.bmu_parity(ref_spec, x.astype(np.float64) if dist == "norm_p" and p == 2.5 else x, w if p != 2.5 else w.astype(np.float64), bmu)
     print("\n[bmu %s p=%g n=%d d=%d] near-tie %.2e mismatch %.2e" % (dist, p, n, d, r["near_tie_rate"], r["mismatch_rate"]))
+    assert r["bad"] == 0, r
+
+
+@pytest.mark.parametrize("algo", ["tc", "tc16"])
+def test_bmu_wide_dynamic_range(eng, algo):
+    """Rows and neurons whose magnitudes span 12 orders of magnitude, plus zero rows: the per-row /
+    per-neuron power-of-two scaling must keep the fp16 split as accurate as the TF32 one."""
+    rng = np.random.RandomState(3)
+    n, d, gx, gy = 4000, 96, 16, 16
+    x = U.blobs(n, d, seed=5)
+    x *= (10.0 ** rng.uniform(-6, 6, size=(n, 1))).astype(np.float32)      # per-row scale
+    x[::500] = 0.0                                                           # zero samples
+    x[:, ::7] *= 1e-4                                                        # tiny features
+    spec = so.SomSpec(gx=gx, gy=gy, dim=d, random_seed=1)
+    w = U.uniform(gx * gy, d, 2).reshape(gx, gy, d) * (10.0 ** rng.uniform(-6, 6, size=(gx, gy, 1))).astype(np.float32)
+    w[3, 3] = 0.0
+    bmu = _gpu_bmu(eng, x, w, "euclidean", 2.0, algo)
+    r = U.bmu_parity(spec, x, w, bmu)
+    print("\n[bmu %s wide range] near-tie %.2e mismatch %.2e worst %.2e" % (algo, r["near_tie_rate"], r["mismatch_rate"], r["worst_rel_gap"]))
     assert r["bad"] == 0, r
 
 
@@ -166,7 +186,7 @@ def test_neigh_apply_skips_empty_bmus(eng):
 EPOCHS = U.load_json("epochs.json")
 
 
-@pytest.mark.parametrize("algo", ["simt", "tc", "auto"])
+@pytest.mark.parametrize("algo", ["simt", "tc", "tc16", "auto"])
 @pytest.mark.parametrize("case", EPOCHS, ids=[c["name"] for c in EPOCHS])
 def test_epoch_teacher_forced_vs_reference(case, algo):
     """W_t from the reference -> one epoch on the GPU -> compare with the reference's W_{t+1}."""
@@ -175,8 +195,8 @@ def test_epoch_teacher_forced_vs_reference(case, algo):
     name = case["name"]
     spec = U.spec_from_case(case)
     dist = case["kwargs"].get("activation_distance", "euclidean")
-    if algo == "tc" and dist not in ("euclidean", "cosine"):
-        pytest.skip("tensor-core kernel: contraction distances only")
+    if algo in ("tc", "tc16") and dist not in ("euclidean", "cosine"):
+        pytest.skip("tensor-core kernels: contraction distances only")
     data = g[name + "_data"]
     som = XPySom(case["gx"], case["gy"], case["D"], random_seed=case["seed"], algo=algo, **case["kwargs"])
     np.testing.assert_array_equal(som._weights, g[name + "_w_init"])      # bit-compatible init (xpysom.py:189-190)
@@ -280,7 +300,7 @@ def test_train_host_c_abi_matches_class():
     lib = _lib.load()
     n, d, gx, gy, T = 6000, 24, 10, 9, 4
     data = U.blobs(n, d, seed=9)
-    for algo in ("simt", "auto"):
+    for algo in ("simt", "auto", "tc16"):
         som = XPySom(gx, gy, d, random_seed=5, algo=algo)
         for t in range(T):
             w_t = np.ascontiguousarray(som._weights, dtype=np.float32)

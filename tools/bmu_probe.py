@@ -15,6 +15,7 @@ from xpysom_dask_b200.engine import CudaEngine             # noqa: E402
 n, d, k = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 fused = len(sys.argv) > 4 and sys.argv[4] == "fused"
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
+algo = sys.argv[6] if len(sys.argv) > 6 else "tc"
 eng = CudaEngine("cuda:0")
 g = torch.Generator(device="cuda").manual_seed(0)
 x = torch.rand(n, d, generator=g, device="cuda")
@@ -22,17 +23,18 @@ w = torch.rand(k, d, generator=g, device="cuda")
 ws = eng.workspace(0, k, d)
 eng.prepare_codebook(w, 0, 2.0, ws)
 bmu = eng.empty(n, dtype=torch.int32)
+xs = eng.prepare_samples(x) if algo in ("tc16", "auto") else None
 S, c = eng.zeros(k, d), eng.zeros(k)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(reps + 2):
     if i == 2:
         e0.record()
     if fused:
-        eng.epoch_accumulate(x, w, 0, 2.0, _lib.ALGO["tc"], S, c, ws, bmu_out=bmu)
+        eng.epoch_accumulate(x, w, 0, 2.0, _lib.ALGO[algo], S, c, ws, bmu_out=bmu, xscale=xs)
     else:
-        eng.bmu(x, w, 0, 2.0, _lib.ALGO["tc"], ws, bmu_out=bmu)
+        eng.bmu(x, w, 0, 2.0, _lib.ALGO[algo], ws, bmu_out=bmu, xscale=xs)
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
-print("n=%d d=%d K=%d fused=%s: %.3f ms, %.1f TFLOP/s algorithmic, %.3e elements/s"
+print(algo, "n=%d d=%d K=%d fused=%s: %.3f ms, %.1f TFLOP/s algorithmic, %.3e elements/s"
       % (n, d, k, fused, ms, 2.0 * n * k * d / ms / 1e9, n * k / ms * 1e3))

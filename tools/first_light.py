@@ -41,7 +41,8 @@ def stage_bmu(eng, algo, shapes, dist="euclidean"):
         ws = eng.workspace(0, k, d)
         eng.prepare_codebook(w, _lib.DIST[dist], 2.0, ws)
         best = eng.empty(n)
-        bmu = eng.bmu(x, w, _lib.DIST[dist], 2.0, _lib.ALGO[algo], ws, best_out=best)
+        xs = eng.prepare_samples(x) if algo == "tc16" else None
+        bmu = eng.bmu(x, w, _lib.DIST[dist], 2.0, _lib.ALGO[algo], ws, best_out=best, xscale=xs)
         torch.cuda.synchronize()
         # fp64 truth on a subset of rows
         m = min(n, 4096)
@@ -56,7 +57,7 @@ def stage_bmu(eng, algo, shapes, dist="euclidean"):
         mism = (bmu[:m].long() != truth)
         worst = gap[mism].max().item() if mism.any() else 0.0
         score_err = (best[:m].double() - dd.min(1).values).abs().max().item() if dist == "euclidean" else float("nan")
-        ms = ev_time(lambda: eng.bmu(x, w, _lib.DIST[dist], 2.0, _lib.ALGO[algo], ws, bmu_out=bmu))
+        ms = ev_time(lambda: eng.bmu(x, w, _lib.DIST[dist], 2.0, _lib.ALGO[algo], ws, bmu_out=bmu, xscale=xs))
         tf = 2.0 * n * k * d / (ms * 1e-3) / 1e12
         print("[%s %s] n=%d d=%d K=%d: mismatch vs fp64 %d/%d (worst rel gap %.2e), |score err| %.2e, %.3f ms, %.1f TFLOP/s algorithmic"
               % (algo, dist, n, d, k, int(mism.sum()), m, worst, score_err, ms, tf), flush=True)
@@ -70,7 +71,7 @@ def stage_epoch(eng):
                                (1_000_000, 128, 50, 50, dict(topology="hexagonal", neighborhood_function="mexican_hat",
                                                              activation_distance="cosine"))]:
         x = data(n, d, 3)
-        for algo in ("tc", "simt"):
+        for algo in ("tc16", "tc", "simt"):
             som = XPySom(gx, gy, d, random_seed=0, algo=algo, **kw)
             som.train(x, 100, iter_beg=0, iter_end=2)
             torch.cuda.synchronize()
@@ -92,6 +93,10 @@ if __name__ == "__main__":
     big = [(1_000_000, 64, 1024), (2_000_000, 16, 1600), (100_000, 784, 10_000), (500_000, 128, 2500)]
     if stage == "simt":
         stage_bmu(eng, "simt", small + big[:1])
+    elif stage == "tc16":
+        stage_bmu(eng, "tc16", small)
+        stage_bmu(eng, "tc16", small[:3], dist="cosine")
+        stage_bmu(eng, "tc16", big)
     elif stage == "tc":
         stage_bmu(eng, "tc", small)
         stage_bmu(eng, "tc", small[:3], dist="cosine")

@@ -24,12 +24,14 @@ SIGNATURES = {
     "som_b200_neigh_table_floats": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "som_b200_prepare_codebook": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
-    "som_b200_bmu": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int,
+    "som_b200_prepare_samples": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p,
+                                                ctypes.c_void_p]),
+    "som_b200_bmu": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, c_f32p, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_float, ctypes.c_int, c_i32p, c_f32p,
                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "som_b200_accumulate": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_i32p, ctypes.c_int,
                                            c_f32p, c_f32p, ctypes.c_void_p]),
-    "som_b200_epoch_accumulate": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p,
+    "som_b200_epoch_accumulate": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, c_f32p,
                                                  ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
                                                  c_f32p, c_f32p, c_i32p, ctypes.c_void_p, ctypes.c_size_t,
                                                  ctypes.c_void_p]),
@@ -60,7 +62,7 @@ DIST = {"euclidean": 0, "euclidean_no_opt": 0, "cosine": 1, "manhattan": 2, "man
         "chebyshev": 3, "norm_p": 4, "norm_p_no_opt": 4}
 NEIGH = {"gaussian": 0, "mexican_hat": 1, "bubble": 2, "triangle": 3}
 TOPO = {"rectangular": 0, "hexagonal": 1}
-ALGO = {"auto": 0, "simt": 1, "tc": 2}
+ALGO = {"auto": 0, "simt": 1, "tc": 2, "tc16": 3}
 
 _lib = None
 

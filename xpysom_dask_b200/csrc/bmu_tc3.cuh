@@ -1,0 +1,406 @@
+// K1 (v3): fp16-split tensor-core distance contraction + fused BMU argmin + fused accumulate.
+//
+// Same contract and CTA-pair structure as bmu_tc2.cuh, different arithmetic: kind::f16 MMAs run
+// at twice the kind::tf32 rate and fp16 carries the same 11-bit significand as TF32, so splitting
+// every fp32 operand into hi = rn_f16(v), lo = rn_f16(v - hi) and accumulating
+// lo*hi + hi*lo + hi*hi in fp32 (TMEM) keeps the 3xTF32 accuracy (|v - hi - lo| <= 2^-22 |v|) at
+// half the tensor-pipe time.  fp16's narrow exponent is handled by EXACT power-of-two scaling:
+//   x^ = x * 2^a_r   (per sample row, a_r from row_scale_kernel; max |x^| in [2^14, 2^15))
+//   w^ = w' * 2^b_k  (per neuron, from prepare_codebook_kernel)
+// and the epilogue minimises  acc * 2^-b_k + bias_k * 2^a_r  = 2^a_r (x . w'_k + bias_k), a positive
+// row-constant multiple of the score, so the argmin is unchanged.  Elements far below their row's
+// maximum fall into fp16's subnormal range and lose RELATIVE precision, but their absolute error
+// stays below 2^-39 of the row maximum, far inside the stated BMU epsilon.
+//
+// Operand staging (per CTA, 32 KB slots, SWIZZLE_128B, 64 features = 128 B of halves per row):
+//   A ring (3 slots): the raw fp32 X chunk [128 rows x 64 floats] lands by TMA (two 16 KB boxes);
+//       the converter warpgroup reads it into registers, synchronises, and overwrites the slot IN
+//       PLACE with the fp16 hi tile (first 16 KB) and lo tile (second 16 KB).
+//       When D <= 128 the A tiles of a 256-row tile stay RESIDENT across all neuron tiles
+//       (loaded and converted once per row tile); for larger D they stream once per neuron tile.
+//   B ring (3 slots): this CTA's half (128 neurons) of the W'hi and W'lo fp16 tiles.
+// 12 MMAs (M=256 N=256 K=16 over the CTA pair) per 64-feature block.
+//
+// Warp roles per CTA (640 threads): 0 B producer | 1 MMA issuer (leader) + TMEM alloc | 2 A producer |
+// 3 spare | 4-7 converter | 8-15 epilogue (two warps per TMEM lane quarter) | 16-19 scatter.
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include "common.cuh"
+#include "bmu_tc.cuh"
+#include "bmu_tc2.cuh"
+
+namespace somb200 {
+namespace tc3 {
+
+using tc::FusedAcc;
+using tc::smem_u32;
+using namespace tc2;   // cluster / 2-SM wrappers
+
+constexpr int BM = 128, BN = 256, BNH = 128;
+constexpr int BK = 64;                   // features per block: 128 bytes of fp16
+constexpr int UMMA_K = 16;
+constexpr int NA = 3, NB = 3;
+constexpr int SLOT_BYTES = 32 * 1024;    // A: raw fp32 [128 x 64] -> hi | lo ;  B: W'hi half | W'lo half
+constexpr int HALF_SLOT = 16 * 1024;
+constexpr int NUM_THREADS = 640;
+constexpr int APROD_WARP = 2, CONV_WARP0 = 4, EPI_WARP0 = 8, SCAT_WARP0 = 16;
+constexpr int EPI_THREADS = 256;
+constexpr int RESIDENT_MAX_KB = 2;       // D <= 128: X tiles resident across neuron tiles
+constexpr int NUM_BARS = 3 * NA + 2 * NB + 4 + 4;
+constexpr int SMEM_BYTES = (NA + NB) * SLOT_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
+
+__device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n\t.reg .pred p;\n\t"
+                 "setp.ne.b32 p, %4, 0;\n\t"
+                 "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// D = f32 (bit 4), A = B = f16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 over the pair)
+constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+
+// running argmin on the scaled scores: sc = acc * 2^-b_k + bias_k * 2^a_r
+struct RunMinScaled : tc::RunMin {
+    __device__ __forceinline__ void chunk(const uint32_t (&acc)[32], const float *bias32, const float *winv32,
+                                          float rs, int colbase) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+        const float4 *s4 = reinterpret_cast<const float4 *>(winv32);
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b = __ldg(b4 + j4), s = __ldg(s4 + j4);
+            const float bb[4] = {b.x, b.y, b.z, b.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                const float sc = fmaf(__uint_as_float(acc[j]), ss[e], bb[e] * rs);
+                const int a = j % tc::EPI_ACC;
+                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
+            }
+        }
+    }
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
+bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
+               const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
+               const float *__restrict__ wsinv, const float *__restrict__ xscale,
+               int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
+               int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    const uint32_t a_base = smem_base, b_base = smem_base + NA * SLOT_BYTES;
+    uint8_t *tail = smem + (NA + NB) * SLOT_BYTES;
+
+    float    *mrg_v = reinterpret_cast<float *>(tail);                   // [2][BM]
+    int      *mrg_i = reinterpret_cast<int *>(tail + 2 * BM * 4);        // [2][BM]
+    int      *bmu_s = reinterpret_cast<int *>(tail + 2 * BM * 8);        // [2][BM]
+    uint64_t *bars  = reinterpret_cast<uint64_t *>(tail + 2 * BM * 8 + 2 * BM * 4);
+    const uint32_t bar0 = smem_u32(bars);
+    auto afull_bar  = [&](int s) { return bar0 + 8u * s; };                       // local: raw X chunk landed
+    auto aready_bar = [&](int s) { return bar0 + 8u * (NA + s); };                // leader: both converters done
+    auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * NA + s); };            // local: A slot consumed
+    auto bfull_bar  = [&](int s) { return bar0 + 8u * (3 * NA + s); };            // leader: both W' halves landed
+    auto bempty_bar = [&](int s) { return bar0 + 8u * (3 * NA + NB + s); };       // local: B slot consumed
+    auto tfull_bar  = [&](int a) { return bar0 + 8u * (3 * NA + 2 * NB + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * NA + 2 * NB + 2 + a); };
+    auto bfullq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * NB + 4 + b); };
+    auto bemptyq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * NB + 6 + b); };
+    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + NUM_BARS);
+    __shared__ unsigned int last_cta;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const bool fused = acc.S != nullptr;
+    const bool resident = num_k_blocks <= RESIDENT_MAX_KB;   // A tiles live across the neuron tiles
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 256); tc::mbar_init(aempty_bar(s), 1); }
+        for (int s = 0; s < NB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
+        for (int a = 0; a < 2; ++a) {
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS);
+            tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
+        }
+        tc::fence_barrier_init();
+        tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
+    }
+    if (warp == 1) tmem_alloc_2sm(smem_u32((const void *)tmem_slot), 512);
+    tc::tc_fence_before();
+    cluster_sync();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== B producer: this CTA's half of W'hi / W'lo per (row tile, neuron tile, k block) ====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
+                for (int nt = 0; nt < num_n_tiles; ++nt)
+                    for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                        const int s = it % NB; const uint32_t ph = (it / NB) & 1;
+                        tc::mbar_wait(bempty_bar(s), ph ^ 1);
+                        const uint32_t st = b_base + s * SLOT_BYTES;
+                        if (leader) tc::mbar_expect_tx(bfull_bar(s), 2 * SLOT_BYTES);
+                        tma_load_2d_2sm(st,             &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                        tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                    }
+        }
+    } else if (warp == APROD_WARP) {
+        // ===================== A producer: raw fp32 X chunks [128 rows x 64 features] ==========================
+        if (lane == 0) {
+            uint32_t ia = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs) {
+                const int reps = resident ? 1 : num_n_tiles;
+                for (int rep = 0; rep < reps; ++rep)
+                    for (int kb = 0; kb < num_k_blocks; ++kb, ++ia) {
+                        const int s = ia % NA; const uint32_t ph = (ia / NA) & 1;
+                        tc::mbar_wait(aempty_bar(s), ph ^ 1);
+                        const uint32_t st = a_base + s * SLOT_BYTES;
+                        tc::mbar_expect_tx(afull_bar(s), SLOT_BYTES);
+                        const int row0 = pt * (2 * BM) + (int)rank * BM;
+                        tc::tma_load_2d(st,             &map_x, kb * BK,      row0, afull_bar(s));
+                        tc::tma_load_2d(st + HALF_SLOT, &map_x, kb * BK + 32, row0, afull_bar(s));
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA) ==========================================================
+        if (leader && lane == 0) {
+            uint32_t it = 0, acc_it = 0, tile_it = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it)
+                for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
+                    const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
+                    mbar_wait_cluster(tempty_bar(a), aph ^ 1);
+                    tc::tc_fence_after();
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+                    for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                        const uint32_t ia = resident ? (tile_it * (uint32_t)num_k_blocks + kb) : it;
+                        const int sa = ia % NA; const uint32_t pha = (ia / NA) & 1;
+                        const int sb = it % NB; const uint32_t phb = (it / NB) & 1;
+                        mbar_wait_cluster(aready_bar(sa), pha);       // hi/lo tiles of both CTAs written
+                        mbar_wait_cluster(bfull_bar(sb), phb);        // W' halves of both CTAs landed
+                        tc::tc_fence_after();
+                        const uint32_t sta = a_base + sa * SLOT_BYTES, stb = b_base + sb * SLOT_BYTES;
+                        const uint64_t a_hi = tc::make_smem_desc(sta), a_lo = tc::make_smem_desc(sta + HALF_SLOT);
+                        const uint64_t b_hi = tc::make_smem_desc(stb), b_lo = tc::make_smem_desc(stb + HALF_SLOT);
+#pragma unroll
+                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);    // +32 B along K
+                            umma_f16_2sm(tmem_d, a_lo + off, b_hi + off, kIdescF16, (kb | kk) != 0);
+                            umma_f16_2sm(tmem_d, a_hi + off, b_lo + off, kIdescF16, 1);
+                            umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, kIdescF16, 1);
+                        }
+                        umma_commit_2sm(bempty_bar(sb));
+                        if (!resident || nt == num_n_tiles - 1) umma_commit_2sm(aempty_bar(sa));
+                    }
+                    umma_commit_2sm(tfull_bar(a));
+                }
+        }
+    } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
+        // ===================== converter: raw fp32 -> scaled fp16 hi | lo, in place ==============================
+        const int t = threadIdx.x - CONV_WARP0 * 32;   // 0..127
+        uint32_t ia = 0;
+        for (int pt = pair; pt < num_pair_tiles; pt += num_pairs) {
+            const int reps = resident ? 1 : num_n_tiles;
+            const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
+            for (int rep = 0; rep < reps; ++rep)
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++ia) {
+                    const int s = ia % NA; const uint32_t ph = (ia / NA) & 1;
+                    tc::mbar_wait(afull_bar(s), ph);
+                    uint8_t *slot = smem + s * SLOT_BYTES;
+                    const float4 *raw = reinterpret_cast<const float4 *>(slot);
+                    float4 v[16];
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) v[i] = raw[t + 128 * i];     // linear: conflict-free
+                    asm volatile("bar.sync 2, 128;" ::: "memory");              // everyone has read the slot
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        // raw layout: two SWIZZLE_128B boxes of [128 rows x 32 floats]; float4 index e
+                        const int e = t + 128 * i;
+                        const int box = e >> 10, r = (e & 1023) >> 3, cpos = e & 7;
+                        const int j = cpos ^ (r & 7);                 // logical 16-byte chunk within the 32 floats
+                        const int k0 = box * 32 + j * 4;              // first of 4 consecutive features
+                        const int64_t grow = row0 + r;
+                        const float rs = grow < n ? __ldg(xscale + grow) : 1.f;
+                        const float x0 = v[i].x * rs, x1 = v[i].y * rs, x2 = v[i].z * rs, x3 = v[i].w * rs;
+                        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+                        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y);
+                        const __half2 l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+                        // fp16 tile [128 rows x 64 halves], SWIZZLE_128B: 16-byte chunk (k0 / 8) ^ (r % 8)
+                        const int off = r * 128 + (((k0 >> 3) ^ (r & 7)) << 4) + ((k0 & 7) << 1);
+                        uint2 hv, lv;
+                        hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
+                        lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
+                        *reinterpret_cast<uint2 *>(slot + off) = hv;
+                        *reinterpret_cast<uint2 *>(slot + HALF_SLOT + off) = lv;
+                    }
+                    tc::fence_proxy_async();
+                    mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
+                }
+        }
+    } else if (warp >= EPI_WARP0 && warp < SCAT_WARP0) {
+        // ===================== epilogue: TMEM -> registers -> running argmin ====================================
+        const int q = warp & 3;
+        const int h = (warp - EPI_WARP0) >> 2;
+        const int row_in_tile = q * 32 + lane;
+        uint32_t acc_it = 0, tile_it = 0;
+        for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
+            const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
+            const float rs = row < n ? __ldg(xscale + row) : 1.f;
+            RunMinScaled rm; rm.reset();
+            for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
+                const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
+                const int col0 = nt * BN + h * (BN / 2);
+                tc::mbar_wait(tfull_bar(a), aph);
+                tc::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
+#pragma unroll 1
+                for (int c = 0; c < BN / 2 / 32; ++c) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(taddr + c * 32, v);
+                    tc::tmem_ld_wait_dep(v);
+                    rm.chunk(v, bias + col0 + c * 32, wsinv + col0 + c * 32, rs, col0 + c * 32);
+                }
+                tc::tc_fence_before();
+                mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+            }
+            float best; int bidx;
+            rm.result(best, bidx);
+            const int mb = (tile_it & 1) * BM;
+            if (h == 1) { mrg_v[mb + row_in_tile] = best; mrg_i[mb + row_in_tile] = bidx; }
+            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (h == 0) {
+                argmin_merge(best, bidx, mrg_v[mb + row_in_tile], mrg_i[mb + row_in_tile]);
+                if (row < n) {
+                    if (bmu_out) bmu_out[row] = bidx;
+                    if (best_out) best_out[row] = best / rs;          // undo the row scale (exact)
+                }
+                if (fused) {
+                    const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
+                    tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
+                    bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
+                    tc::mbar_arrive(bfullq_bar(b));
+                }
+            }
+        }
+    } else if (warp >= SCAT_WARP0) {
+        // ===================== scatter: S[bmu[r], :] += X[r, :], cnt[bmu[r]] += 1 ================================
+        if (fused) {
+            const int t = threadIdx.x - SCAT_WARP0 * 32;
+            const int wq = warp - SCAT_WARP0;
+            const int d4 = acc.d >> 2;
+            uint32_t tile_it = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
+                const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
+                tc::mbar_wait(bfullq_bar(b), bph);
+                const int *bm = bmu_s + b * BM;
+                const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
+                { const int mine = bm[t]; if (mine >= 0) atomicAdd(acc.cnt + mine, 1); }
+                if (acc.vec) {
+                    if (d4 <= 32) {
+                        const int lanes_per_row = d4 <= 1 ? 1 : d4 <= 2 ? 2 : d4 <= 4 ? 4 : d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
+                        const int rows_per_pass = 32 / lanes_per_row;
+                        const int sub = lane / lanes_per_row, c4 = lane % lanes_per_row;
+                        for (int r = wq * rows_per_pass + sub; r < BM; r += 4 * rows_per_pass) {
+                            const int bb = bm[r];
+                            if (bb >= 0 && c4 < d4) {
+                                const float4 v = __ldg(reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx) + c4);
+                                red_add_v4(acc.S + (int64_t)bb * acc.d + c4 * 4, v);
+                            }
+                        }
+                    } else {
+                        for (int r = wq; r < BM; r += 4) {
+                            const int bb = bm[r];
+                            if (bb < 0) continue;
+                            const float4 *xr = reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx);
+                            float *sr = acc.S + (int64_t)bb * acc.d;
+                            for (int c4 = lane; c4 < d4; c4 += 32) red_add_v4(sr + c4 * 4, __ldg(xr + c4));
+                        }
+                    }
+                } else {
+                    for (int r = wq; r < BM; r += 4) {
+                        const int bb = bm[r];
+                        if (bb < 0) continue;
+                        for (int cc = lane; cc < acc.d; cc += 32)
+                            atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
+                    }
+                }
+                tc::mbar_arrive(bemptyq_bar(b));
+            }
+        }
+    }
+
+    __syncwarp();
+    tc::tc_fence_before();
+    cluster_sync();
+    if (warp == 1) { tc::tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
+
+    if (fused) {
+        if (threadIdx.x == 0) {
+            __threadfence();
+            last_cta = (atomicAdd(acc.done, 1u) == gridDim.x - 1) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (last_cta) {
+            __threadfence();
+            for (int i = threadIdx.x; i < acc.k; i += blockDim.x) {
+                const int v = atomicExch(acc.cnt + i, 0);
+                if (v) atomicAdd(acc.c + i, (float)v);
+            }
+            if (threadIdx.x == 0) *acc.done = 0u;
+        }
+    }
+}
+
+inline int make_map_2d_f16(CUtensorMap *m, const void *base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
+                           uint32_t box_inner, uint32_t box_outer) {
+    tc::EncodeTiledFn enc = tc::get_encode_fn();
+    SOM_REQUIRE(enc != nullptr, SOM_E_NODEVICE, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {row_stride_bytes};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    SOM_REQUIRE(r == CUDA_SUCCESS, SOM_E_SHAPE, "cuTensorMapEncodeTiled(f16) failed with CUresult %d", (int)r);
+    return 0;
+}
+
+inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const float *xscale, int k, const WsLayout &L,
+                          uint8_t *ws, int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
+    SOM_REQUIRE(tc::shape_ok(X, n, d, ldx), SOM_E_SHAPE,
+                "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
+    SOM_REQUIRE(xscale != nullptr, SOM_E_BADARG, "the fp16-split kernel needs the per-row scales (som_b200_prepare_samples)");
+    CUtensorMap mx, mhi, mlo;
+    int rc;
+    if ((rc = tc::make_map_2d(&mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)ldx * 4, 32, BM))) return rc;
+    if ((rc = make_map_2d_f16(&mhi, ws + L.w16hi_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, BNH))) return rc;
+    if ((rc = make_map_2d_f16(&mlo, ws + L.w16lo_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, BNH))) return rc;
+    static bool attr_set = false;
+    if (!attr_set) {
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        attr_set = true;
+    }
+    const int num_pair_tiles = (int)ceil_div(n, 2 * BM);
+    const int num_n_tiles = L.k_pad / BN;
+    const int num_k_blocks = L.d_pad64 / BK;
+    int pairs = sm_count / 2;
+    if (pairs > num_pair_tiles) pairs = num_pair_tiles;
+    if (pairs < 1) pairs = 1;
+    FusedAcc acc;
+    acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = S; acc.c = c;
+    acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
+    acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
+    acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+    bmu_tc3_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
+        mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off), reinterpret_cast<const float *>(ws + L.wsinv_off),
+        xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+    return check_cuda(cudaGetLastError(), "bmu_tc3_kernel launch");
+}
+
+}  // namespace tc3
+}  // namespace somb200

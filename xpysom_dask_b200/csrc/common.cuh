@@ -25,6 +25,10 @@ struct WsLayout {
     size_t bias_off;  // k_pad floats: additive bias of the tensor-core epilogue (+inf on padding)
     size_t whi_off;   // k_pad x d_pad floats: TF32 "hi" part of the scaled codebook
     size_t wlo_off;   // k_pad x d_pad floats: TF32 "lo" part
+    int    d_pad64;   // feature padding of the fp16 operand copies: one 128-byte swizzle row of halves
+    size_t w16hi_off; // k_pad x d_pad64 halves: fp16 "hi" part of the scaled codebook times 2^b_k
+    size_t w16lo_off; // k_pad x d_pad64 halves: fp16 "lo" part
+    size_t wsinv_off; // k_pad floats: 2^-b_k, the inverse of the per-neuron power-of-two scale
     size_t cnt_off;   // k_pad int32: exact per-BMU counts of the fused kernel (zero between launches)
     size_t done_off;  // one uint32: CTAs-finished ticket of the fused kernel (zero between launches)
     size_t total;
@@ -39,6 +43,10 @@ __host__ inline WsLayout ws_layout(int k, int d) {
     L.bias_off = off; off += round_up((size_t)L.k_pad * 4, 1024);
     L.whi_off = off;  off += round_up((size_t)L.k_pad * L.d_pad * 4, 1024);
     L.wlo_off = off;  off += round_up((size_t)L.k_pad * L.d_pad * 4, 1024);
+    L.d_pad64 = (int)round_up(d, 64);
+    L.w16hi_off = off; off += round_up((size_t)L.k_pad * L.d_pad64 * 2, 1024);
+    L.w16lo_off = off; off += round_up((size_t)L.k_pad * L.d_pad64 * 2, 1024);
+    L.wsinv_off = off; off += round_up((size_t)L.k_pad * 4, 1024);
     L.cnt_off = off;  off += round_up((size_t)L.k_pad * 4, 1024);
     L.done_off = off; off += 1024;
     L.total = off;
@@ -76,6 +84,16 @@ __device__ __forceinline__ double warp_sum(double v) {
 __device__ __forceinline__ void red_add_v4(float *addr, float4 v) {
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};"
                  :: "l"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+// power-of-two factor that brings a row whose largest magnitude is amax into [2^14, 2^15): the fp16
+// hi/lo split then keeps 22 significant bits of every element that matters (exact scaling, undone
+// exactly in the epilogue).  Zero / non-finite rows are left alone.
+__device__ __forceinline__ float pow2_scale_for(float amax) {
+    if (!(amax > 0.f) || !isfinite(amax)) return 1.f;
+    int a = 14 - ilogbf(amax);
+    a = a < -100 ? -100 : (a > 100 ? 100 : a);
+    return ldexpf(1.f, a);
 }
 
 // lexicographic (value, index) minimum: the first minimum wins, as numpy's argmin.

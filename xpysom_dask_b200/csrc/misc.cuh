@@ -1,6 +1,7 @@
 // Small kernels around the epoch: codebook preparation (Q), merge (M),
 // quantization error and the U-matrix.
 #pragma once
+#include <cuda_fp16.h>
 #include "common.cuh"
 
 namespace somb200 {
@@ -18,9 +19,13 @@ __device__ __forceinline__ float tf32_rna(float v) {
 //   bias[k] = additive term of the tensor-core epilogue: |w|^2 / 0, +inf on padding neurons
 //   whi/wlo = TF32 split of the SCALED codebook row (-2 w for euclidean: exact; -w/|w| for cosine),
 //             zero on padding, so that score = x . w' + bias is what both kernels minimise.
+//   w16hi/w16lo/wsinv = the same scaled row times 2^b_k (b_k brings its largest magnitude into
+//             [2^14, 2^15)) split into two fp16 numbers, and 2^-b_k for the epilogue.
 __global__ void prepare_codebook_kernel(const float *__restrict__ W, int k, int d, int dist_kind,
                                         int k_pad, int d_pad, float *__restrict__ aux, float *__restrict__ bias,
-                                        float *__restrict__ whi, float *__restrict__ wlo) {
+                                        float *__restrict__ whi, float *__restrict__ wlo,
+                                        int d_pad64, __half *__restrict__ w16hi, __half *__restrict__ w16lo,
+                                        float *__restrict__ wsinv) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= k_pad) return;
@@ -48,6 +53,37 @@ __global__ void prepare_codebook_kernel(const float *__restrict__ W, int k, int 
             whi[(int64_t)warp * d_pad + c] = hi;
             wlo[(int64_t)warp * d_pad + c] = lo;
         }
+    }
+    if (w16hi != nullptr) {
+        float amax = 0.f;
+        if (real)
+            for (int c = lane; c < d; c += 32) amax = fmaxf(amax, fabsf(W[(int64_t)warp * d + c] * scale));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        const float ps = pow2_scale_for(amax);
+        if (lane == 0) wsinv[warp] = 1.f / ps;          // exact: ps is a power of two
+        for (int c = lane; c < d_pad64; c += 32) {
+            float v = 0.f;
+            if (real && c < d) v = W[(int64_t)warp * d + c] * scale * ps;
+            const __half hi = __float2half_rn(v);
+            const __half lo = __float2half_rn(v - __half2float(hi));
+            w16hi[(int64_t)warp * d_pad64 + c] = hi;
+            w16lo[(int64_t)warp * d_pad64 + c] = lo;
+        }
+    }
+}
+
+// per-row power-of-two scale of the samples for the fp16-split kernel: xscale[r] = 2^a_r with
+// max_c |x[r,c]| * 2^a_r in [2^14, 2^15).  One warp per row; one HBM pass, done once per upload.
+__global__ void row_scale_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, float *__restrict__ xscale) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
+        float amax = 0.f;
+        for (int c = lane; c < d; c += 32) amax = fmaxf(amax, fabsf(__ldg(X + r * ldx + c)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+        if (lane == 0) xscale[r] = pow2_scale_for(amax);
     }
 }
 

@@ -10,6 +10,7 @@
 #include "bmu_simt.cuh"
 #include "bmu_tc.cuh"
 #include "bmu_tc2.cuh"
+#include "bmu_tc3.cuh"
 #include "accumulate.cuh"
 #include "neigh.cuh"
 #include "misc.cuh"
@@ -58,19 +59,26 @@ static bool use_tc_v1() {
     return v == 1;
 }
 
-static int launch_tc(const float *X, int64_t n, int d, int64_t ldx, int k, const WsLayout &L, uint8_t *ws,
-                     int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
+static int launch_tc(int use, const float *X, int64_t n, int d, int64_t ldx, const float *xscale, int k,
+                     const WsLayout &L, uint8_t *ws, int32_t *bmu, float *best, float *S, float *c, int sm_count,
+                     cudaStream_t st) {
+    if (use == SOM_ALGO_TC_3XF16)
+        return tc3::launch_bmu_tc3(X, n, d, ldx, xscale, k, L, ws, bmu, best, S, c, sm_count, st);
     if (use_tc_v1()) return tc::launch_bmu_tc(X, n, d, ldx, k, L, ws, bmu, best, S, c, sm_count, st);
     return tc2::launch_bmu_tc2(X, n, d, ldx, k, L, ws, bmu, best, S, c, sm_count, st);
 }
 
 static bool known_dist(int k) { return k >= SOM_DIST_EUCLIDEAN && k <= SOM_DIST_NORM_P; }
 
-// AUTO: the tensor-core kernel for the two contraction distances whenever TMA can address X.
-static int pick_algo(int algo, int dist_kind, const float *X, int64_t n, int d, int64_t ldx) {
+// AUTO: a tensor-core kernel for the two contraction distances whenever TMA can address X — the
+// fp16-split one when the row scales are available and D fills its 64-feature blocks reasonably,
+// the TF32 one (32-feature blocks) otherwise.
+static int pick_algo(int algo, int dist_kind, const float *X, int64_t n, int d, int64_t ldx, const float *xscale) {
     const bool contraction = dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE;
-    if (algo == SOM_ALGO_AUTO)
-        return (contraction && tc::shape_ok(X, n, d, ldx) && d >= 8) ? SOM_ALGO_TC_3XTF32 : SOM_ALGO_SIMT_FP32;
+    if (algo == SOM_ALGO_AUTO) {
+        if (!(contraction && tc::shape_ok(X, n, d, ldx) && d >= 8)) return SOM_ALGO_SIMT_FP32;
+        return (xscale != nullptr && d > 32) ? SOM_ALGO_TC_3XF16 : SOM_ALGO_TC_3XTF32;
+    }
     return algo;
 }
 
@@ -124,12 +132,25 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
     prepare_codebook_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
         w_dev, k, d, dist_kind, L.k_pad, L.d_pad, reinterpret_cast<float *>(ws + L.aux_off),
         reinterpret_cast<float *>(ws + L.bias_off), split ? reinterpret_cast<float *>(ws + L.whi_off) : nullptr,
-        split ? reinterpret_cast<float *>(ws + L.wlo_off) : nullptr);
+        split ? reinterpret_cast<float *>(ws + L.wlo_off) : nullptr, L.d_pad64,
+        split ? reinterpret_cast<__half *>(ws + L.w16hi_off) : nullptr,
+        split ? reinterpret_cast<__half *>(ws + L.w16lo_off) : nullptr, reinterpret_cast<float *>(ws + L.wsinv_off));
     return check_cuda(cudaGetLastError(), "prepare_codebook_kernel launch");
 }
 
-int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int dist_kind,
-                 float p, int algo, int32_t *bmu_dev, float *best_dev, void *ws_dev, size_t ws_bytes, void *stream) {
+int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, void *stream) {
+    SOM_REQUIRE(n >= 0 && d > 0 && ldx >= d, SOM_E_BADARG, "prepare_samples: bad argument");
+    if (n == 0) return 0;
+    SOM_REQUIRE(x_dev && xscale_dev, SOM_E_BADARG, "prepare_samples: NULL pointer");
+    int64_t blocks = ceil_div(n, 8);
+    if (blocks > 148 * 32) blocks = 148 * 32;
+    row_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, n, d, ldx, xscale_dev);
+    return check_cuda(cudaGetLastError(), "row_scale_kernel launch");
+}
+
+int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float *xscale_dev, const float *w_dev, int k,
+                 int dist_kind, float p, int algo, int32_t *bmu_dev, float *best_dev, void *ws_dev, size_t ws_bytes,
+                 void *stream) {
     SOM_REQUIRE(w_dev && ws_dev && bmu_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "bmu: bad argument");
     SOM_REQUIRE(known_dist(dist_kind), SOM_E_BADARG, "bmu: unknown distance kind %d", dist_kind);
     if (n == 0) return 0;
@@ -140,11 +161,12 @@ int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float 
     int rc = device_info(di);
     if (rc) return rc;
     uint8_t *ws = static_cast<uint8_t *>(ws_dev);
-    const int use = pick_algo(algo, dist_kind, x_dev, n, d, ldx);
-    if (use == SOM_ALGO_TC_3XTF32) {
+    const int use = pick_algo(algo, dist_kind, x_dev, n, d, ldx, xscale_dev);
+    if (use == SOM_ALGO_TC_3XTF32 || use == SOM_ALGO_TC_3XF16) {
         SOM_REQUIRE(dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE, SOM_E_SHAPE,
-                    "the tensor-core kernel computes contraction distances only (euclidean, cosine)");
-        return launch_tc(x_dev, n, d, ldx, k, L, ws, bmu_dev, best_dev, nullptr, nullptr, di.sm, (cudaStream_t)stream);
+                    "the tensor-core kernels compute contraction distances only (euclidean, cosine)");
+        return launch_tc(use, x_dev, n, d, ldx, xscale_dev, k, L, ws, bmu_dev, best_dev, nullptr, nullptr, di.sm,
+                         (cudaStream_t)stream);
     }
     SOM_REQUIRE(use == SOM_ALGO_SIMT_FP32, SOM_E_BADARG, "bmu: unknown algo %d", algo);
     return launch_bmu_simt(x_dev, n, d, ldx, w_dev, k, dist_kind, p, reinterpret_cast<const float *>(ws + L.aux_off),
@@ -162,23 +184,24 @@ int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const
     return launch_accumulate(x_dev, n, d, ldx, bmu_dev, k, s_dev, c_dev, di.sm, (cudaStream_t)stream);
 }
 
-int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k,
-                              int dist_kind, float p, int algo, float *s_dev, float *c_dev, int32_t *bmu_dev,
-                              void *ws_dev, size_t ws_bytes, void *stream) {
+int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const float *xscale_dev,
+                              const float *w_dev, int k, int dist_kind, float p, int algo, float *s_dev, float *c_dev,
+                              int32_t *bmu_dev, void *ws_dev, size_t ws_bytes, void *stream) {
     SOM_REQUIRE(n >= 0 && k > 0 && d > 0 && ldx >= d, SOM_E_BADARG, "epoch_accumulate: bad argument");
     if (n == 0) return 0;
     SOM_REQUIRE(x_dev && w_dev && s_dev && c_dev && ws_dev, SOM_E_BADARG, "epoch_accumulate: NULL pointer");
     SOM_REQUIRE(known_dist(dist_kind), SOM_E_BADARG, "epoch_accumulate: unknown distance kind %d", dist_kind);
     const WsLayout L = ws_layout(k, d);
-    if (pick_algo(algo, dist_kind, x_dev, n, d, ldx) == SOM_ALGO_TC_3XTF32 &&
+    const int use = pick_algo(algo, dist_kind, x_dev, n, d, ldx, xscale_dev);
+    if ((use == SOM_ALGO_TC_3XTF32 || use == SOM_ALGO_TC_3XF16) &&
         (dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE)) {
         // one kernel: contraction + argmin + per-BMU sums (X read from HBM once)
         SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "epoch_accumulate: workspace %zu < %zu bytes", ws_bytes, L.total);
         DevInfo di;
         int rc = device_info(di);
         if (rc) return rc;
-        return launch_tc(x_dev, n, d, ldx, k, L, static_cast<uint8_t *>(ws_dev), bmu_dev, nullptr, s_dev, c_dev, di.sm,
-                         (cudaStream_t)stream);
+        return launch_tc(use, x_dev, n, d, ldx, xscale_dev, k, L, static_cast<uint8_t *>(ws_dev), bmu_dev, nullptr, s_dev,
+                         c_dev, di.sm, (cudaStream_t)stream);
     }
     int32_t *bmu = bmu_dev;
     if (!bmu) {
@@ -187,7 +210,7 @@ int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
                     "epoch_accumulate: workspace %zu < %zu bytes (no bmu buffer given)", ws_bytes, need);
         bmu = reinterpret_cast<int32_t *>(static_cast<uint8_t *>(ws_dev) + L.total);
     }
-    int rc = som_b200_bmu(x_dev, n, d, ldx, w_dev, k, dist_kind, p, algo, bmu, nullptr, ws_dev, ws_bytes, stream);
+    int rc = som_b200_bmu(x_dev, n, d, ldx, xscale_dev, w_dev, k, dist_kind, p, algo, bmu, nullptr, ws_dev, ws_bytes, stream);
     if (rc) return rc;
     return som_b200_accumulate(x_dev, n, d, ldx, bmu, k, s_dev, c_dev, stream);
 }
@@ -249,9 +272,9 @@ int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_ho
     const int d = cfg->d, K = cfg->gx * cfg->gy;
     SOM_REQUIRE(d > 0 && K > 0 && ldx >= d, SOM_E_BADARG, "train_host: bad shape");
     struct Bufs {
-        float *x = nullptr, *w = nullptr, *sc = nullptr, *nd = nullptr, *tab = nullptr;
+        float *x = nullptr, *w = nullptr, *sc = nullptr, *nd = nullptr, *tab = nullptr, *xs = nullptr;
         uint8_t *ws = nullptr; cudaStream_t st = nullptr;
-        ~Bufs() { cudaFree(x); cudaFree(w); cudaFree(sc); cudaFree(nd); cudaFree(tab); cudaFree(ws); if (st) cudaStreamDestroy(st); }
+        ~Bufs() { cudaFree(x); cudaFree(w); cudaFree(sc); cudaFree(nd); cudaFree(tab); cudaFree(xs); cudaFree(ws); if (st) cudaStreamDestroy(st); }
     } b;
     const int64_t dld = round_up(d, 4);                 // device row stride: 16-byte aligned rows for TMA / float4
     const size_t ws_bytes = som_b200_shard_workspace_bytes(n, K, d);
@@ -262,15 +285,20 @@ int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_ho
     SOM_CUDA(cudaMalloc(&b.nd, ((size_t)K * d + K) * 4));
     SOM_CUDA(cudaMalloc(&b.tab, som_b200_neigh_table_floats(cfg->gx, cfg->gy) * 4));
     SOM_CUDA(cudaMalloc(&b.ws, ws_bytes));
+    SOM_CUDA(cudaMalloc(&b.xs, (size_t)n * 4));
     if (dld != d) SOM_CUDA(cudaMemsetAsync(b.x, 0, (size_t)n * dld * 4, b.st));
     SOM_CUDA(cudaMemcpy2DAsync(b.x, dld * 4, x_host, ldx * 4, (size_t)d * 4, (size_t)n, cudaMemcpyHostToDevice, b.st));
     SOM_CUDA(cudaMemcpyAsync(b.w, w_host, (size_t)K * d * 4, cudaMemcpyHostToDevice, b.st));
     float *S = b.sc, *c = b.sc + (size_t)K * d, *num = b.nd, *den = b.nd + (size_t)K * d;
+    {
+        int rc = som_b200_prepare_samples(b.x, n, d, dld, b.xs, b.st);
+        if (rc) return rc;
+    }
     for (int e = 0; e < n_epochs; ++e) {
         int rc;
         SOM_CUDA(cudaMemsetAsync(b.sc, 0, ((size_t)K * d + K) * 4, b.st));
         if ((rc = som_b200_prepare_codebook(b.w, K, d, cfg->dist_kind, cfg->p, b.ws, ws_bytes, b.st))) return rc;
-        if ((rc = som_b200_epoch_accumulate(b.x, n, d, dld, b.w, K, cfg->dist_kind, cfg->p, cfg->algo, S, c, nullptr,
+        if ((rc = som_b200_epoch_accumulate(b.x, n, d, dld, b.xs, b.w, K, cfg->dist_kind, cfg->p, cfg->algo, S, c, nullptr,
                                             b.ws, ws_bytes, b.st))) return rc;
         if ((rc = som_b200_neigh_apply(S, c, cfg->gx, cfg->gy, d, cfg->topology, cfg->neigh_kind, sigma_per_epoch[e],
                                        eta_per_epoch[e], cfg->std_coeff, cfg->compact_support, num, den, b.tab, b.st))) return rc;

@@ -65,13 +65,24 @@ class CudaEngine:
                                                           ws.numel(), self._stream()), "som_b200_prepare_codebook")
         self.launches += 1
 
-    def bmu(self, x, w, dist_kind, p, algo, ws, bmu_out=None, best_out=None):
+    def prepare_samples(self, x):
+        """Per-row power-of-two scales for the fp16-split kernel (one pass over x)."""
+        n, d = x.shape
+        xs = self.empty(max(n, 1))
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_prepare_samples(self._p(x), n, d, x.stride(0), self._p(xs), self._stream()),
+                       "som_b200_prepare_samples")
+        self.launches += 1
+        return xs
+
+    def bmu(self, x, w, dist_kind, p, algo, ws, bmu_out=None, best_out=None, xscale=None):
         n, d = x.shape
         k = w.shape[0]
         if bmu_out is None:
             bmu_out = self.empty(n, dtype=torch.int32)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.som_b200_bmu(self._p(x), n, d, x.stride(0), self._p(w), k, dist_kind, float(p), algo,
+            _lib.check(self.lib.som_b200_bmu(self._p(x), n, d, x.stride(0), self._p(xscale), self._p(w), k, dist_kind,
+                                             float(p), algo,
                                              self._p(bmu_out), self._p(best_out), self._p(ws), ws.numel(),
                                              self._stream()), "som_b200_bmu")
         self.launches += 1
@@ -84,11 +95,12 @@ class CudaEngine:
                                                     self._p(c), self._stream()), "som_b200_accumulate")
         self.launches += 1
 
-    def epoch_accumulate(self, x, w, dist_kind, p, algo, s, c, ws, bmu_out=None):
+    def epoch_accumulate(self, x, w, dist_kind, p, algo, s, c, ws, bmu_out=None, xscale=None):
         n, d = x.shape
         k = w.shape[0]
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.som_b200_epoch_accumulate(self._p(x), n, d, x.stride(0), self._p(w), k, dist_kind,
+            _lib.check(self.lib.som_b200_epoch_accumulate(self._p(x), n, d, x.stride(0), self._p(xscale), self._p(w), k,
+                                                          dist_kind,
                                                           float(p), algo, self._p(s), self._p(c), self._p(bmu_out),
                                                           self._p(ws), ws.numel(), self._stream()),
                        "som_b200_epoch_accumulate")

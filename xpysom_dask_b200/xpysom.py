@@ -141,6 +141,9 @@ class XPySom:
         p = float(self._activation_distance_kwargs.get('p', 2))
         return _lib.DIST[name], p
 
+    def _wants_xscale(self, dist_kind):
+        return self._algo in ('auto', 'tc16') and dist_kind in (_lib.DIST['euclidean'], _lib.DIST['cosine'])
+
     def _group(self):
         pg = self._process_group
         if pg is None or pg is False:
@@ -213,6 +216,8 @@ class XPySom:
         num, den = nd[:K * d], nd[K * d:]
         ws = eng.workspace(0, K, d)
         bmu = eng.empty(n, dtype=torch.int32)
+        # per-row power-of-two scales for the fp16-split contraction: once per upload, not per epoch
+        xscale = eng.prepare_samples(x) if self._wants_xscale(dist_kind) else None
         tables = eng.neigh_tables(gx, gy)
         prof = self._profile_events if getattr(self, '_profile', False) else None
 
@@ -225,7 +230,7 @@ class XPySom:
                 ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                 ev[0].record()
             # K1/K2 + K3: distance + argmin + per-BMU sums (one fused kernel on the tensor-core path)
-            eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu)
+            eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
             if prof is not None:
                 ev[1].record()
                 prof.append(ev)
@@ -262,7 +267,8 @@ class XPySom:
         x = self._data_to_device(eng, data)
         ws = eng.workspace(0, gx * gy, d)
         eng.prepare_codebook(w, dist_kind, p, ws)
-        bmu = eng.bmu(x, w, dist_kind, p, _lib.ALGO[self._algo], ws)
+        xscale = eng.prepare_samples(x) if self._wants_xscale(dist_kind) else None
+        bmu = eng.bmu(x, w, dist_kind, p, _lib.ALGO[self._algo], ws, xscale=xscale)
         return bmu, x, w, eng
 
     def winner(self, x):
