@@ -41,8 +41,8 @@ def stage_bmu(eng, algo, shapes, dist="euclidean"):
         ws = eng.workspace(0, k, d)
         eng.prepare_codebook(w, _lib.DIST[dist], 2.0, ws)
         best = eng.empty(n)
-        xs = eng.prepare_samples(x) if algo == "tc16" else None
-        bmu = eng.bmu(x, w, _lib.DIST[dist], 2.0, _lib.ALGO[algo], ws, best_out=best, xscale=xs)
+        xsc = eng.prepare_samples(x) if algo == "tc16" else None
+        bmu = eng.bmu(x, w, _lib.DIST[dist], 2.0, _lib.ALGO[algo], ws, best_out=best, xscale=xsc)
         torch.cuda.synchronize()
         # fp64 truth on a subset of rows
         m = min(n, 4096)
@@ -57,7 +57,7 @@ def stage_bmu(eng, algo, shapes, dist="euclidean"):
         mism = (bmu[:m].long() != truth)
         worst = gap[mism].max().item() if mism.any() else 0.0
         score_err = (best[:m].double() - dd.min(1).values).abs().max().item() if dist == "euclidean" else float("nan")
-        ms = ev_time(lambda: eng.bmu(x, w, _lib.DIST[dist], 2.0, _lib.ALGO[algo], ws, bmu_out=bmu, xscale=xs))
+        ms = ev_time(lambda: eng.bmu(x, w, _lib.DIST[dist], 2.0, _lib.ALGO[algo], ws, bmu_out=bmu, xscale=xsc))
         tf = 2.0 * n * k * d / (ms * 1e-3) / 1e12
         print("[%s %s] n=%d d=%d K=%d: mismatch vs fp64 %d/%d (worst rel gap %.2e), |score err| %.2e, %.3f ms, %.1f TFLOP/s algorithmic"
               % (algo, dist, n, d, k, int(mism.sum()), m, worst, score_err, ms, tf), flush=True)

@@ -41,8 +41,9 @@ constexpr int NUM_THREADS = 576;
 constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6, SCAT_WARP0 = 14;
 constexpr int EPI_THREADS = 256;
 constexpr int NUM_BARS = 4 * STAGES + 4 + 4;
-// stages | merge buffers [2][BM] (float + int) | bmu hand-off [2][BM] | barriers | tmem slot | align slack
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
+// stages | per-warp bias slices | merge buffers [2][BM] (float + int) | bmu hand-off [2][BM] | barriers | tmem slot | slack
+constexpr int EPI_STAGE_BYTES = 8 * 128 * 4;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
 
 // ---- cluster / 2-SM PTX wrappers -------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -113,10 +114,12 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
-    float    *mrg_v  = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                       // [2][BM]
-    int      *mrg_i  = reinterpret_cast<int *>(smem + STAGES * STAGE_BYTES + 2 * BM * 4);            // [2][BM]
-    int      *bmu_s  = reinterpret_cast<int *>(smem + STAGES * STAGE_BYTES + 2 * BM * 8);            // [2][BM]
-    uint64_t *bars   = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4);
+    float    *epi_stage = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                    // [8 warps][128]
+    uint8_t  *tail   = smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES;
+    float    *mrg_v  = reinterpret_cast<float *>(tail);                       // [2][BM]
+    int      *mrg_i  = reinterpret_cast<int *>(tail + 2 * BM * 4);            // [2][BM]
+    int      *bmu_s  = reinterpret_cast<int *>(tail + 2 * BM * 8);            // [2][BM]
+    uint64_t *bars   = reinterpret_cast<uint64_t *>(tail + 2 * BM * 8 + 2 * BM * 4);
     const uint32_t bar0 = smem_u32(bars);
     auto xfull_bar  = [&](int s) { return bar0 + 8u * s; };                     // local: X chunk landed
     auto bfull_bar  = [&](int s) { return bar0 + 8u * (STAGES + s); };          // leader: both W' halves landed
@@ -234,10 +237,17 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         uint32_t acc_it = 0, tile_it = 0;
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
             tc::RunMin rm; rm.reset();
+            // this warp's 128 bias values of the current neuron tile live in its private shared-memory
+            // slice; the next tile's are prefetched into registers while this one is drained
+            float *bs = epi_stage + (warp - EPI_WARP0) * 128;
+            float4 nb = __ldg(reinterpret_cast<const float4 *>(bias + h * (BN / 2)) + lane);
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                 const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
                 const int col0 = nt * BN + h * (BN / 2);
-                const float *bs = bias + col0;            // read through L1 (uniform address per warp)
+                __syncwarp();
+                reinterpret_cast<float4 *>(bs)[lane] = nb;
+                __syncwarp();
+                nb = __ldg(reinterpret_cast<const float4 *>(bias + (nt + 1 < num_n_tiles ? nt + 1 : 0) * BN + h * (BN / 2)) + lane);
                 tc::mbar_wait(tfull_bar(a), aph);
                 tc::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));

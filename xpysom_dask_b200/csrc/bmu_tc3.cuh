@@ -48,7 +48,8 @@ constexpr int APROD_WARP = 2, CONV_WARP0 = 4, EPI_WARP0 = 8, SCAT_WARP0 = 16;
 constexpr int EPI_THREADS = 256;
 constexpr int RESIDENT_MAX_KB = 2;       // D <= 128: X tiles resident across neuron tiles
 constexpr int NUM_BARS = 3 * NA + 2 * NB + 4 + 4;
-constexpr int SMEM_BYTES = (NA + NB) * SLOT_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
+constexpr int EPI_STAGE_BYTES = 8 * 2 * 128 * 4;   // per epilogue warp: 128 bias + 128 inverse-scale floats
+constexpr int SMEM_BYTES = (NA + NB) * SLOT_BYTES + EPI_STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
 
 __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\t"
@@ -63,11 +64,11 @@ constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint3
 struct RunMinScaled : tc::RunMin {
     __device__ __forceinline__ void chunk(const uint32_t (&acc)[32], const float *bias32, const float *winv32,
                                           float rs, int colbase) {
-        const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias32);     // shared memory, broadcast reads
         const float4 *s4 = reinterpret_cast<const float4 *>(winv32);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-            const float4 b = __ldg(b4 + j4), s = __ldg(s4 + j4);
+            const float4 b = b4[j4], s = s4[j4];
             const float bb[4] = {b.x, b.y, b.z, b.w}, ss[4] = {s.x, s.y, s.z, s.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -90,7 +91,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
     const uint32_t a_base = smem_base, b_base = smem_base + NA * SLOT_BYTES;
-    uint8_t *tail = smem + (NA + NB) * SLOT_BYTES;
+    float *epi_stage = reinterpret_cast<float *>(smem + (NA + NB) * SLOT_BYTES);
+    uint8_t *tail = smem + (NA + NB) * SLOT_BYTES + EPI_STAGE_BYTES;
 
     float    *mrg_v = reinterpret_cast<float *>(tail);                   // [2][BM]
     int      *mrg_i = reinterpret_cast<int *>(tail + 2 * BM * 4);        // [2][BM]
@@ -251,9 +253,23 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
             const float rs = row < n ? __ldg(xscale + row) : 1.f;
             RunMinScaled rm; rm.reset();
+            // this warp's 128 bias / inverse-scale values of the current neuron tile live in its private
+            // shared-memory slice; the next tile's are prefetched into registers while this one is drained
+            float *wb = epi_stage + (warp - EPI_WARP0) * 256;
+            float4 nb = __ldg(reinterpret_cast<const float4 *>(bias + h * (BN / 2)) + lane);
+            float4 ns = __ldg(reinterpret_cast<const float4 *>(wsinv + h * (BN / 2)) + lane);
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                 const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
                 const int col0 = nt * BN + h * (BN / 2);
+                __syncwarp();
+                reinterpret_cast<float4 *>(wb)[lane] = nb;
+                reinterpret_cast<float4 *>(wb + 128)[lane] = ns;
+                __syncwarp();
+                {
+                    const int nn = (nt + 1 < num_n_tiles ? nt + 1 : 0) * BN + h * (BN / 2);
+                    nb = __ldg(reinterpret_cast<const float4 *>(bias + nn) + lane);
+                    ns = __ldg(reinterpret_cast<const float4 *>(wsinv + nn) + lane);
+                }
                 tc::mbar_wait(tfull_bar(a), aph);
                 tc::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
@@ -262,7 +278,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait_dep(v);
-                    rm.chunk(v, bias + col0 + c * 32, wsinv + col0 + c * 32, rs, col0 + c * 32);
+                    rm.chunk(v, wb + c * 32, wb + 128 + c * 32, rs, col0 + c * 32);
                 }
                 tc::tc_fence_before();
                 mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
