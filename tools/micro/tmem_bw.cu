@@ -61,6 +61,42 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
                 } else if (MODE == 3) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) bv[j & 7] = fminf(bv[j & 7], __uint_as_float(v[j]));
+                } else if (MODE == 4 || MODE == 5) {
+                    // scaled score (2 FMA-pipe ops) made non-negative, compared as unsigned bits with the
+                    // DPX min-with-predicate: 1 ALU op for the value + 1 for the index
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * 128 + c * 32) % 256);
+                    const float rs = 1.5f + threadIdx.x * 1e-3f, crow = 100.f;
+                    uint32_t *kv = reinterpret_cast<uint32_t *>(bv);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b = b4[j4], s4 = b4[(j4 + 3) & 7];
+                        const float bb[4] = {b.x, b.y, b.z, b.w}, ss[4] = {s4.x, s4.y, s4.z, s4.w};
+                        float sc[4];
+                        if (MODE == 4) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) sc[e] = fmaf(__uint_as_float(v[j4 * 4 + e]), ss[e], fmaf(bb[e], rs, crow));
+                        } else {
+#pragma unroll
+                            for (int e = 0; e < 4; e += 2) {
+                                unsigned long long a2, b2, s2, r2, c2, t2, o2;
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(a2) : "r"(v[j4 * 4 + e]), "r"(v[j4 * 4 + e + 1]));
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(b2) : "f"(bb[e]), "f"(bb[e + 1]));
+                                asm("mov.b64 %0, {%1, %2};" : "=l"(s2) : "f"(ss[e]), "f"(ss[e + 1]));
+                                asm("mov.b64 %0, {%1, %1};" : "=l"(r2) : "f"(rs));
+                                asm("mov.b64 %0, {%1, %1};" : "=l"(c2) : "f"(crow));
+                                asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(t2) : "l"(b2), "l"(r2), "l"(c2));
+                                asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(o2) : "l"(a2), "l"(s2), "l"(t2));
+                                asm("mov.b64 {%0, %1}, %2;" : "=f"(sc[e]), "=f"(sc[e + 1]) : "l"(o2));
+                            }
+                        }
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 * 4 + e;
+                            bool keep;
+                            kv[j & 7] = __vibmin_u32(kv[j & 7], __float_as_uint(sc[e]), &keep);
+                            if (!keep) bi[j & 7] = t * 256 + c * 32 + j;
+                        }
+                    }
                 } else {
                     const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * 128 + c * 32) % 256);
 #pragma unroll
@@ -112,6 +148,8 @@ int main() {
         run<3>("LDTM + value-only min", w);
         run<2>("LDTM + argmin (no bias)", w);
         run<1>("LDTM + smem bias + argmin", w);
+        run<4>("scaled + vibmin argmin", w);
+        run<5>("scaled(f32x2) + vibmin", w);
     }
     return 0;
 }

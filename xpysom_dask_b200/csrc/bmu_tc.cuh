@@ -52,12 +52,15 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
+// try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (prompt
+// wake-up) or the hint expires, instead of burning issue slots that the epilogue warps need
+constexpr uint32_t kSuspendHintNs = 20000;
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
-                 : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+                 : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
     return ok != 0;
 }
 // Bounded wait: a protocol bug must trap (-> CUDA error on the host), never hang the GPU.
