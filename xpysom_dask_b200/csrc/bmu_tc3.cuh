@@ -60,22 +60,41 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
 // D = f32 (bit 4), A = B = f16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 over the pair)
 constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
+// packed fp32x2 arithmetic (sm_100): one instruction for two lanes of a register pair
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r;
+}
+__device__ __forceinline__ uint64_t pack2u(uint32_t lo, uint32_t hi) {
+    uint64_t r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float &lo, float &hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+    uint64_t r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r;
+}
+
 // running argmin on the scaled scores: sc = acc * 2^-b_k + bias_k * 2^a_r
 struct RunMinScaled : tc::RunMin {
     __device__ __forceinline__ void chunk(const uint32_t (&acc)[32], const float *bias32, const float *winv32,
                                           float rs, int colbase) {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias32);     // shared memory, broadcast reads
         const float4 *s4 = reinterpret_cast<const float4 *>(winv32);
+        const uint64_t rs2 = pack2(rs, rs);
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = b4[j4], s = s4[j4];
-            const float bb[4] = {b.x, b.y, b.z, b.w}, ss[4] = {s.x, s.y, s.z, s.w};
+            float sc[4];
+            unpack2(fma2(pack2u(acc[j4 * 4 + 0], acc[j4 * 4 + 1]), pack2(s.x, s.y), mul2(pack2(b.x, b.y), rs2)), sc[0], sc[1]);
+            unpack2(fma2(pack2u(acc[j4 * 4 + 2], acc[j4 * 4 + 3]), pack2(s.z, s.w), mul2(pack2(b.z, b.w), rs2)), sc[2], sc[3]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 4 + e;
-                const float sc = fmaf(__uint_as_float(acc[j]), ss[e], bb[e] * rs);
                 const int a = j % tc::EPI_ACC;
-                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
+                if (sc[e] < v[a]) { v[a] = sc[e]; i[a] = colbase + j; }
             }
         }
     }
