@@ -214,6 +214,7 @@ struct FusedAcc {
     int *cnt;            // k ints, zero on entry, zero again on exit
     unsigned int *done;  // ticket counter, zero on entry and exit
     int vec;             // rows are 16-byte aligned and d % 4 == 0: 128-bit path
+    int dbg;             // experiments only (SOM_B200_DBG); 0 in production
 };
 
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -475,6 +476,7 @@ inline int launch_bmu_tc(const float *X, int64_t n, int d, int64_t ldx, int k, c
     acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+    acc.dbg = 0;
     bmu_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off),
                                                          n, num_m_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
     return check_cuda(cudaGetLastError(), "bmu_tc_kernel launch");

@@ -376,6 +376,7 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+    acc.dbg = 0;
     bmu_tc2_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off),
                                                                n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
     return check_cuda(cudaGetLastError(), "bmu_tc2_kernel launch");

@@ -297,6 +297,18 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait_dep(v);
+                    if (acc.dbg == 1) {          // experiment: TMEM drain only
+                        uint32_t x = 0;
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) x ^= v[j];
+                        if (x == 0x7fc12345u) rm.i[0] = 1;
+                    } else if (acc.dbg == 2) {   // experiment: unscaled compare
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float sc = __uint_as_float(v[j]);
+                            if (sc < rm.v[j & 7]) { rm.v[j & 7] = sc; rm.i[j & 7] = col0 + c * 32 + j; }
+                        }
+                    } else
                     rm.chunk(v, wb + c * 32, wb + 128 + c * 32, rs, col0 + c * 32);
                 }
                 tc::tc_fence_before();
@@ -431,6 +443,7 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+    { const char *e = getenv("SOM_B200_DBG"); acc.dbg = e ? atoi(e) : 0; }
     bmu_tc3_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
         mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off), reinterpret_cast<const float *>(ws + L.wsinv_off),
         xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
