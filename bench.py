@@ -89,29 +89,6 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
 
 
-def measure_tf32_gemm_tflops(dev):
-    """Dense TF32 GEMM rate of this GPU right now (cuBLAS through torch.matmul, 8192^3, best of 5).
-    MEASURED_PEAKS.json only holds the bf16 rate; the BMU kernel runs kind::tf32 MMAs."""
-    import torch
-    old = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = True
-    try:
-        a = torch.randn(8192, 8192, device=dev)
-        b = torch.randn(8192, 8192, device=dev)
-        best = 0.0
-        for i in range(7):
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            torch.matmul(a, b)
-            e1.record()
-            torch.cuda.synchronize()
-            if i >= 2:
-                best = max(best, 2.0 * 8192 ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
-        return best
-    finally:
-        torch.backends.cuda.matmul.allow_tf32 = old
-
-
 def synth(n, d, seed):
     """U[0,1) iid float32 — SURVEY §8d distribution (i): throughput, worst-case near-ties."""
     rng = np.random.RandomState(seed)
@@ -228,10 +205,18 @@ def run_gpu(args, wl, rank, world, local_rank):
         total = n * world
         value = total * args.steps / (ms * 1e-3)
         flops = 2.0 * n * K * d                       # algorithmic flops of one BMU launch
-        tf32_live = measure_tf32_gemm_tflops(dev)
-        # dense TF32 peak: the larger of half the measured bf16 rate and a live cuBLAS TF32 GEMM
-        tf32_peak = max(pk["bf16"] / 2.0, tf32_live)
-        contraction = wl["kw"].get("activation_distance", "euclidean") in ("euclidean", "cosine") and args.algo != "simt"
+        dist_name = wl["kw"].get("activation_distance", "euclidean")
+        contraction = dist_name in ("euclidean", "cosine") and args.algo != "simt"
+        # which tensor-core kernel AUTO resolves to (som_api.cu: pick_algo)
+        f16 = contraction and (args.algo == "tc16" or (args.algo == "auto" and d > 32))
+        if not contraction:
+            kernel, peak, peak_note = "bmu_simt_kernel + accumulate_kernel", None, "SIMT fp32"
+        elif f16:
+            kernel = "bmu_tc3_kernel (tcgen05 kind::f16, 3-term fp16 split, cta_group::2, argmin + per-BMU accumulate fused)"
+            peak, peak_note = pk["bf16"], "dense bf16/fp16 tensor rate bf16_tflops from %s" % pk["source"]
+        else:
+            kernel = "bmu_tc2_kernel (tcgen05 kind::tf32, 3-term TF32 split, cta_group::2, argmin + per-BMU accumulate fused)"
+            peak, peak_note = pk["bf16"] / 2.0, "dense TF32 rate taken as half of bf16_tflops from %s" % pk["source"]
         ach = flops / (bmu_ms * 1e-3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
@@ -239,15 +224,14 @@ def run_gpu(args, wl, rank, world, local_rank):
             with open(tp) as f:
                 traffic = json.load(f).get(args.workload)
         roofline = {
-            "kernel": "bmu_tc_kernel (contraction + argmin + fused per-BMU accumulate)" if contraction
-                      else "bmu_simt_kernel + accumulate_kernel",
-            "bound": "tensor", "achieved": ach, "peak": tf32_peak, "unit": "TFLOP/s", "frac": ach / tf32_peak,
+            "kernel": kernel,
+            "bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+            "frac": (ach / peak) if peak else None,
             "traffic": traffic,
-            "note": "achieved = 2*n*K*D algorithmic flops / CUDA-event time of the BMU kernel inside the timed epochs; "
-                    "peak = max(bf16_tflops/2 from %s = %.0f, live cuBLAS TF32 8192^3 GEMM = %.0f); the kernel "
-                    "executes 3x the algorithmic flops (3xTF32 split), so its attainable ceiling is frac 0.333"
-                    % (pk["source"], pk["bf16"] / 2.0, tf32_live),
-            "frac_of_3xtf32_ceiling": ach / (tf32_peak / 3.0),
+            "note": "achieved = 2*n*K*D algorithmic flops / CUDA-event time of the fused BMU kernel inside the timed "
+                    "epochs; peak = %s; the kernel executes 3x the algorithmic flops (hi/lo split for fp32 accuracy), "
+                    "so its attainable ceiling is frac 0.333" % peak_note,
+            "frac_of_3pass_ceiling": (ach / (peak / 3.0)) if peak else None,
             "kernel_ms": bmu_ms, "step_ms": ms / args.steps,
             "hbm": {"achieved": 4.0 * n * d / ((ms / args.steps) * 1e-3) / 1e9, "peak": pk["hbm_gbs"], "unit": "GB/s",
                     "note": "sample-read bytes 4*D per sample-epoch / step time"},
@@ -255,7 +239,8 @@ def run_gpu(args, wl, rank, world, local_rank):
         line = {
             "metric": "SOM training samples*epochs/sec", "value": value, "unit": "samples*epochs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 (3xTF32 contraction)",
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tensor-core contraction on a 3-term %s split)" % ("fp16" if f16 else "tf32") if contraction else "f32",
             "data": "synthetic",
             "config": {"workload": wl["name"], "rows_per_gpu": n, "map": "%dx%d" % (gx, gy), "features": d,
                        "algo": args.algo, "parallelism": "dp%d" % world,
