@@ -79,6 +79,24 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
 
 // running argmin on the scaled scores: sc = acc * 2^-b_k + bias_k * 2^a_r
 struct RunMinScaled : tc::RunMin {
+    // uniform codebook scale: sc = acc + bias_k * rsg  (one FFMA per score, one shared-memory operand)
+    __device__ __forceinline__ void chunk_uniform(const uint32_t (&acc)[32], const float *bias32, float rsg, int colbase) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+        float4 bq[8];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) bq[j4] = b4[j4];
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float bb[4] = {bq[j4].x, bq[j4].y, bq[j4].z, bq[j4].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                const float sc = fmaf(bb[e], rsg, __uint_as_float(acc[j]));
+                const int a = j % tc::EPI_ACC;
+                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
+            }
+        }
+    }
     __device__ __forceinline__ void chunk(const uint32_t (&acc)[32], const float *bias32, const float *winv32,
                                           float rs, int colbase) {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias32);     // shared memory, broadcast reads
@@ -103,8 +121,8 @@ struct RunMinScaled : tc::RunMin {
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
-               const float *__restrict__ wsinv, const float *__restrict__ xscale,
-               int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
+               const float *__restrict__ wsinv, const unsigned int *__restrict__ gstat,
+               const float *__restrict__ xscale, int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
                int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -136,6 +154,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const bool fused = acc.S != nullptr;
     const bool resident = num_k_blocks <= RESIDENT_MAX_KB;   // A tiles live across the neuron tiles
+    const bool uniform = gstat[2] != 0u;                     // one power-of-two scale for the whole codebook
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 256); tc::mbar_init(aempty_bar(s), 1); }
@@ -271,6 +290,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
             const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
             const float rs = row < n ? __ldg(xscale + row) : 1.f;
+            // uniform codebook scale 2^b: argmin of acc * 2^-b + bias * rs == argmin of acc + bias * (rs * 2^b)
+            const float rsg = uniform ? rs / __ldg(wsinv) : 0.f;
             RunMinScaled rm; rm.reset();
             // this warp's 128 bias / inverse-scale values of the current neuron tile live in its private
             // shared-memory slice; the next tile's are prefetched into registers while this one is drained
@@ -308,8 +329,11 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             const float sc = __uint_as_float(v[j]);
                             if (sc < rm.v[j & 7]) { rm.v[j & 7] = sc; rm.i[j & 7] = col0 + c * 32 + j; }
                         }
-                    } else
-                    rm.chunk(v, wb + c * 32, wb + 128 + c * 32, rs, col0 + c * 32);
+                    } else if (uniform) {
+                        rm.chunk_uniform(v, wb + c * 32, rsg, col0 + c * 32);
+                    } else {
+                        rm.chunk(v, wb + c * 32, wb + 128 + c * 32, rs, col0 + c * 32);
+                    }
                 }
                 tc::tc_fence_before();
                 mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
@@ -323,7 +347,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 argmin_merge(best, bidx, mrg_v[mb + row_in_tile], mrg_i[mb + row_in_tile]);
                 if (row < n) {
                     if (bmu_out) bmu_out[row] = bidx;
-                    if (best_out) best_out[row] = best / rs;          // undo the row scale (exact)
+                    if (best_out) best_out[row] = uniform ? best / rsg : best / rs;   // undo the scaling (exact)
                 }
                 if (fused) {
                     const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
@@ -446,7 +470,7 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     { const char *e = getenv("SOM_B200_DBG"); acc.dbg = e ? atoi(e) : 0; }
     bmu_tc3_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
         mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off), reinterpret_cast<const float *>(ws + L.wsinv_off),
-        xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+        reinterpret_cast<const unsigned int *>(ws + L.gstat_off), xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
     return check_cuda(cudaGetLastError(), "bmu_tc3_kernel launch");
 }
 

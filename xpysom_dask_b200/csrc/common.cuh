@@ -31,6 +31,9 @@ struct WsLayout {
     size_t wsinv_off; // k_pad floats: 2^-b_k, the inverse of the per-neuron power-of-two scale
     size_t cnt_off;   // k_pad int32: exact per-BMU counts of the fused kernel (zero between launches)
     size_t done_off;  // one uint32: CTAs-finished ticket of the fused kernel (zero between launches)
+    size_t gstat_off; // codebook statistics of the current prepare: [0] bits of max_k amax_k, [1] ~bits of the
+                      // smallest non-zero amax_k (both via atomicMax, zeroed by prepare), [2] uniform-scale flag
+    size_t amax_off;  // k_pad floats: amax_k = max_c |w'_k[c]|
     size_t total;
 };
 
@@ -49,6 +52,8 @@ __host__ inline WsLayout ws_layout(int k, int d) {
     L.wsinv_off = off; off += round_up((size_t)L.k_pad * 4, 1024);
     L.cnt_off = off;  off += round_up((size_t)L.k_pad * 4, 1024);
     L.done_off = off; off += 1024;
+    L.gstat_off = off; off += 1024;
+    L.amax_off = off; off += round_up((size_t)L.k_pad * 4, 1024);
     L.total = off;
     return L;
 }

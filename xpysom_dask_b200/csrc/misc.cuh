@@ -13,63 +13,86 @@ __device__ __forceinline__ float tf32_rna(float v) {
     return __uint_as_float(r);
 }
 
-// Q: one warp per (padded) neuron.
+// Q, pass 1: one warp per (padded) neuron.
 //   aux[k]  = |w_k|^2 (euclidean; xpysom.py:529-537)  or 1/|w_k| (cosine; 0 for a zero neuron,
 //             which makes its similarity 0 like nan_to_num in distances.py:57)
 //   bias[k] = additive term of the tensor-core epilogue: |w|^2 / 0, +inf on padding neurons
-//   whi/wlo = TF32 split of the SCALED codebook row (-2 w for euclidean: exact; -w/|w| for cosine),
-//             zero on padding, so that score = x . w' + bias is what both kernels minimise.
-//   w16hi/w16lo/wsinv = the same scaled row times 2^b_k (b_k brings its largest magnitude into
-//             [2^14, 2^15)) split into two fp16 numbers, and 2^-b_k for the epilogue.
-__global__ void prepare_codebook_kernel(const float *__restrict__ W, int k, int d, int dist_kind,
-                                        int k_pad, int d_pad, float *__restrict__ aux, float *__restrict__ bias,
-                                        float *__restrict__ whi, float *__restrict__ wlo,
-                                        int d_pad64, __half *__restrict__ w16hi, __half *__restrict__ w16lo,
-                                        float *__restrict__ wsinv) {
+//   amax[k] = largest magnitude of the SCALED row w'_k (-2 w for euclidean: exact; -w/|w| for cosine);
+//   gstat   = running max / min-non-zero of amax over the codebook (decides the fp16 scaling mode)
+__device__ __forceinline__ float codebook_row_scale(int dist_kind, double s) {
+    if (dist_kind == SOM_DIST_EUCLIDEAN) return -2.f;
+    if (dist_kind == SOM_DIST_COSINE) return s > 0.0 ? -(float)(1.0 / sqrt(s)) : 0.f;
+    return 0.f;
+}
+
+__global__ void codebook_stats_kernel(const float *__restrict__ W, int k, int d, int dist_kind, int k_pad,
+                                      float *__restrict__ aux, float *__restrict__ bias, float *__restrict__ amax,
+                                      unsigned int *__restrict__ gstat) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= k_pad) return;
     const bool real = warp < k;
     double s = 0.0;
+    float m = 0.f;
     if (real)
-        for (int c = lane; c < d; c += 32) { const double v = W[(int64_t)warp * d + c]; s += v * v; }
+        for (int c = lane; c < d; c += 32) { const float v = W[(int64_t)warp * d + c]; s += (double)v * v; m = fmaxf(m, fabsf(v)); }
     s = warp_sum(s);
-    const float wsq = (float)s;
-    float scale = 0.f, a = 0.f, b = INFINITY;
-    if (real) {
-        if (dist_kind == SOM_DIST_EUCLIDEAN) { scale = -2.f; a = wsq; b = wsq; }
-        else if (dist_kind == SOM_DIST_COSINE) {
-            const float rn = s > 0.0 ? (float)(1.0 / sqrt(s)) : 0.f;
-            scale = -rn; a = rn; b = 0.f;
-        } else { a = wsq; b = 0.f; }
-    }
-    if (lane == 0) { aux[warp] = a; bias[warp] = b; }
-    if (whi != nullptr) {
-        for (int c = lane; c < d_pad; c += 32) {
-            float v = 0.f;
-            if (real && c < d) v = W[(int64_t)warp * d + c] * scale;
-            const float hi = tf32_rna(v);
-            const float lo = tf32_rna(v - hi);
-            whi[(int64_t)warp * d_pad + c] = hi;
-            wlo[(int64_t)warp * d_pad + c] = lo;
-        }
-    }
-    if (w16hi != nullptr) {
-        float amax = 0.f;
-        if (real)
-            for (int c = lane; c < d; c += 32) amax = fmaxf(amax, fabsf(W[(int64_t)warp * d + c] * scale));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        const float ps = pow2_scale_for(amax);
-        if (lane == 0) wsinv[warp] = 1.f / ps;          // exact: ps is a power of two
-        for (int c = lane; c < d_pad64; c += 32) {
-            float v = 0.f;
-            if (real && c < d) v = W[(int64_t)warp * d + c] * scale * ps;
-            const __half hi = __float2half_rn(v);
-            const __half lo = __float2half_rn(v - __half2float(hi));
-            w16hi[(int64_t)warp * d_pad64 + c] = hi;
-            w16lo[(int64_t)warp * d_pad64 + c] = lo;
-        }
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane != 0) return;
+    const float wsq = (float)s;
+    float a = 0.f, b = INFINITY;
+    if (real) {
+        if (dist_kind == SOM_DIST_EUCLIDEAN) { a = wsq; b = wsq; }
+        else if (dist_kind == SOM_DIST_COSINE) { a = -codebook_row_scale(dist_kind, s); b = 0.f; }
+        else { a = wsq; b = 0.f; }
+    }
+    aux[warp] = a; bias[warp] = b;
+    const float am = real ? m * fabsf(codebook_row_scale(dist_kind, s)) : 0.f;
+    amax[warp] = am;
+    if (am > 0.f && isfinite(am)) {
+        atomicMax(gstat + 0, __float_as_uint(am));
+        atomicMax(gstat + 1, ~__float_as_uint(am));
+    }
+}
+
+// Q, pass 2: operand copies of the scaled codebook for the tensor-core kernels.
+//   whi/wlo      TF32 split of w'_k (zero on padding)
+//   w16hi/w16lo  fp16 split of w'_k * 2^b_k, wsinv[k] = 2^-b_k.  When every non-zero neuron's amax is within
+//                2^12 of the largest one, ONE power of two serves the whole codebook (b_k = b, gstat[2] = 1) and
+//                the epilogue needs a single fused multiply-add per score; otherwise each neuron gets its own
+//                b_k (exact, undone per column in the epilogue) so that tiny neurons keep their 22 bits.
+__global__ void codebook_split_kernel(const float *__restrict__ W, int k, int d, int dist_kind, int k_pad, int d_pad,
+                                      float *__restrict__ whi, float *__restrict__ wlo, int d_pad64,
+                                      __half *__restrict__ w16hi, __half *__restrict__ w16lo, float *__restrict__ wsinv,
+                                      const float *__restrict__ aux, const float *__restrict__ amax,
+                                      unsigned int *__restrict__ gstat) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= k_pad) return;
+    const bool real = warp < k;
+    float scale = 0.f;
+    if (real) scale = dist_kind == SOM_DIST_EUCLIDEAN ? -2.f : -aux[warp];     // aux = 1/|w| for cosine
+    const float gmax = __uint_as_float(gstat[0]);
+    const unsigned int nmin = gstat[1];
+    const float gmin = nmin ? __uint_as_float(~nmin) : gmax;
+    const bool uniform = !(gmax > 0.f) || gmin >= gmax * (1.f / 4096.f);
+    if (warp == 0 && lane == 0) gstat[2] = uniform ? 1u : 0u;
+    for (int c = lane; c < d_pad; c += 32) {
+        float v = 0.f;
+        if (real && c < d) v = W[(int64_t)warp * d + c] * scale;
+        const float hi = tf32_rna(v);
+        whi[(int64_t)warp * d_pad + c] = hi;
+        wlo[(int64_t)warp * d_pad + c] = tf32_rna(v - hi);
+    }
+    const float ps = pow2_scale_for(uniform ? gmax : amax[warp]);
+    if (lane == 0) wsinv[warp] = 1.f / ps;              // exact: ps is a power of two
+    for (int c = lane; c < d_pad64; c += 32) {
+        float v = 0.f;
+        if (real && c < d) v = W[(int64_t)warp * d + c] * scale * ps;
+        const __half hi = __float2half_rn(v);
+        w16hi[(int64_t)warp * d_pad64 + c] = hi;
+        w16lo[(int64_t)warp * d_pad64 + c] = __float2half_rn(v - __half2float(hi));
     }
 }
 

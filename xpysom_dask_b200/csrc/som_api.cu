@@ -126,16 +126,20 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
     SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "prepare_codebook: workspace %zu < %zu bytes", ws_bytes, L.total);
     uint8_t *ws = static_cast<uint8_t *>(ws_dev);
     const bool split = dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE;
-    SOM_CUDA(cudaMemsetAsync(ws + L.cnt_off, 0, L.total - L.cnt_off, (cudaStream_t)stream));   // counts + ticket
+    SOM_CUDA(cudaMemsetAsync(ws + L.cnt_off, 0, L.amax_off - L.cnt_off, (cudaStream_t)stream));   // counts, ticket, stats
     const int threads = 256, warps_per_block = threads / 32;
     const int blocks = (int)ceil_div(L.k_pad, warps_per_block);
-    prepare_codebook_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
-        w_dev, k, d, dist_kind, L.k_pad, L.d_pad, reinterpret_cast<float *>(ws + L.aux_off),
-        reinterpret_cast<float *>(ws + L.bias_off), split ? reinterpret_cast<float *>(ws + L.whi_off) : nullptr,
-        split ? reinterpret_cast<float *>(ws + L.wlo_off) : nullptr, L.d_pad64,
-        split ? reinterpret_cast<__half *>(ws + L.w16hi_off) : nullptr,
-        split ? reinterpret_cast<__half *>(ws + L.w16lo_off) : nullptr, reinterpret_cast<float *>(ws + L.wsinv_off));
-    return check_cuda(cudaGetLastError(), "prepare_codebook_kernel launch");
+    float *aux = reinterpret_cast<float *>(ws + L.aux_off), *amax = reinterpret_cast<float *>(ws + L.amax_off);
+    unsigned int *gstat = reinterpret_cast<unsigned int *>(ws + L.gstat_off);
+    codebook_stats_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        w_dev, k, d, dist_kind, L.k_pad, aux, reinterpret_cast<float *>(ws + L.bias_off), amax, gstat);
+    int rc = check_cuda(cudaGetLastError(), "codebook_stats_kernel launch");
+    if (rc || !split) return rc;
+    codebook_split_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
+        w_dev, k, d, dist_kind, L.k_pad, L.d_pad, reinterpret_cast<float *>(ws + L.whi_off),
+        reinterpret_cast<float *>(ws + L.wlo_off), L.d_pad64, reinterpret_cast<__half *>(ws + L.w16hi_off),
+        reinterpret_cast<__half *>(ws + L.w16lo_off), reinterpret_cast<float *>(ws + L.wsinv_off), aux, amax, gstat);
+    return check_cuda(cudaGetLastError(), "codebook_split_kernel launch");
 }
 
 int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, void *stream) {
