@@ -157,11 +157,11 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const bool uniform = gstat[2] != 0u;                     // one power-of-two scale for the whole codebook
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 256); tc::mbar_init(aempty_bar(s), 1); }
+        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 8); tc::mbar_init(aempty_bar(s), 1); }
         for (int s = 0; s < NB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS);
-            tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS / 32);   // per-warp arrives
+            tc::mbar_init(bfullq_bar(a), 4); tc::mbar_init(bemptyq_bar(a), 4);
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
@@ -278,7 +278,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         *reinterpret_cast<uint2 *>(slot + HALF_SLOT + off) = lv;
                     }
                     tc::fence_proxy_async();
-                    mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
                 }
         }
     } else if (warp >= EPI_WARP0 && warp < SCAT_WARP0) {
@@ -301,11 +302,13 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                 const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
                 const int col0 = nt * BN + h * (BN / 2);
+                if (acc.dbg != 5) {
                 __syncwarp();
                 reinterpret_cast<float4 *>(wb)[lane] = nb;
                 reinterpret_cast<float4 *>(wb + 128)[lane] = ns;
                 __syncwarp();
-                {
+                }
+                if (acc.dbg != 5) {
                     const int nn = (nt + 1 < num_n_tiles ? nt + 1 : 0) * BN + h * (BN / 2);
                     nb = __ldg(reinterpret_cast<const float4 *>(bias + nn) + lane);
                     ns = __ldg(reinterpret_cast<const float4 *>(wsinv + nn) + lane);
@@ -329,6 +332,22 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             const float sc = __uint_as_float(v[j]);
                             if (sc < rm.v[j & 7]) { rm.v[j & 7] = sc; rm.i[j & 7] = col0 + c * 32 + j; }
                         }
+                    } else if (acc.dbg == 3) {   // experiment: uniform math, bias operand from a register
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float sc = fmaf(rs, rsg, __uint_as_float(v[j]));
+                            if (sc < rm.v[j & 7]) { rm.v[j & 7] = sc; rm.i[j & 7] = col0 + c * 32 + j; }
+                        }
+                    } else if (acc.dbg == 4) {   // experiment: uniform math + smem bias, value-only min
+                        const float4 *b4 = reinterpret_cast<const float4 *>(wb + c * 32);
+#pragma unroll
+                        for (int j4 = 0; j4 < 8; ++j4) {
+                            const float4 b = b4[j4];
+                            const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e)
+                                rm.v[(j4 * 4 + e) & 7] = fminf(rm.v[(j4 * 4 + e) & 7], fmaf(bb[e], rsg, __uint_as_float(v[j4 * 4 + e])));
+                        }
                     } else if (uniform) {
                         rm.chunk_uniform(v, wb + c * 32, rsg, col0 + c * 32);
                     } else {
@@ -336,7 +355,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     }
                 }
                 tc::tc_fence_before();
-                mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
             }
             float best; int bidx;
             rm.result(best, bidx);
@@ -353,7 +373,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                     tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
                     bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
-                    tc::mbar_arrive(bfullq_bar(b));
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(bfullq_bar(b));
                 }
             }
         }
@@ -399,7 +420,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
                     }
                 }
-                tc::mbar_arrive(bemptyq_bar(b));
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
             }
         }
     }
