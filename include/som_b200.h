@@ -153,6 +153,10 @@ int som_b200_quantize(const float *x_dev, int64_t n, int d, int64_t ldx,
 int som_b200_distance_map(const float *w_dev, int gx, int gy, int d, int topology,
                           float *um_dev, void *stream);
 
+/* Experiments only: with SOM_B200_DBG=9 the fp16 kernel stamps clock64() at its pipeline hand-off
+ * points; this copies the first n stamps (8 per tile) to host memory. */
+int som_b200_debug_timeline(long long *host_out, int n);
+
 /* Whole-job entry with HOST buffers: what a maintainer of the reference would
  * bind from XPySom.train (xpysom.py:458-594) with numpy arrays — uploads the
  * samples once, runs epochs [iter_beg, iter_end) with the given per-epoch

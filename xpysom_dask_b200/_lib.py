@@ -43,6 +43,7 @@ SIGNATURES = {
                                          c_i32p, c_f32p, c_f32p, ctypes.c_void_p]),
     "som_b200_distance_map": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                              c_f32p, ctypes.c_void_p]),
+    "som_b200_debug_timeline": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "som_b200_train_host": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p,
                                            ctypes.c_void_p, ctypes.POINTER(ctypes.c_double),
                                            ctypes.POINTER(ctypes.c_double), ctypes.c_int]),

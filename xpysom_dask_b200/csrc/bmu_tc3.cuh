@@ -79,6 +79,42 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
 
 // running argmin on the scaled scores: sc = acc * 2^-b_k + bias_k * 2^a_r
 struct RunMinScaled : tc::RunMin {
+    // 16 accumulator columns, uniform codebook scale: sc = acc + bias_k * rsg
+    __device__ __forceinline__ void chunk16_uniform(const uint32_t (&acc)[16], const float *bias16, float rsg, int colbase) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
+        float4 bq[4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) bq[j4] = b4[j4];
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const float bb[4] = {bq[j4].x, bq[j4].y, bq[j4].z, bq[j4].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                const float sc = fmaf(bb[e], rsg, __uint_as_float(acc[j]));
+                const int a = j % tc::EPI_ACC;
+                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
+            }
+        }
+    }
+    // 16 accumulator columns, per-neuron scale: sc = acc * winv_k + bias_k * rs
+    __device__ __forceinline__ void chunk16_scaled(const uint32_t (&acc)[16], const float *bias16, const float *winv16,
+                                                   float rs, int colbase) {
+        const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
+        const float4 *s4 = reinterpret_cast<const float4 *>(winv16);
+#pragma unroll
+        for (int j4 = 0; j4 < 4; ++j4) {
+            const float4 b = b4[j4], s = s4[j4];
+            const float bb[4] = {b.x, b.y, b.z, b.w}, ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                const float sc = fmaf(__uint_as_float(acc[j]), ss[e], bb[e] * rs);
+                const int a = j % tc::EPI_ACC;
+                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
+            }
+        }
+    }
     // uniform codebook scale: sc = acc + bias_k * rsg  (one FFMA per score, one shared-memory operand)
     __device__ __forceinline__ void chunk_uniform(const uint32_t (&acc)[32], const float *bias32, float rsg, int colbase) {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
@@ -155,6 +191,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const bool fused = acc.S != nullptr;
     const bool resident = num_k_blocks <= RESIDENT_MAX_KB;   // A tiles live across the neuron tiles
     const bool uniform = gstat[2] != 0u;                     // one power-of-two scale for the whole codebook
+    const int probe = (acc.dbg == 9 && blockIdx.x == 0) ? 1 : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 8); tc::mbar_init(aempty_bar(s), 1); }
@@ -212,8 +249,10 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it)
                 for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                     const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
+                    tc::dbg_stamp(probe, 0, acc_it);                 // MMA: starts waiting for the accumulator
                     mbar_wait_cluster(tempty_bar(a), aph ^ 1);
                     tc::tc_fence_after();
+                    tc::dbg_stamp(probe, 1, acc_it);                 // MMA: accumulator free
                     const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                         const uint32_t ia = resident ? (tile_it * (uint32_t)num_k_blocks + kb) : it;
@@ -222,6 +261,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         mbar_wait_cluster(aready_bar(sa), pha);       // hi/lo tiles of both CTAs written
                         mbar_wait_cluster(bfull_bar(sb), phb);        // W' halves of both CTAs landed
                         tc::tc_fence_after();
+                        if (kb == 0) tc::dbg_stamp(probe, 2, acc_it);    // MMA: operands of the first k block ready
                         const uint32_t sta = a_base + sa * SLOT_BYTES, stb = b_base + sb * SLOT_BYTES;
                         const uint64_t a_hi = tc::make_smem_desc(sta), a_lo = tc::make_smem_desc(sta + HALF_SLOT);
                         const uint64_t b_hi = tc::make_smem_desc(stb), b_lo = tc::make_smem_desc(stb + HALF_SLOT);
@@ -236,6 +276,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         if (!resident || nt == num_n_tiles - 1) umma_commit_2sm(aempty_bar(sa));
                     }
                     umma_commit_2sm(tfull_bar(a));
+                    tc::dbg_stamp(probe, 3, acc_it);                 // MMA: all MMAs of the tile issued + committed
                 }
         }
     } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
@@ -287,76 +328,61 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int q = warp & 3;
         const int h = (warp - EPI_WARP0) >> 2;
         const int row_in_tile = q * 32 + lane;
+        const float winv0 = __ldg(wsinv);                    // 2^-b of the uniform codebook scale
+        float *wb = epi_stage + (warp - EPI_WARP0) * 256;    // this warp's private bias | inverse-scale slice
         uint32_t acc_it = 0, tile_it = 0;
+        // row scale of the FIRST tile; later ones are fetched one tile ahead (no exposed global latency)
+        float rs_next = 1.f;
+        {
+            const int64_t row = (int64_t)pair * (2 * BM) + (int64_t)rank * BM + row_in_tile;
+            if (pair < num_pair_tiles && row < n) rs_next = __ldg(xscale + row);
+        }
+        float4 nb = __ldg(reinterpret_cast<const float4 *>(bias + h * (BN / 2)) + lane);
+        float4 ns = __ldg(reinterpret_cast<const float4 *>(wsinv + h * (BN / 2)) + lane);
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
             const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
-            const float rs = row < n ? __ldg(xscale + row) : 1.f;
+            const float rs = rs_next;
+            {
+                const int64_t nrow = row + (int64_t)num_pairs * (2 * BM);
+                rs_next = (pt + num_pairs < num_pair_tiles && nrow < n) ? __ldg(xscale + nrow) : 1.f;
+            }
             // uniform codebook scale 2^b: argmin of acc * 2^-b + bias * rs == argmin of acc + bias * (rs * 2^b)
-            const float rsg = uniform ? rs / __ldg(wsinv) : 0.f;
+            const float rsg = rs / winv0;
             RunMinScaled rm; rm.reset();
-            // this warp's 128 bias / inverse-scale values of the current neuron tile live in its private
-            // shared-memory slice; the next tile's are prefetched into registers while this one is drained
-            float *wb = epi_stage + (warp - EPI_WARP0) * 256;
-            float4 nb = __ldg(reinterpret_cast<const float4 *>(bias + h * (BN / 2)) + lane);
-            float4 ns = __ldg(reinterpret_cast<const float4 *>(wsinv + h * (BN / 2)) + lane);
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                 const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
                 const int col0 = nt * BN + h * (BN / 2);
-                if (acc.dbg != 5) {
                 __syncwarp();
                 reinterpret_cast<float4 *>(wb)[lane] = nb;
                 reinterpret_cast<float4 *>(wb + 128)[lane] = ns;
                 __syncwarp();
-                }
-                if (acc.dbg != 5) {
+                {   // prefetch the next neuron tile's slice (wraps to tile 0 for the next row tile)
                     const int nn = (nt + 1 < num_n_tiles ? nt + 1 : 0) * BN + h * (BN / 2);
                     nb = __ldg(reinterpret_cast<const float4 *>(bias + nn) + lane);
                     ns = __ldg(reinterpret_cast<const float4 *>(wsinv + nn) + lane);
                 }
+                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 4, acc_it);   // EPI: starts waiting for the tile
                 tc::mbar_wait(tfull_bar(a), aph);
                 tc::tc_fence_after();
+                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 5, acc_it);   // EPI: tile complete in TMEM
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
+                // 128 columns in 8 pieces of 16, TMEM loads double-buffered in registers
+                uint32_t va[16], vb[16];
+                tc::tmem_ld16(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < BN / 2 / 32; ++c) {
-                    uint32_t v[32];
-                    tc::tmem_ld32(taddr + c * 32, v);
-                    tc::tmem_ld_wait_dep(v);
-                    if (acc.dbg == 1) {          // experiment: TMEM drain only
-                        uint32_t x = 0;
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) x ^= v[j];
-                        if (x == 0x7fc12345u) rm.i[0] = 1;
-                    } else if (acc.dbg == 2) {   // experiment: unscaled compare
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float sc = __uint_as_float(v[j]);
-                            if (sc < rm.v[j & 7]) { rm.v[j & 7] = sc; rm.i[j & 7] = col0 + c * 32 + j; }
-                        }
-                    } else if (acc.dbg == 3) {   // experiment: uniform math, bias operand from a register
-#pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float sc = fmaf(rs, rsg, __uint_as_float(v[j]));
-                            if (sc < rm.v[j & 7]) { rm.v[j & 7] = sc; rm.i[j & 7] = col0 + c * 32 + j; }
-                        }
-                    } else if (acc.dbg == 4) {   // experiment: uniform math + smem bias, value-only min
-                        const float4 *b4 = reinterpret_cast<const float4 *>(wb + c * 32);
-#pragma unroll
-                        for (int j4 = 0; j4 < 8; ++j4) {
-                            const float4 b = b4[j4];
-                            const float bb[4] = {b.x, b.y, b.z, b.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e)
-                                rm.v[(j4 * 4 + e) & 7] = fminf(rm.v[(j4 * 4 + e) & 7], fmaf(bb[e], rsg, __uint_as_float(v[j4 * 4 + e])));
-                        }
-                    } else if (uniform) {
-                        rm.chunk_uniform(v, wb + c * 32, rsg, col0 + c * 32);
-                    } else {
-                        rm.chunk(v, wb + c * 32, wb + 128 + c * 32, rs, col0 + c * 32);
-                    }
+                for (int c = 0; c < BN / 2 / 16; c += 2) {
+                    tc::tmem_ld_wait_dep16(va);
+                    tc::tmem_ld16(taddr + (c + 1) * 16, vb);
+                    if (uniform) rm.chunk16_uniform(va, wb + c * 16, rsg, col0 + c * 16);
+                    else         rm.chunk16_scaled(va, wb + c * 16, wb + 128 + c * 16, rs, col0 + c * 16);
+                    tc::tmem_ld_wait_dep16(vb);
+                    if (c + 2 < BN / 2 / 16) tc::tmem_ld16(taddr + (c + 2) * 16, va);
+                    if (uniform) rm.chunk16_uniform(vb, wb + (c + 1) * 16, rsg, col0 + (c + 1) * 16);
+                    else         rm.chunk16_scaled(vb, wb + (c + 1) * 16, wb + 128 + (c + 1) * 16, rs, col0 + (c + 1) * 16);
                 }
                 tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 6, acc_it);   // EPI: this warp drained its half
+                mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
             }
             float best; int bidx;
             rm.result(best, bidx);
@@ -373,8 +399,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                     tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
                     bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(bfullq_bar(b));
+                    tc::mbar_arrive(bfullq_bar(b));
                 }
             }
         }

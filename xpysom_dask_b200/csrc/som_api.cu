@@ -269,6 +269,12 @@ int som_b200_distance_map(const float *w_dev, int gx, int gy, int d, int topolog
     return check_cuda(cudaGetLastError(), "distance_map_kernel launch");
 }
 
+int som_b200_debug_timeline(long long *host_out, int n) {
+    SOM_REQUIRE(host_out && n > 0 && n <= 8 * 256, SOM_E_BADARG, "debug_timeline: bad argument");
+    SOM_CUDA(cudaMemcpyFromSymbol(host_out, tc::g_dbg, (size_t)n * sizeof(long long)));
+    return 0;
+}
+
 int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_host, const som_b200_train_config *cfg,
                         const double *sigma_per_epoch, const double *eta_per_epoch, int n_epochs) {
     SOM_REQUIRE(x_host && w_host && cfg && sigma_per_epoch && eta_per_epoch && n > 0 && n_epochs >= 0, SOM_E_BADARG,
