@@ -141,11 +141,11 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(xfull_bar(s), 1); tc::mbar_init(bfull_bar(s), 1);
-            tc::mbar_init(ready_bar(s), 8); tc::mbar_init(empty_bar(s), 1);   // ready: one elected arrive per converter warp
+            tc::mbar_init(ready_bar(s), 256); tc::mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS / 32);   // per-warp arrives
-            tc::mbar_init(bfullq_bar(a), 4); tc::mbar_init(bemptyq_bar(a), 4);
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS);
+            tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
@@ -226,8 +226,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         ahi[e] = h; alo[e] = l;
                     }
                     tc::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(map_to_cta(ready_bar(s), 0));   // the leader's barrier counts both CTAs
+                    mbar_arrive_cluster(map_to_cta(ready_bar(s), 0));       // the leader's barrier counts both CTAs
                 }
     } else if (warp < SCAT_WARP0) {
         // ===================== epilogue: TMEM -> registers -> running argmin =====================
@@ -260,8 +259,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     rm.chunk(v, bs + c * 32, col0 + c * 32);
                 }
                 tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+                mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
             }
             float best; int bidx;
             rm.result(best, bidx);
@@ -280,8 +278,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                     tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
                     bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
-                    __syncwarp();
-                    if (lane == 0) tc::mbar_arrive(bfullq_bar(b));
+                    tc::mbar_arrive(bfullq_bar(b));
                 }
             }
         }
@@ -327,8 +324,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
                     }
                 }
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
+                tc::mbar_arrive(bemptyq_bar(b));
             }
         }
     }

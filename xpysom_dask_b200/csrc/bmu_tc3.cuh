@@ -194,11 +194,11 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int probe = (acc.dbg == 9 && blockIdx.x == 0) ? 1 : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 8); tc::mbar_init(aempty_bar(s), 1); }
+        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 256); tc::mbar_init(aempty_bar(s), 1); }
         for (int s = 0; s < NB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS / 32);   // per-warp arrives
-            tc::mbar_init(bfullq_bar(a), 4); tc::mbar_init(bemptyq_bar(a), 4);
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS);
+            tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
@@ -319,8 +319,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         *reinterpret_cast<uint2 *>(slot + HALF_SLOT + off) = lv;
                     }
                     tc::fence_proxy_async();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
+                    mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
                 }
         }
     } else if (warp >= EPI_WARP0 && warp < SCAT_WARP0) {
@@ -445,8 +444,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
                     }
                 }
-                __syncwarp();
-                if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
+                tc::mbar_arrive(bemptyq_bar(b));
             }
         }
     }
