@@ -365,19 +365,13 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 tc::tc_fence_after();
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 5, acc_it);   // EPI: tile complete in TMEM
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
-                // 128 columns in 8 pieces of 16, TMEM loads double-buffered in registers
-                uint32_t va[16], vb[16];
-                tc::tmem_ld16(taddr, va);
 #pragma unroll 1
-                for (int c = 0; c < BN / 2 / 16; c += 2) {
-                    tc::tmem_ld_wait_dep16(va);
-                    tc::tmem_ld16(taddr + (c + 1) * 16, vb);
-                    if (uniform) rm.chunk16_uniform(va, wb + c * 16, rsg, col0 + c * 16);
-                    else         rm.chunk16_scaled(va, wb + c * 16, wb + 128 + c * 16, rs, col0 + c * 16);
-                    tc::tmem_ld_wait_dep16(vb);
-                    if (c + 2 < BN / 2 / 16) tc::tmem_ld16(taddr + (c + 2) * 16, va);
-                    if (uniform) rm.chunk16_uniform(vb, wb + (c + 1) * 16, rsg, col0 + (c + 1) * 16);
-                    else         rm.chunk16_scaled(vb, wb + (c + 1) * 16, wb + 128 + (c + 1) * 16, rs, col0 + (c + 1) * 16);
+                for (int c = 0; c < BN / 2 / 32; ++c) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(taddr + c * 32, v);
+                    tc::tmem_ld_wait_dep(v);
+                    if (uniform) rm.chunk_uniform(v, wb + c * 32, rsg, col0 + c * 32);
+                    else         rm.chunk(v, wb + c * 32, wb + 128 + c * 32, rs, col0 + c * 32);
                 }
                 tc::tc_fence_before();
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 6, acc_it);   // EPI: this warp drained its half
