@@ -127,14 +127,18 @@ size_t som_b200_shard_workspace_bytes(int64_t n, int k, int d);
  * neighbourhood evaluated on the fly for every (bmu, neuron) pair.  Replaces
  * neighborhoods.py:14-130 and xpysom.py:434-441.  num (K,D) and den (K) are
  * overwritten.  tables_dev is scratch of som_b200_neigh_table_floats(gx,gy)
- * floats.  Returns SOM_E_SHAPE for the combinations the reference rejects
+ * floats (tables_floats says how many were given).  Returns SOM_E_SHAPE for the combinations the reference rejects
  * (triangle on a hexagonal map; mexican_hat + compact_support on a rectangular
  * map with gx != gy, whose broadcast raises in neighborhoods.py:69-71). */
 int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy, int d,
                          int topology, int neigh_kind, double sigma, double eta,
                          double std_coeff, int compact_support,
-                         float *num_dev, float *den_dev, float *tables_dev, void *stream);
+                         float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats, void *stream);
+/* minimum scratch (factor tables only: the direct K^2 D kernel is used) */
 size_t som_b200_neigh_table_floats(int gx, int gy);
+/* scratch that also holds the intermediates of the two-pass separable path (rectangular gaussian / bubble /
+ * triangle on maps of >= 1024 neurons: 2 K (gx+gy) D flops instead of 2 K^2 D) */
+size_t som_b200_neigh_scratch_floats(int gx, int gy, int d);
 
 /* M: W <- den != 0 ? num/den : W   (XPySom._merge_updates, xpysom.py:446-455). */
 int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev,

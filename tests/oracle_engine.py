@@ -30,7 +30,7 @@ class OracleEngine:
     def workspace(self, n, k, d):
         return torch.empty(1, dtype=torch.uint8)
 
-    def neigh_tables(self, gx, gy):
+    def neigh_tables(self, gx, gy, d=None):
         return torch.empty(1)
 
     def prepare_codebook(self, w, dist_kind, p, ws):

@@ -172,6 +172,35 @@ def test_neigh_apply_matches_reference_tables(eng):
     print("\n[neigh_apply] %d reference tables, worst rel err %.2e" % (len(cases), worst))
 
 
+@pytest.mark.parametrize("fn,compact", [("gaussian", False), ("gaussian", True), ("bubble", False), ("triangle", False),
+                                        ("triangle", True), ("mexican_hat", False)])
+@pytest.mark.parametrize("topology", ["rectangular", "hexagonal"])
+def test_neigh_apply_large_map_separable_path(eng, fn, compact, topology):
+    """Maps of >= 1024 neurons: rectangular product-form neighbourhoods take the two-pass separable path,
+    everything else the direct kernel; both must agree with the oracle's H^T S."""
+    from xpysom_dask_b200 import _lib
+    if topology == "hexagonal" and fn == "triangle":
+        pytest.skip("rejected by the reference")
+    gx, gy, d = 40, 30, 20
+    K = gx * gy
+    rng = np.random.RandomState(1)
+    S = rng.randn(K, d).astype(np.float32)
+    c = rng.randint(0, 30, size=K).astype(np.float32)
+    S[c == 0] = 0
+    spec = so.SomSpec(gx=gx, gy=gy, dim=d, sigma=1.0, neighborhood_function=fn, topology=topology, compact_support=compact)
+    for sigma in (7.3, 1.0):
+        H = so.neighborhood_table(spec, sigma).astype(np.float64)
+        Sd, cd = torch.from_numpy(S).cuda(), torch.from_numpy(c).cuda()
+        num, den = eng.empty(K, d), eng.empty(K)
+        eng.neigh_apply(Sd, cd, gx, gy, d, _lib.TOPO[topology], _lib.NEIGH[fn], sigma, 0.5, 0.5, compact, num, den,
+                        eng.neigh_tables(gx, gy, d))
+        torch.cuda.synchronize()
+        num_ref, den_ref = 0.5 * H.T @ S.astype(np.float64), 0.5 * H.T @ c.astype(np.float64)
+        e1 = np.abs(num.cpu().numpy() - num_ref).max() / np.abs(num_ref).max()
+        e2 = np.abs(den.cpu().numpy() - den_ref).max() / np.abs(den_ref).max()
+        assert e1 < 1e-5 and e2 < 1e-5, (fn, compact, topology, sigma, e1, e2)
+
+
 def test_neigh_apply_skips_empty_bmus(eng):
     case = dict(gx=6, gy=5, topology="rectangular", fn="gaussian", compact=False)
     S = np.zeros((30, 4), np.float32); c = np.zeros(30, np.float32)

@@ -22,6 +22,7 @@ SIGNATURES = {
     "som_b200_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "som_b200_shard_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "som_b200_neigh_table_floats": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "som_b200_neigh_scratch_floats": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "som_b200_prepare_codebook": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "som_b200_prepare_samples": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p,
@@ -37,7 +38,7 @@ SIGNATURES = {
                                                  ctypes.c_void_p]),
     "som_b200_neigh_apply": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
-                                            ctypes.c_int, c_f32p, c_f32p, c_f32p, ctypes.c_void_p]),
+                                            ctypes.c_int, c_f32p, c_f32p, c_f32p, ctypes.c_size_t, ctypes.c_void_p]),
     "som_b200_merge": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "som_b200_quantize": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int,
                                          c_i32p, c_f32p, c_f32p, ctypes.c_void_p]),

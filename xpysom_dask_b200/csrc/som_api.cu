@@ -117,6 +117,11 @@ size_t som_b200_neigh_table_floats(int gx, int gy) {
     return neigh_table_floats(gx, gy);
 }
 
+size_t som_b200_neigh_scratch_floats(int gx, int gy, int d) {
+    if (gx <= 0 || gy <= 0 || d <= 0) return 0;
+    return neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d);
+}
+
 int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, float p,
                               void *ws_dev, size_t ws_bytes, void *stream) {
     (void)p;
@@ -221,7 +226,7 @@ int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
 
 int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy, int d, int topology,
                          int neigh_kind, double sigma, double eta, double std_coeff, int compact_support,
-                         float *num_dev, float *den_dev, float *tables_dev, void *stream) {
+                         float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats, void *stream) {
     SOM_REQUIRE(s_dev && c_dev && num_dev && den_dev && tables_dev && gx > 0 && gy > 0 && d > 0, SOM_E_BADARG,
                 "neigh_apply: bad argument");
     SOM_REQUIRE(topology == SOM_TOPO_RECTANGULAR || topology == SOM_TOPO_HEXAGONAL, SOM_E_BADARG,
@@ -235,11 +240,16 @@ int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy,
                 SOM_E_SHAPE, "mexican_hat with compact_support broadcasts (n,gx)*(n,gy) in the reference "
                 "(neighborhoods.py:69-71): needs gx == gy");
     SOM_REQUIRE(sigma != 0.0 && std_coeff != 0.0, SOM_E_BADARG, "neigh_apply: sigma and std_coeff must be non-zero");
+    SOM_REQUIRE(tables_floats >= neigh_table_floats(gx, gy), SOM_E_WORKSPACE,
+                "neigh_apply: scratch of %zu floats < %zu", tables_floats, neigh_table_floats(gx, gy));
     DevInfo di;
     int rc = device_info(di);
     if (rc) return rc;
+    // the two-pass separable path needs room for its intermediates after the factor tables
+    float *scratch = tables_floats >= neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d)
+                         ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
     return launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support,
-                              num_dev, den_dev, tables_dev, di.sm, (cudaStream_t)stream);
+                              num_dev, den_dev, tables_dev, scratch, di.sm, (cudaStream_t)stream);
 }
 
 int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev, int k, int d, void *stream) {
@@ -293,7 +303,7 @@ int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_ho
     SOM_CUDA(cudaMalloc(&b.w, (size_t)K * d * 4));
     SOM_CUDA(cudaMalloc(&b.sc, ((size_t)K * d + K) * 4));
     SOM_CUDA(cudaMalloc(&b.nd, ((size_t)K * d + K) * 4));
-    SOM_CUDA(cudaMalloc(&b.tab, som_b200_neigh_table_floats(cfg->gx, cfg->gy) * 4));
+    SOM_CUDA(cudaMalloc(&b.tab, som_b200_neigh_scratch_floats(cfg->gx, cfg->gy, d) * 4));
     SOM_CUDA(cudaMalloc(&b.ws, ws_bytes));
     SOM_CUDA(cudaMalloc(&b.xs, (size_t)n * 4));
     if (dld != d) SOM_CUDA(cudaMemsetAsync(b.x, 0, (size_t)n * dld * 4, b.st));
@@ -311,7 +321,8 @@ int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_ho
         if ((rc = som_b200_epoch_accumulate(b.x, n, d, dld, b.xs, b.w, K, cfg->dist_kind, cfg->p, cfg->algo, S, c, nullptr,
                                             b.ws, ws_bytes, b.st))) return rc;
         if ((rc = som_b200_neigh_apply(S, c, cfg->gx, cfg->gy, d, cfg->topology, cfg->neigh_kind, sigma_per_epoch[e],
-                                       eta_per_epoch[e], cfg->std_coeff, cfg->compact_support, num, den, b.tab, b.st))) return rc;
+                                       eta_per_epoch[e], cfg->std_coeff, cfg->compact_support, num, den, b.tab,
+                                       som_b200_neigh_scratch_floats(cfg->gx, cfg->gy, d), b.st))) return rc;
         if ((rc = som_b200_merge(b.w, num, den, K, d, b.st))) return rc;
     }
     SOM_CUDA(cudaMemcpyAsync(w_host, b.w, (size_t)K * d * 4, cudaMemcpyDeviceToHost, b.st));

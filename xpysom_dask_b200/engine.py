@@ -54,8 +54,12 @@ class CudaEngine:
         nbytes = self.lib.som_b200_shard_workspace_bytes(int(n), int(k), int(d))
         return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
-    def neigh_tables(self, gx, gy):
-        return self.empty(self.lib.som_b200_neigh_table_floats(int(gx), int(gy)))
+    def neigh_tables(self, gx, gy, d=None):
+        """Scratch of the neighbourhood apply: factor tables, plus (when d is given) the intermediates of
+        the two-pass separable path."""
+        if d is None:
+            return self.empty(self.lib.som_b200_neigh_table_floats(int(gx), int(gy)))
+        return self.empty(self.lib.som_b200_neigh_scratch_floats(int(gx), int(gy), int(d)))
 
     # -- kernels -----------------------------------------------------------------
     def prepare_codebook(self, w, dist_kind, p, ws):
@@ -110,7 +114,8 @@ class CudaEngine:
         with torch.cuda.device(self.device):
             _lib.check(self.lib.som_b200_neigh_apply(self._p(s), self._p(c), gx, gy, d, topology, neigh_kind,
                                                      float(sigma), float(eta), float(std_coeff), int(bool(compact)),
-                                                     self._p(num), self._p(den), self._p(tables), self._stream()),
+                                                     self._p(num), self._p(den), self._p(tables), tables.numel(),
+                                                     self._stream()),
                        "som_b200_neigh_apply")
         self.launches += 2
 

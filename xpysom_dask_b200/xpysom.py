@@ -218,7 +218,7 @@ class XPySom:
         bmu = eng.empty(n, dtype=torch.int32)
         # per-row power-of-two scales for the fp16-split contraction: once per upload, not per epoch
         xscale = eng.prepare_samples(x) if self._wants_xscale(dist_kind) else None
-        tables = eng.neigh_tables(gx, gy)
+        tables = eng.neigh_tables(gx, gy, d)
         prof = self._profile_events if getattr(self, '_profile', False) else None
 
         for t in range(iter_beg, iter_end):
