@@ -21,13 +21,17 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-# SURVEY §8d synthetic workloads (BASELINE.json configs[1..4]); rows are PER GPU (weak scaling)
+# SURVEY §8d synthetic workloads (BASELINE.json configs[1..4]).  `n` is the number of rows PER GPU (weak
+# scaling): c2 is the metric's own single-GPU configuration; c3/c4/c5 are the 1/8 shards of the named
+# multi-GPU configurations (16M, 8M, 4M rows over 8 GPUs), so that N=8 reproduces the named sizes.
 WORKLOADS = {
     "c2": dict(name="synthetic 1Mx64 f32, 32x32 map, gaussian/euclidean", n=1_000_000, d=64, gx=32, gy=32, kw={}),
-    "c3": dict(name="synthetic 16Mx16 f32, 40x40 map, linear decay", n=16_000_000, d=16, gx=40, gy=40,
-               kw=dict(decay_function="linear")),
-    "c4": dict(name="synthetic 8Mx784 f32, 100x100 map", n=8_000_000, d=784, gx=100, gy=100, kw={}),
-    "c5": dict(name="synthetic 4Mx128 f32, 50x50 hexagonal, mexican_hat, cosine", n=4_000_000, d=128, gx=50, gy=50,
+    "c3": dict(name="synthetic 16Mx16 f32 over 8 GPUs (2M rows per GPU), 40x40 map, linear decay", n=2_000_000, d=16,
+               gx=40, gy=40, kw=dict(decay_function="linear")),
+    "c4": dict(name="synthetic 8Mx784 f32 over 8 GPUs (1M rows per GPU), 100x100 map", n=1_000_000, d=784,
+               gx=100, gy=100, kw={}),
+    "c5": dict(name="synthetic 4Mx128 f32 over 8 GPUs (500k rows per GPU), 50x50 hexagonal, mexican_hat, cosine",
+               n=500_000, d=128, gx=50, gy=50,
                kw=dict(topology="hexagonal", neighborhood_function="mexican_hat", activation_distance="cosine")),
 }
 TOTAL_EPOCHS = 100   # length of the decay schedule the timed epochs are taken from
