@@ -140,6 +140,16 @@ size_t som_b200_neigh_table_floats(int gx, int gy);
  * triangle on maps of >= 1024 neurons: 2 K (gx+gy) D flops instead of 2 K^2 D) */
 size_t som_b200_neigh_scratch_floats(int gx, int gy, int d);
 
+/* Graph-replay variant of som_b200_neigh_apply: sigma and the learning rate are read on the device,
+ * sigma = sched_dev[2e], eta = sched_dev[2e+1] with e = *epoch_dev, so ONE captured CUDA graph of the epoch
+ * (prepare, BMU+accumulate, all-reduce, apply, merge, som_b200_epoch_advance) serves every epoch. */
+int som_b200_neigh_apply_sched(const float *s_dev, const float *c_dev, int gx, int gy, int d,
+                               int topology, int neigh_kind, const double *sched_dev, const int *epoch_dev,
+                               double std_coeff, int compact_support,
+                               float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats, void *stream);
+/* *epoch_dev += 1 (last node of the epoch graph) */
+int som_b200_epoch_advance(int *epoch_dev, void *stream);
+
 /* M: W <- den != 0 ? num/den : W   (XPySom._merge_updates, xpysom.py:446-455). */
 int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev,
                    int k, int d, void *stream);

@@ -39,6 +39,11 @@ SIGNATURES = {
     "som_b200_neigh_apply": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
                                             ctypes.c_int, c_f32p, c_f32p, c_f32p, ctypes.c_size_t, ctypes.c_void_p]),
+    "som_b200_neigh_apply_sched": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                  ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_double,
+                                                  ctypes.c_int, c_f32p, c_f32p, c_f32p, ctypes.c_size_t,
+                                                  ctypes.c_void_p]),
+    "som_b200_epoch_advance": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "som_b200_merge": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "som_b200_quantize": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int,
                                          c_i32p, c_f32p, c_f32p, ctypes.c_void_p]),

@@ -26,16 +26,33 @@ struct NeighParams {
     float  inv_d;         // 1/d,   d = 2 std_coeff^2 sigma^2
     float  two_over_d;    // 2/d
     float  eta;
+    // optional device-side schedule (CUDA-graph replay): sigma = sched[2e], eta = sched[2e+1], e = *epoch
+    const double *sched;
+    const int    *epoch;
+    double std_coeff;
     const float *tx, *ty;     // product factors or squared offsets
     const float *mx, *my;     // compact-support windows (mexican hat only)
 };
+
+__device__ __forceinline__ void neigh_resolve(const NeighParams &P, float &inv_d, float &two_over_d, float &eta) {
+    if (P.sched == nullptr) { inv_d = P.inv_d; two_over_d = P.two_over_d; eta = P.eta; return; }
+    const int e = *P.epoch;
+    const double sigma = P.sched[2 * e];
+    const double dd = 2.0 * P.std_coeff * P.std_coeff * sigma * sigma;
+    inv_d = (float)(1.0 / dd); two_over_d = (float)(2.0 / dd); eta = (float)P.sched[2 * e + 1];
+}
 
 // hexagonal rule of xpysom.py:201-206: rows (gy-1-j) even are shifted by -0.5
 __host__ __device__ inline int hex_shift(int j, int gy) { return ((gy - 1 - j) & 1) == 0 ? 1 : 0; }
 
 // one thread per table entry; all arithmetic in fp64, stored as fp32
 __global__ void neigh_tables_kernel(int gx, int gy, int kind, int compact, int shifted,
-                                    double sigma, double dd, float *tx, float *ty, float *mx, float *my) {
+                                    double sigma, double dd, float *tx, float *ty, float *mx, float *my,
+                                    const double *sched, const int *epoch, double std_coeff) {
+    if (sched != nullptr) {          // schedule read on the device (graph replay)
+        sigma = sched[2 * (*epoch)];
+        dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
+    }
     const int nxe = 3 * gx * gx, nye = gy * gy;
     for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nxe + nye; e += gridDim.x * blockDim.x) {
         const bool isx = e < nxe;
@@ -68,7 +85,7 @@ __global__ void neigh_tables_kernel(int gx, int gy, int kind, int compact, int s
     }
 }
 
-__device__ __forceinline__ float neigh_eval(const NeighParams &P, int bi, int bj, int i, int j) {
+__device__ __forceinline__ float neigh_eval(const NeighParams &P, float inv_d, float two_over_d, int bi, int bj, int i, int j) {
     const int q = P.shifted ? (hex_shift(bj, P.gy) - hex_shift(j, P.gy) + 1) : 1;
     const int xe = (q * P.gx + bi) * P.gx + i;
     const int ye = bj * P.gy + j;
@@ -81,7 +98,7 @@ __device__ __forceinline__ float neigh_eval(const NeighParams &P, int bi, int bj
         px *= __ldg(P.mx + xe) * wy;
     }
     const float p = px + fy;
-    return expf(-p * P.inv_d) * (1.f - P.two_over_d * p);
+    return expf(-p * inv_d) * (1.f - two_over_d * p);
 }
 
 constexpr int NB_M = 64, NB_N = 64, NB_K = 16, NB_THREADS = 256;
@@ -93,6 +110,8 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
     __shared__ __align__(16) float Ss[NB_K][NB_N + 4];
     __shared__ float cs[NB_K];
     const int K = P.gx * P.gy, D = P.d;
+    float inv_d, two_over_d, eta;
+    neigh_resolve(P, inv_d, two_over_d, eta);
     const int k0 = blockIdx.x * NB_M, n0 = blockIdx.y * NB_N;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 
@@ -124,7 +143,7 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
             if (cb != 0.f) {   // an empty BMU contributes nothing (S[b] = 0 as well)
                 const int bi = b / P.gy, bj = b % P.gy;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) h4[e] = neigh_eval(P, bi, bj, ki[e], kj[e]);
+                for (int e = 0; e < 4; ++e) h4[e] = neigh_eval(P, inv_d, two_over_d, bi, bj, ki[e], kj[e]);
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int col = n0 + hk + e;
@@ -162,13 +181,13 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
         for (int bb = 0; bb < 4; ++bb) {
             const int col = n0 + tx * 4 + bb;
             if (col < D) {                                                    // g = h * eta (xpysom.py:434)
-                if (gridDim.z == 1) num[(int64_t)kk * D + col] = acc[a][bb] * P.eta;
-                else                atomicAdd(num + (int64_t)kk * D + col, acc[a][bb] * P.eta);
+                if (gridDim.z == 1) num[(int64_t)kk * D + col] = acc[a][bb] * eta;
+                else                atomicAdd(num + (int64_t)kk * D + col, acc[a][bb] * eta);
             }
         }
         if (tx == 0 && blockIdx.y == 0) {
-            if (gridDim.z == 1) den[kk] = dacc[a] * P.eta;
-            else                atomicAdd(den + kk, dacc[a] * P.eta);
+            if (gridDim.z == 1) den[kk] = dacc[a] * eta;
+            else                atomicAdd(den + kk, dacc[a] * eta);
         }
     }
 }
@@ -182,7 +201,8 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
 constexpr int AX_THREADS = 128, AX_J = 16;
 __global__ void __launch_bounds__(AX_THREADS)
 axis_contract_kernel(const float *__restrict__ in, const float *__restrict__ M, int ldm, int A, int B, int J, int64_t C,
-                     float scale, float *__restrict__ out) {
+                     float scale, const double *__restrict__ sched, const int *__restrict__ epoch, float *__restrict__ out) {
+    if (sched != nullptr) scale = (float)sched[2 * (*epoch) + 1];      // eta of the current epoch (graph replay)
     extern __shared__ float Ms[];                         // [B][AX_J] slice of M for this block's j range
     const int a = blockIdx.z, j0 = blockIdx.y * AX_J;
     const int64_t c = (int64_t)blockIdx.x * AX_THREADS + threadIdx.x;
@@ -215,10 +235,10 @@ axis_contract_kernel(const float *__restrict__ in, const float *__restrict__ M, 
 }
 
 inline int launch_axis_contract(const float *in, const float *M, int ldm, int A, int B, int J, int64_t C, float scale,
-                                float *out, cudaStream_t st) {
+                                const double *sched, const int *epoch, float *out, cudaStream_t st) {
     dim3 grid((unsigned)ceil_div(C, AX_THREADS), (unsigned)ceil_div(J, AX_J), (unsigned)A);
     const size_t smem = (size_t)B * AX_J * sizeof(float);
-    axis_contract_kernel<<<grid, AX_THREADS, smem, st>>>(in, M, ldm, A, B, J, C, scale, out);
+    axis_contract_kernel<<<grid, AX_THREADS, smem, st>>>(in, M, ldm, A, B, J, C, scale, sched, epoch, out);
     return check_cuda(cudaGetLastError(), "axis_contract_kernel launch");
 }
 
@@ -236,8 +256,10 @@ inline size_t neigh_table_floats(int gx, int gy) {
 
 inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, int d, int topology, int kind,
                               double sigma, double eta, double std_coeff, int compact,
-                              float *num, float *den, float *tables, float *scratch, int sm_count, cudaStream_t st) {
+                              float *num, float *den, float *tables, float *scratch, int sm_count, cudaStream_t st,
+                              const double *sched = nullptr, const int *epoch = nullptr) {
     NeighParams P;
+    P.sched = sched; P.epoch = epoch; P.std_coeff = std_coeff;
     P.gx = gx; P.gy = gy; P.d = d; P.topology = topology; P.kind = kind; P.compact = compact ? 1 : 0;
     // bubble and triangle use integer grid indices on both topologies (xpysom.py:266-269, 277-278)
     P.shifted = (topology == SOM_TOPO_HEXAGONAL && (kind == SOM_NEIGH_GAUSSIAN || kind == SOM_NEIGH_MEXICAN_HAT)) ? 1 : 0;
@@ -250,7 +272,8 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
     float *tx = tables, *ty = tx + nxe, *mx = ty + nye, *my = mx + nxe;
     P.tx = tx; P.ty = ty; P.mx = mx; P.my = my;
     const int tot = (int)(nxe + nye);
-    neigh_tables_kernel<<<(tot + 255) / 256, 256, 0, st>>>(gx, gy, kind, P.compact, P.shifted, sigma, dd, tx, ty, mx, my);
+    neigh_tables_kernel<<<(tot + 255) / 256, 256, 0, st>>>(gx, gy, kind, P.compact, P.shifted, sigma, dd, tx, ty, mx, my,
+                                                           sched, epoch, std_coeff);
     int rc = check_cuda(cudaGetLastError(), "neigh_tables_kernel launch");
     if (rc) return rc;
     const int K = gx * gy;
@@ -259,11 +282,11 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
         const float *TX = tx + (size_t)gx * gx, *TY = ty;
         float *T = scratch, *Tc = scratch + (size_t)K * d;
         // pass 1 (over bj): T[bi, j, :] = sum_bj TY[bj][j] S[bi, bj, :]      in: (gx, gy, D)
-        if ((rc = launch_axis_contract(S, TY, gy, gx, gy, gy, d, 1.f, T, st))) return rc;
-        if ((rc = launch_axis_contract(c, TY, gy, gx, gy, gy, 1, 1.f, Tc, st))) return rc;
+        if ((rc = launch_axis_contract(S, TY, gy, gx, gy, gy, d, 1.f, nullptr, nullptr, T, st))) return rc;
+        if ((rc = launch_axis_contract(c, TY, gy, gx, gy, gy, 1, 1.f, nullptr, nullptr, Tc, st))) return rc;
         // pass 2 (over bi): num[i, (j, :)] = eta * sum_bi TX[bi][i] T[bi, (j, :)]   in: (1, gx, gy*D)
-        if ((rc = launch_axis_contract(T, TX, gx, 1, gx, gx, (int64_t)gy * d, P.eta, num, st))) return rc;
-        return launch_axis_contract(Tc, TX, gx, 1, gx, gx, gy, P.eta, den, st);
+        if ((rc = launch_axis_contract(T, TX, gx, 1, gx, gx, (int64_t)gy * d, P.eta, sched, epoch, num, st))) return rc;
+        return launch_axis_contract(Tc, TX, gx, 1, gx, gx, gy, P.eta, sched, epoch, den, st);
     }
     const int gxy = (int)(ceil_div(K, NB_M) * ceil_div(d, NB_N));
     int slices = (2 * sm_count + gxy - 1) / gxy;                 // aim for >= 2 CTAs per SM

@@ -252,6 +252,42 @@ int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy,
                               num_dev, den_dev, tables_dev, scratch, di.sm, (cudaStream_t)stream);
 }
 
+// same as som_b200_neigh_apply, with sigma and eta read ON THE DEVICE from sched_dev[2e], sched_dev[2e+1],
+// e = *epoch_dev, so that one captured CUDA graph can be replayed for every epoch
+int som_b200_neigh_apply_sched(const float *s_dev, const float *c_dev, int gx, int gy, int d, int topology,
+                               int neigh_kind, const double *sched_dev, const int *epoch_dev, double std_coeff,
+                               int compact_support, float *num_dev, float *den_dev, float *tables_dev,
+                               size_t tables_floats, void *stream) {
+    SOM_REQUIRE(s_dev && c_dev && num_dev && den_dev && tables_dev && sched_dev && epoch_dev && gx > 0 && gy > 0 && d > 0,
+                SOM_E_BADARG, "neigh_apply_sched: bad argument");
+    SOM_REQUIRE(topology == SOM_TOPO_RECTANGULAR || topology == SOM_TOPO_HEXAGONAL, SOM_E_BADARG,
+                "neigh_apply_sched: unknown topology %d", topology);
+    SOM_REQUIRE(neigh_kind >= SOM_NEIGH_GAUSSIAN && neigh_kind <= SOM_NEIGH_TRIANGLE, SOM_E_BADARG,
+                "neigh_apply_sched: unknown neighbourhood %d", neigh_kind);
+    SOM_REQUIRE(!(neigh_kind == SOM_NEIGH_TRIANGLE && topology == SOM_TOPO_HEXAGONAL), SOM_E_SHAPE,
+                "triangle is not available on a hexagonal map (xpysom.py:272-279)");
+    SOM_REQUIRE(!(neigh_kind == SOM_NEIGH_MEXICAN_HAT && compact_support && topology == SOM_TOPO_RECTANGULAR && gx != gy),
+                SOM_E_SHAPE, "mexican_hat with compact_support needs gx == gy (neighborhoods.py:69-71)");
+    SOM_REQUIRE(std_coeff != 0.0, SOM_E_BADARG, "neigh_apply_sched: std_coeff must be non-zero");
+    SOM_REQUIRE(tables_floats >= neigh_table_floats(gx, gy), SOM_E_WORKSPACE,
+                "neigh_apply_sched: scratch of %zu floats < %zu", tables_floats, neigh_table_floats(gx, gy));
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    float *scratch = tables_floats >= neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d)
+                         ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
+    return launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, 1.0, 1.0, std_coeff, compact_support,
+                              num_dev, den_dev, tables_dev, scratch, di.sm, (cudaStream_t)stream, sched_dev, epoch_dev);
+}
+
+__global__ void epoch_advance_kernel(int *epoch) { *epoch += 1; }
+
+int som_b200_epoch_advance(int *epoch_dev, void *stream) {
+    SOM_REQUIRE(epoch_dev, SOM_E_BADARG, "epoch_advance: NULL pointer");
+    epoch_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(epoch_dev);
+    return check_cuda(cudaGetLastError(), "epoch_advance_kernel launch");
+}
+
 int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev, int k, int d, void *stream) {
     SOM_REQUIRE(w_dev && num_dev && den_dev && k > 0 && d > 0, SOM_E_BADARG, "merge: bad argument");
     const int64_t tot = (int64_t)k * d;

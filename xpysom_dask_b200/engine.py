@@ -119,6 +119,21 @@ class CudaEngine:
                        "som_b200_neigh_apply")
         self.launches += 2
 
+    def neigh_apply_sched(self, s, c, gx, gy, d, topology, neigh_kind, sched, epoch, std_coeff, compact, num, den, tables):
+        """neigh_apply with sigma / eta read on the device from sched[2e], sched[2e+1], e = epoch[0]."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_neigh_apply_sched(self._p(s), self._p(c), gx, gy, d, topology, neigh_kind,
+                                                           self._p(sched), self._p(epoch), float(std_coeff),
+                                                           int(bool(compact)), self._p(num), self._p(den),
+                                                           self._p(tables), tables.numel(), self._stream()),
+                       "som_b200_neigh_apply_sched")
+        self.launches += 2
+
+    def epoch_advance(self, epoch):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_epoch_advance(self._p(epoch), self._stream()), "som_b200_epoch_advance")
+        self.launches += 1
+
     def merge(self, w, num, den):
         k, d = w.shape
         with torch.cuda.device(self.device):

@@ -57,13 +57,15 @@ class XPySom:
                  decay_function='exponential', neighborhood_function='gaussian', std_coeff=0.5,
                  topology='rectangular', activation_distance='euclidean', activation_distance_kwargs={},
                  random_seed=None, n_parallel=0, compact_support=False, xp=None, use_dask=False,
-                 dask_chunks='auto', *, device=None, algo='auto', process_group=None, engine=None):
+                 dask_chunks='auto', *, device=None, algo='auto', process_group=None, engine=None,
+                 use_cuda_graph=True):
         """Same arguments as the reference constructor (xpysom.py:73-82).
 
         Keyword-only additions: ``device`` (CUDA device of this process),
         ``algo`` ('auto' | 'tc' | 'simt': which BMU kernel), ``process_group``
         (a torch.distributed group, or True for the default group: this process
-        holds one shard of the samples) and ``engine`` (test hook).
+        holds one shard of the samples), ``engine`` (test hook) and ``use_cuda_graph`` (replay one
+        captured CUDA graph per epoch instead of launching the epoch's kernels one by one).
         """
         if sigma >= x or sigma >= y:
             warn('Warning: sigma is too high for the dimension of the map.')
@@ -119,6 +121,7 @@ class XPySom:
         self._device = device
         self._process_group = process_group
         self._engine = engine
+        self._use_cuda_graph = bool(use_cuda_graph)
         self._profile = False              # bench.py: record CUDA events around the BMU / accumulate kernels
         self._profile_events = []
         self.stats = {}
@@ -221,27 +224,64 @@ class XPySom:
         tables = eng.neigh_tables(gx, gy, d)
         prof = self._profile_events if getattr(self, '_profile', False) else None
 
-        for t in range(iter_beg, iter_end):
-            eta = self._decay_function(self._learning_rate, self._learning_rateN, t, num_epochs)
-            sig = self._decay_function(self._sigma, self._sigmaN, t, num_epochs)   # same rule (xpysom.py:541-543)
-            sc.zero_()
-            eng.prepare_codebook(w, dist_kind, p, ws)
-            if prof is not None:
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-                ev[0].record()
-            # K1/K2 + K3: distance + argmin + per-BMU sums (one fused kernel on the tensor-core path)
-            eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
-            if prof is not None:
-                ev[1].record()
-                prof.append(ev)
+        def schedule(t):
+            eta_t = self._decay_function(self._learning_rate, self._learning_rateN, t, num_epochs)
+            sig_t = self._decay_function(self._sigma, self._sigmaN, t, num_epochs)   # same rule (xpysom.py:541-543)
+            return sig_t, eta_t
+
+        def reduce_shards():
             if group is not None:
                 import torch.distributed as dist
                 dist.all_reduce(sc, op=dist.ReduceOp.SUM, group=group)
-            eng.neigh_apply(S, c, gx, gy, d, topo, neigh, sig, eta, self._std_coeff, self.compact_support,
-                            num, den, tables)
-            eng.merge(w, num, den)
-            if verbose:
-                print('\r [ %d / %d ]' % (t + 1, num_epochs), end='')
+
+        n_ep = iter_end - iter_beg
+        graphed = (self._use_cuda_graph and prof is None and not verbose and n_ep >= 3
+                   and getattr(eng, 'name', '') == 'cuda')
+        if graphed:
+            # One CUDA graph of the whole epoch, replayed n_ep - 1 times: sigma / eta live in a device-side
+            # schedule indexed by a device-side epoch counter, so the captured launches never change.
+            sched = eng.to_device(torch.tensor([[float(v) for v in schedule(t)] for t in range(iter_beg, iter_end)],
+                                               dtype=torch.float64))
+            epoch_idx = eng.zeros(1, dtype=torch.int32)
+
+            def epoch_body():
+                sc.zero_()
+                eng.prepare_codebook(w, dist_kind, p, ws)
+                eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
+                reduce_shards()
+                eng.neigh_apply_sched(S, c, gx, gy, d, topo, neigh, sched, epoch_idx, self._std_coeff,
+                                      self.compact_support, num, den, tables)
+                eng.merge(w, num, den)
+                eng.epoch_advance(epoch_idx)
+
+            launches0 = eng.launches
+            epoch_body()                               # first epoch eagerly: warms up every kernel / NCCL
+            per_epoch = eng.launches - launches0
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                epoch_body()                           # captured, not executed
+            for _ in range(n_ep - 1):
+                graph.replay()
+            eng.launches = launches0 + per_epoch * n_ep    # kernels actually executed (capture launches none)
+        else:
+            for t in range(iter_beg, iter_end):
+                sig, eta = schedule(t)
+                sc.zero_()
+                eng.prepare_codebook(w, dist_kind, p, ws)
+                if prof is not None:
+                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                    ev[0].record()
+                # K1/K2 + K3: distance + argmin + per-BMU sums (one fused kernel on the tensor-core path)
+                eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
+                if prof is not None:
+                    ev[1].record()
+                    prof.append(ev)
+                reduce_shards()
+                eng.neigh_apply(S, c, gx, gy, d, topo, neigh, sig, eta, self._std_coeff, self.compact_support,
+                                num, den, tables)
+                eng.merge(w, num, den)
+                if verbose:
+                    print('\r [ %d / %d ]' % (t + 1, num_epochs), end='')
 
         self._weights = w.cpu().numpy().reshape(gx, gy, d)      # synchronises; fp32 like xpysom.py:580-583
         if verbose:
