@@ -160,7 +160,7 @@ def run_gpu(args, wl, rank, world, local_rank):
 
     x_host = torch.from_numpy(synth(n, d, seed=rank)).pin_memory()
     x_dev = x_host.to(dev)
-    som = XPySom(gx, gy, d, random_seed=0, algo=args.algo, device=dev,
+    som = XPySom(gx, gy, d, random_seed=0, algo=args.algo, device=dev, use_cuda_graph=args.cuda_graph,
                  process_group=True if world > 1 else None, **wl["kw"])
     eng = som._get_engine()
 
@@ -170,8 +170,6 @@ def run_gpu(args, wl, rank, world, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput: K epochs in ONE train() call ------------------------
-    # train() launches its first epoch kernel by kernel and replays one captured CUDA graph for the
-    # others; the timed call covers exactly `steps` epochs (its own first one included).
     som.train(x_dev, TOTAL_EPOCHS, iter_beg=0, iter_end=args.warmup)             # warm-up epochs
     sampler = ClockSampler(local_rank)
     barrier()
@@ -288,6 +286,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--algo", default="auto", choices=["auto", "tc16", "tc", "simt"])
     ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug)")
+    ap.add_argument("--cuda-graph", action="store_true", help="replay one captured CUDA graph per epoch")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -320,6 +320,25 @@ def test_api_known_answers_from_reference_tests():
     assert hexs.quantization_error(g["hex_data"]) == pytest.approx(float(g["hex_qe"]), rel=1e-5)
 
 
+def test_cuda_graph_replay_matches_eager_launches():
+    """use_cuda_graph=True replays one captured graph per epoch with sigma / eta read from a device-side
+    schedule; after a few epochs it must land where the kernel-by-kernel path lands."""
+    from xpysom_dask_b200 import XPySom
+    data = U.blobs(8000, 32, seed=21, centres=24)
+    for kw in (dict(), dict(topology="hexagonal", neighborhood_function="mexican_hat", decay_function="linear")):
+        a = XPySom(12, 11, 32, sigma=2.0, random_seed=4, use_cuda_graph=False, **kw)
+        b = XPySom(12, 11, 32, sigma=2.0, random_seed=4, use_cuda_graph=True, **kw)
+        a.train(data, 6)
+        b.train(data, 6)
+        assert U.codebook_rel_err(b._weights, a._weights) < 2e-3      # free-running: BMU flips amplify (SURVEY 4.4)
+        assert b.quantization_error(data) == pytest.approx(a.quantization_error(data), rel=1e-3)
+        # schedule bookkeeping: resuming mid-schedule through the graph path
+        a2 = XPySom(12, 11, 32, sigma=2.0, random_seed=4, use_cuda_graph=True, **kw)
+        a2.train(data, 6, iter_beg=0, iter_end=3)
+        a2.train(data, 6, iter_beg=3, iter_end=6)
+        assert U.codebook_rel_err(a2._weights, a._weights) < 2e-3
+
+
 def test_train_host_c_abi_matches_class():
     """The whole-job C entry with HOST buffers (what the reference would bind) == the Python class.
     Teacher-forced, one epoch per call from the same W_t: free-running epochs amplify any BMU flip

@@ -58,14 +58,15 @@ class XPySom:
                  topology='rectangular', activation_distance='euclidean', activation_distance_kwargs={},
                  random_seed=None, n_parallel=0, compact_support=False, xp=None, use_dask=False,
                  dask_chunks='auto', *, device=None, algo='auto', process_group=None, engine=None,
-                 use_cuda_graph=True):
+                 use_cuda_graph=False):
         """Same arguments as the reference constructor (xpysom.py:73-82).
 
         Keyword-only additions: ``device`` (CUDA device of this process),
         ``algo`` ('auto' | 'tc' | 'simt': which BMU kernel), ``process_group``
         (a torch.distributed group, or True for the default group: this process
         holds one shard of the samples), ``engine`` (test hook) and ``use_cuda_graph`` (replay one
-        captured CUDA graph per epoch instead of launching the epoch's kernels one by one).
+        captured CUDA graph per epoch instead of launching the epoch's ~10 kernels one by one; capture
+        costs a few milliseconds, so it only pays off for runs of several hundred epochs on small maps).
         """
         if sigma >= x or sigma >= y:
             warn('Warning: sigma is too high for the dimension of the map.')
