@@ -59,7 +59,9 @@ def test_kernels_agree_up_to_near_ties(eng, name, n, d, gx, gy, dist):
         if diff.numel():
             sa = _score64(x[diff], w, got[diff], dist)
             sb = _score64(x[diff], w, ref[diff], dist)
-            scale = (x[diff].double() ** 2).sum(1) + sb.abs() if dist == "euclidean" else torch.ones_like(sb)
+            # euclidean: |x|^2 + |d| (the epsilon of the parity criterion); cosine: the kernels minimise
+            # -x.w/|w|, which is |x| times the cosine similarity the criterion is stated on
+            scale = (x[diff].double() ** 2).sum(1) + sb.abs() if dist == "euclidean" else x[diff].double().norm(dim=1)
             worst = ((sa - sb).abs() / scale).max().item()
         else:
             worst = 0.0
