@@ -118,13 +118,13 @@ def test_update_fixed_point_and_empty_neurons():
     data = np.tile(v, (5000, 1))
     som = XPySom(32, 32, 64, random_seed=0)
     som.train(data, 3, iter_beg=0, iter_end=1)
-    np.testing.assert_allclose(som._weights, np.broadcast_to(v, som._weights.shape), rtol=3e-5)   # fp32 sum of 5000 rows
+    np.testing.assert_allclose(som._weights, np.broadcast_to(v, som._weights.shape), rtol=1.5e-4)   # fp32 running sum of 5000 identical rows: biased rounding
     som = XPySom(16, 16, 64, sigma=0.9, sigmaN=0.9, neighborhood_function="bubble", random_seed=1)
     w0 = np.asarray(som._weights, dtype=np.float32).copy()
     som.train(data, 2, iter_beg=0, iter_end=1)
     moved = np.abs(som._weights - w0).max(axis=2) > 0
     assert moved.sum() == 1                                    # only the single BMU changes
-    np.testing.assert_allclose(som._weights[moved][0], v, rtol=3e-5)
+    np.testing.assert_allclose(som._weights[moved][0], v, rtol=1.5e-4)
 
 
 def test_full_size_config2_epochs_reduce_quantization_error():
