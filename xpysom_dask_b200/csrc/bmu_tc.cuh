@@ -1,30 +1,14 @@
-// K1: tensor-core distance contraction with a fused BMU argmin (sm_100a).
+// Shared building blocks of the tensor-core BMU kernels (bmu_tc2.cuh: kind::tf32, bmu_tc3.cuh:
+// kind::f16): PTX wrappers for mbarrier / TMA / tcgen05 / TMEM, the shared-memory matrix descriptor,
+// the running-argmin epilogue state, the fused-accumulate arguments and the TMA tensor-map helpers.
 //
-// Replaces xp.dot(x, w.T) + w_sq.T + argmin of the reference
-// (distances.py:22-23 / 55-59 and xpysom.py:416) for the Euclidean and cosine
-// activation distances.  score[r, k] = x_r . w'_k + bias_k is minimised over k,
-// with w' = -2 w, bias = |w|^2 (euclidean) or w' = -w/|w|, bias = 0 (cosine),
-// both prepared once per epoch by prepare_codebook_kernel.
-//
-// fp32 accuracy from TF32 tensor cores: every fp32 operand is split into
-// hi = rna_tf32(v) and lo = rna_tf32(v - hi) and three MMAs accumulate
-// lo*hi + hi*lo + hi*hi into the same fp32 TMEM accumulator (the lo*lo term,
-// ~2^-22 relative, is dropped).  W is split by the prepare kernel; X is split
-// inside this kernel, in shared memory, by a converter warpgroup, so X is read
-// from HBM exactly once and never re-written.
-//
-// Pipeline (one CTA per SM, persistent over 128-row tiles of X):
-//   warp 0      TMA producer   X chunk [128 x 32] + W'hi/W'lo chunks [256 x 32], SWIZZLE_128B
-//   warp 1      MMA issuer     tcgen05.mma.kind::tf32, M=128 N=256 K=8, accumulators in TMEM (2 x 256 cols)
-//   warps 2-5   converter      X chunk -> hi (in place) and lo, generic->async proxy fence
-//   warps 6-9   epilogue       tcgen05.ld 32 columns at a time, + bias, running (min, argmin) per row;
-//                              then (fused K3) S[bmu] += x for the tile's 128 rows, re-read from L2
-// The (n, K) score matrix lives only in TMEM.
-//
-// Fused accumulate (acc.S != nullptr): once a 128-row tile has its BMUs, the epilogue warps add the
-// tile's rows into the (K, D) accumulator with red.global.add.v4.f32 — the rows were just streamed
-// through L2 by TMA, so HBM sees X once per epoch — and bump exact int32 counts; the last CTA to
-// finish folds the counts into the fp32 c vector (fp32 increments of 1 are lost above 2^24).
+// Contract of those kernels.  They replace xp.dot(x, w.T) + w_sq.T + argmin of the reference
+// (distances.py:22-23 / 55-59 and xpysom.py:416) for the Euclidean and cosine activation distances:
+// score[r, k] = x_r . w'_k + bias_k is minimised over k, with w' = -2 w, bias = |w|^2 (euclidean) or
+// w' = -w/|w|, bias = 0 (cosine), both prepared once per epoch (misc.cuh).  fp32 accuracy on
+// 11-bit-significand tensor-core inputs comes from splitting every fp32 operand into hi + lo and
+// accumulating lo*hi + hi*lo + hi*hi in the fp32 TMEM accumulator (the lo*lo term, ~2^-22
+// relative, is dropped).  The (n, K) score matrix lives only in TMEM.
 #pragma once
 #include <cuda.h>
 #include "common.cuh"
@@ -32,13 +16,7 @@
 namespace somb200 {
 namespace tc {
 
-constexpr int BM = 128, BN = 256, BK = 32, STAGES = 2, UMMA_K = 8;
-constexpr int A_BYTES = BM * BK * 4;   // 16 KB
-constexpr int B_BYTES = BN * BK * 4;   // 32 KB
-constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;   // A_hi | A_lo | B_hi | B_lo = 96 KB
-constexpr int NUM_THREADS = 320;
-constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * BN * 4 /*bias tiles*/ + 256 /*barriers*/ + 1024 /*align slack*/;
+constexpr int BM = 128;     // sample rows per CTA (TMEM lanes)
 
 // ---- PTX wrappers ------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -114,19 +92,6 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
                    "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
                  : "r"(taddr) : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                   "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                 : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tmem_ld_wait_dep16(uint32_t (&v)[16]) {
-    asm volatile("tcgen05.wait::ld.sync.aligned;"
-                 : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]),
-                   "+r"(v[8]), "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
-                 :: "memory");
-}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 // wait::ld that also "touches" the destination registers, so the compiler cannot schedule their
 // consumers above the wait
@@ -152,8 +117,8 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
     d |= (uint64_t)2 << 61;
     return d;
 }
-// instruction descriptor: D=f32 (bit4), A=B=tf32 (2 at bits 7 and 10), K-major both, N>>3 at 17, M>>4 at 24
-constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// (instruction descriptors: D format at bit 4, A / B formats at bits 7 / 10, N >> 3 at bit 17, M >> 4 at
+// bit 24 — kIdesc2 in bmu_tc2.cuh, kIdescF16 in bmu_tc3.cuh)
 
 // Running argmin of the epilogue.  A single (best, index) pair would make every one of the K compares
 // wait for the previous one (FSETP -> FSEL latency per element, ~2x the MMA time of a D=64 tile);
@@ -195,23 +160,6 @@ struct RunMin {
     }
 };
 
-// Drain one accumulator tile (NCHUNK x 32 columns) into the running argmin.  TMEM loads are double
-// buffered in registers: the load of chunk c+1 is in flight while chunk c is compared.
-template <int NCHUNK>
-__device__ __forceinline__ void drain_accumulator(RunMin &rm, uint32_t taddr, const float *bs, int colbase) {
-    uint32_t va[32], vb[32];
-    tmem_ld32(taddr, va);
-#pragma unroll 1
-    for (int c = 0; c < NCHUNK; c += 2) {
-        tmem_ld_wait_dep(va);
-        tmem_ld32(taddr + (c + 1) * 32, vb);
-        rm.chunk(va, bs + c * 32, colbase + c * 32);
-        tmem_ld_wait_dep(vb);
-        if (c + 2 < NCHUNK) tmem_ld32(taddr + (c + 2) * 32, va);
-        rm.chunk(vb, bs + (c + 1) * 32, colbase + (c + 1) * 32);
-    }
-}
-
 __device__ __forceinline__ float tf32_rna_dev(float v) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
@@ -236,205 +184,6 @@ struct FusedAcc {
     int vec;             // rows are 16-byte aligned and d % 4 == 0: 128-bit path
     int dbg;             // experiments only (SOM_B200_DBG); 0 in production
 };
-
-__global__ void __launch_bounds__(NUM_THREADS, 1)
-bmu_tc_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
-              const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
-              int64_t n, int num_m_tiles, int num_n_tiles, int num_k_blocks,
-              int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;   // SWIZZLE_128B needs 1024-byte alignment
-    uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
-
-    float    *bias_s = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);          // [2][BN]
-    uint64_t *bars   = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + 2 * BN * 4);
-    // barrier slots: full[S], ready[S], empty[S], tmem_full[2], tmem_empty[2], then the TMEM base slot
-    const uint32_t bar0 = smem_u32(bars);
-    auto full_bar  = [&](int s) { return bar0 + 8u * s; };
-    auto ready_bar = [&](int s) { return bar0 + 8u * (STAGES + s); };
-    auto empty_bar = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * STAGES + 2 + a); };
-    volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + 3 * STAGES + 4);
-    __shared__ int bmu_s[BM];          // BMUs of the current tile, shared among the epilogue warps
-    __shared__ unsigned int last_cta;
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-    if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(ready_bar(s), 128); mbar_init(empty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
-        fence_barrier_init();
-        tma_prefetch_desc(&map_x); tma_prefetch_desc(&map_whi); tma_prefetch_desc(&map_wlo);
-    }
-    if (warp == 1) tmem_alloc(smem_u32((const void *)tmem_slot), 512);
-    tc_fence_before();
-    __syncthreads();
-    tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
-
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            uint32_t it = 0;
-            for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x)
-                for (int nt = 0; nt < num_n_tiles; ++nt)
-                    for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-                        const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(empty_bar(s), ph ^ 1);
-                        const uint32_t st = smem_base + s * STAGE_BYTES;
-                        mbar_expect_tx(full_bar(s), A_BYTES + 2 * B_BYTES);
-                        tma_load_2d(st,                         &map_x,   kb * BK, mt * BM, full_bar(s));
-                        tma_load_2d(st + 2 * A_BYTES,           &map_whi, kb * BK, nt * BN, full_bar(s));
-                        tma_load_2d(st + 2 * A_BYTES + B_BYTES, &map_wlo, kb * BK, nt * BN, full_bar(s));
-                    }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t it = 0, acc_it = 0;
-            for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x)
-                for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
-                    const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
-                    mbar_wait(tempty_bar(a), aph ^ 1);      // epilogue has drained this accumulator
-                    tc_fence_after();
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
-                    for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-                        const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait(full_bar(s), ph);          // W' tiles landed (async proxy)
-                        mbar_wait(ready_bar(s), ph);         // X hi/lo written by the converter
-                        tc_fence_after();
-                        const uint32_t st = smem_base + s * STAGE_BYTES;
-                        const uint64_t a_hi = make_smem_desc(st), a_lo = make_smem_desc(st + A_BYTES);
-                        const uint64_t b_hi = make_smem_desc(st + 2 * A_BYTES), b_lo = make_smem_desc(st + 2 * A_BYTES + B_BYTES);
-#pragma unroll
-                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                            const uint64_t off = (uint64_t)((kk * UMMA_K * 4) >> 4);   // +32 B along K inside the swizzle atom
-                            umma_tf32(tmem_d, a_lo + off, b_hi + off, kIdesc, (kb | kk) != 0);
-                            umma_tf32(tmem_d, a_hi + off, b_lo + off, kIdesc, 1);
-                            umma_tf32(tmem_d, a_hi + off, b_hi + off, kIdesc, 1);
-                        }
-                        umma_commit(empty_bar(s));           // stage reusable once these MMAs retire
-                    }
-                    umma_commit(tfull_bar(a));               // accumulator complete -> epilogue
-                }
-        }
-    } else if (warp < EPI_WARP0) {
-        // ===================== converter: split X into TF32 hi / lo =====================
-        const int t = threadIdx.x - CONV_WARP0 * 32;   // 0..127
-        uint32_t it = 0;
-        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x)
-            for (int nt = 0; nt < num_n_tiles; ++nt)
-                for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-                    const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
-                    mbar_wait(full_bar(s), ph);
-                    float4 *ahi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
-                    float4 *alo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + A_BYTES);
-#pragma unroll
-                    for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
-                        const int e = t + 128 * i;          // position-preserving, so the swizzle is irrelevant here
-                        const float4 v = ahi[e];
-                        float4 h, l;
-                        h.x = tf32_rna_dev(v.x); h.y = tf32_rna_dev(v.y); h.z = tf32_rna_dev(v.z); h.w = tf32_rna_dev(v.w);
-                        l.x = tf32_rna_dev(v.x - h.x); l.y = tf32_rna_dev(v.y - h.y);
-                        l.z = tf32_rna_dev(v.z - h.z); l.w = tf32_rna_dev(v.w - h.w);
-                        ahi[e] = h; alo[e] = l;
-                    }
-                    fence_proxy_async();                     // generic-proxy writes -> visible to the tensor core
-                    mbar_arrive(ready_bar(s));
-                }
-    } else {
-        // ===================== epilogue: TMEM -> registers -> running argmin =====================
-        const int q = warp & 3;                              // TMEM lane quarter this warp may access
-        const int e = threadIdx.x - EPI_WARP0 * 32;          // 0..127
-        const int row_in_tile = q * 32 + lane;
-        uint32_t acc_it = 0;
-        for (int mt = blockIdx.x; mt < num_m_tiles; mt += gridDim.x) {
-            RunMin rm; rm.reset();
-            for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
-                const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
-                float *bs = bias_s + a * BN;
-                bs[e] = __ldg(bias + (int64_t)nt * BN + e);
-                bs[e + 128] = __ldg(bias + (int64_t)nt * BN + e + 128);
-                asm volatile("bar.sync 1, 128;" ::: "memory");   // bias tile visible to the 4 epilogue warps
-                mbar_wait(tfull_bar(a), aph);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN);
-                drain_accumulator<BN / 32>(rm, taddr, bs, nt * BN);
-                tc_fence_before();
-                mbar_arrive(tempty_bar(a));
-            }
-            float best; int bidx;
-            rm.result(best, bidx);
-            const int64_t row = (int64_t)mt * BM + row_in_tile;
-            if (row < n) {
-                if (bmu_out) bmu_out[row] = bidx;
-                if (best_out) best_out[row] = best;
-            }
-            if (acc.S != nullptr) {
-                // ---- fused K3: S[bmu[r], :] += X[r, :] for the rows of this tile -----------------
-                bmu_s[row_in_tile] = (row < n) ? bidx : -1;
-                if (row < n) atomicAdd(acc.cnt + bidx, 1);
-                asm volatile("bar.sync 2, 128;" ::: "memory");
-                const int64_t row0 = (int64_t)mt * BM;
-                const int wq = warp - EPI_WARP0;                 // this warp takes rows wq, wq+4, ...
-                if (acc.vec) {
-                    const int d4 = acc.d >> 2;
-                    // 32 lanes cover `rows_per_pass` rows x d4 float4 at a time (d4 < 32), or one row in strips
-                    if (d4 <= 32) {
-                        const int lanes_per_row = d4 <= 1 ? 1 : d4 <= 2 ? 2 : d4 <= 4 ? 4 : d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
-                        const int rows_per_pass = 32 / lanes_per_row;
-                        const int sub = lane / lanes_per_row, c4 = lane % lanes_per_row;
-                        for (int r = wq * rows_per_pass + sub; r < BM; r += 4 * rows_per_pass) {
-                            const int b = bmu_s[r];
-                            if (b >= 0 && c4 < d4) {
-                                const float4 v = __ldg(reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx) + c4);
-                                red_add_v4(acc.S + (int64_t)b * acc.d + c4 * 4, v);
-                            }
-                        }
-                    } else {
-                        for (int r = wq; r < BM; r += 4) {
-                            const int b = bmu_s[r];
-                            if (b < 0) continue;
-                            const float4 *xr = reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx);
-                            float *sr = acc.S + (int64_t)b * acc.d;
-                            for (int c4 = lane; c4 < d4; c4 += 32) red_add_v4(sr + c4 * 4, __ldg(xr + c4));
-                        }
-                    }
-                } else {
-                    for (int r = wq; r < BM; r += 4) {
-                        const int b = bmu_s[r];
-                        if (b < 0) continue;
-                        for (int cc = lane; cc < acc.d; cc += 32)
-                            atomicAdd(acc.S + (int64_t)b * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
-                    }
-                }
-                asm volatile("bar.sync 2, 128;" ::: "memory");   // bmu_s is rewritten by the next tile
-            }
-        }
-    }
-
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) { tc_fence_after(); tmem_dealloc(tmem_base, 512); }
-
-    if (acc.S != nullptr) {
-        // the last CTA to get here folds the exact integer counts into the fp32 vector c
-        if (threadIdx.x == 0) {
-            __threadfence();
-            last_cta = (atomicAdd(acc.done, 1u) == gridDim.x - 1) ? 1u : 0u;
-        }
-        __syncthreads();
-        if (last_cta) {
-            __threadfence();
-            for (int i = threadIdx.x; i < acc.k; i += blockDim.x) {
-                const int v = atomicExch(acc.cnt + i, 0);
-                if (v) atomicAdd(acc.c + i, (float)v);
-            }
-            if (threadIdx.x == 0) *acc.done = 0u;
-        }
-    }
-}
 
 // ---- host side -----------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -471,35 +220,6 @@ inline int make_map_2d(CUtensorMap *m, const void *base, uint64_t inner, uint64_
 inline bool shape_ok(const float *X, int64_t n, int d, int64_t ldx) {
     return n > 0 && d >= 1 && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
            n < ((int64_t)1 << 31) - BM;
-}
-
-inline int launch_bmu_tc(const float *X, int64_t n, int d, int64_t ldx, int k, const WsLayout &L, uint8_t *ws,
-                         int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
-    SOM_REQUIRE(shape_ok(X, n, d, ldx), SOM_E_SHAPE,
-                "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
-    CUtensorMap mx, mhi, mlo;
-    int rc;
-    if ((rc = make_map_2d(&mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)ldx * 4, BK, BM))) return rc;
-    if ((rc = make_map_2d(&mhi, ws + L.whi_off, (uint64_t)L.d_pad, (uint64_t)L.k_pad, (uint64_t)L.d_pad * 4, BK, BN))) return rc;
-    if ((rc = make_map_2d(&mlo, ws + L.wlo_off, (uint64_t)L.d_pad, (uint64_t)L.k_pad, (uint64_t)L.d_pad * 4, BK, BN))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
-        SOM_CUDA(cudaFuncSetAttribute(bmu_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
-    const int num_m_tiles = (int)ceil_div(n, BM);
-    const int num_n_tiles = L.k_pad / BN;
-    const int num_k_blocks = L.d_pad / BK;
-    const int grid = num_m_tiles < sm_count ? num_m_tiles : sm_count;
-    FusedAcc acc;
-    acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = S; acc.c = c;
-    acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
-    acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
-    acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
-    acc.dbg = 0;
-    bmu_tc_kernel<<<grid, NUM_THREADS, SMEM_BYTES, st>>>(mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off),
-                                                         n, num_m_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
-    return check_cuda(cudaGetLastError(), "bmu_tc_kernel launch");
 }
 
 }  // namespace tc

@@ -79,42 +79,6 @@ __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
 
 // running argmin on the scaled scores: sc = acc * 2^-b_k + bias_k * 2^a_r
 struct RunMinScaled : tc::RunMin {
-    // 16 accumulator columns, uniform codebook scale: sc = acc + bias_k * rsg
-    __device__ __forceinline__ void chunk16_uniform(const uint32_t (&acc)[16], const float *bias16, float rsg, int colbase) {
-        const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
-        float4 bq[4];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) bq[j4] = b4[j4];
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-            const float bb[4] = {bq[j4].x, bq[j4].y, bq[j4].z, bq[j4].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = j4 * 4 + e;
-                const float sc = fmaf(bb[e], rsg, __uint_as_float(acc[j]));
-                const int a = j % tc::EPI_ACC;
-                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
-            }
-        }
-    }
-    // 16 accumulator columns, per-neuron scale: sc = acc * winv_k + bias_k * rs
-    __device__ __forceinline__ void chunk16_scaled(const uint32_t (&acc)[16], const float *bias16, const float *winv16,
-                                                   float rs, int colbase) {
-        const float4 *b4 = reinterpret_cast<const float4 *>(bias16);
-        const float4 *s4 = reinterpret_cast<const float4 *>(winv16);
-#pragma unroll
-        for (int j4 = 0; j4 < 4; ++j4) {
-            const float4 b = b4[j4], s = s4[j4];
-            const float bb[4] = {b.x, b.y, b.z, b.w}, ss[4] = {s.x, s.y, s.z, s.w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int j = j4 * 4 + e;
-                const float sc = fmaf(__uint_as_float(acc[j]), ss[e], bb[e] * rs);
-                const int a = j % tc::EPI_ACC;
-                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
-            }
-        }
-    }
     // uniform codebook scale: sc = acc + bias_k * rsg  (one FFMA per score, one shared-memory operand)
     __device__ __forceinline__ void chunk_uniform(const uint32_t (&acc)[32], const float *bias32, float rsg, int colbase) {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias32);

@@ -52,19 +52,11 @@ static int device_info(DevInfo &out) {
     return 0;
 }
 
-// The CTA-pair kernel (bmu_tc2) is the product path; SOM_B200_TC_V1=1 selects the one-CTA kernel (A/B runs).
-static bool use_tc_v1() {
-    static int v = -1;
-    if (v < 0) { const char *e = getenv("SOM_B200_TC_V1"); v = (e && e[0] == '1') ? 1 : 0; }
-    return v == 1;
-}
-
 static int launch_tc(int use, const float *X, int64_t n, int d, int64_t ldx, const float *xscale, int k,
                      const WsLayout &L, uint8_t *ws, int32_t *bmu, float *best, float *S, float *c, int sm_count,
                      cudaStream_t st) {
     if (use == SOM_ALGO_TC_3XF16)
         return tc3::launch_bmu_tc3(X, n, d, ldx, xscale, k, L, ws, bmu, best, S, c, sm_count, st);
-    if (use_tc_v1()) return tc::launch_bmu_tc(X, n, d, ldx, k, L, ws, bmu, best, S, c, sm_count, st);
     return tc2::launch_bmu_tc2(X, n, d, ldx, k, L, ws, bmu, best, S, c, sm_count, st);
 }
 
