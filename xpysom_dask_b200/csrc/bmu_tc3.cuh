@@ -118,6 +118,39 @@ struct RunMinScaled : tc::RunMin {
     }
 };
 
+// One A item: raw fp32 chunk (two SWIZZLE_128B boxes of [128 rows x 32 floats]) -> scaled fp16 hi | lo tiles,
+// in place, by NCONV cooperating threads (bar.sync 2 separates the read of the whole slot from its overwrite).
+template <int NCONV>
+__device__ __forceinline__ void convert_item(uint8_t *slot, int t, int64_t row0, int64_t n, const float *__restrict__ xscale) {
+    constexpr int PER = 2048 / NCONV;          // float4 per thread
+    const float4 *raw = reinterpret_cast<const float4 *>(slot);
+    float4 v[PER];
+#pragma unroll
+    for (int i = 0; i < PER; ++i) v[i] = raw[t + NCONV * i];               // linear: conflict-free
+    asm volatile("bar.sync 2, %0;" :: "n"(NCONV) : "memory");                // everyone has read the slot
+#pragma unroll
+    for (int i = 0; i < PER; ++i) {
+        const int e = t + NCONV * i;
+        const int box = e >> 10, r = (e & 1023) >> 3, cpos = e & 7;
+        const int j = cpos ^ (r & 7);                 // logical 16-byte chunk within the 32 floats
+        const int k0 = box * 32 + j * 4;              // first of 4 consecutive features
+        const int64_t grow = row0 + r;
+        const float rs = grow < n ? __ldg(xscale + grow) : 1.f;
+        const float x0 = v[i].x * rs, x1 = v[i].y * rs, x2 = v[i].z * rs, x3 = v[i].w * rs;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y);
+        const __half2 l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        // fp16 tile [128 rows x 64 halves], SWIZZLE_128B: 16-byte chunk (k0 / 8) ^ (r % 8)
+        const int off = r * 128 + (((k0 >> 3) ^ (r & 7)) << 4) + ((k0 & 7) << 1);
+        uint2 hv, lv;
+        hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
+        lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
+        *reinterpret_cast<uint2 *>(slot + off) = hv;
+        *reinterpret_cast<uint2 *>(slot + HALF_SLOT + off) = lv;
+    }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
@@ -155,13 +188,19 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const bool fused = acc.S != nullptr;
     const bool resident = num_k_blocks <= RESIDENT_MAX_KB;   // A tiles live across the neuron tiles
     const bool uniform = gstat[2] != 0u;                     // one power-of-two scale for the whole codebook
+    // Streaming mode (large D) converts one X chunk per MMA block, which 4 warps cannot sustain, while the
+    // epilogue has a whole row of k blocks per tile to drain one accumulator: epilogue warps 12-15 join the
+    // converter and warps 8-11 drain all 256 columns.
+    const bool conv_extra = !resident;
+    const int nconv = conv_extra ? 256 : 128;                // converter threads per CTA
+    const int nepi = conv_extra ? 128 : 256;                 // epilogue threads per CTA
     const int probe = (acc.dbg == 9 && blockIdx.x == 0) ? 1 : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 256); tc::mbar_init(aempty_bar(s), 1); }
+        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 2 * nconv); tc::mbar_init(aempty_bar(s), 1); }
         for (int s = 0; s < NB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS);
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * nepi);
             tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
         }
         tc::fence_barrier_init();
@@ -243,9 +282,10 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     tc::dbg_stamp(probe, 3, acc_it);                 // MMA: all MMAs of the tile issued + committed
                 }
         }
-    } else if (warp >= CONV_WARP0 && warp < EPI_WARP0) {
+    } else if ((warp >= CONV_WARP0 && warp < EPI_WARP0) || (conv_extra && warp >= EPI_WARP0 + 4 && warp < SCAT_WARP0)) {
         // ===================== converter: raw fp32 -> scaled fp16 hi | lo, in place ==============================
-        const int t = threadIdx.x - CONV_WARP0 * 32;   // 0..127
+        const int t = warp < EPI_WARP0 ? (int)threadIdx.x - CONV_WARP0 * 32
+                                       : 128 + (int)threadIdx.x - (EPI_WARP0 + 4) * 32;     // 0..nconv-1
         uint32_t ia = 0;
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs) {
             const int reps = resident ? 1 : num_n_tiles;
@@ -255,44 +295,24 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int s = ia % NA; const uint32_t ph = (ia / NA) & 1;
                     tc::mbar_wait(afull_bar(s), ph);
                     uint8_t *slot = smem + s * SLOT_BYTES;
-                    const float4 *raw = reinterpret_cast<const float4 *>(slot);
-                    float4 v[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) v[i] = raw[t + 128 * i];     // linear: conflict-free
-                    asm volatile("bar.sync 2, 128;" ::: "memory");              // everyone has read the slot
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        // raw layout: two SWIZZLE_128B boxes of [128 rows x 32 floats]; float4 index e
-                        const int e = t + 128 * i;
-                        const int box = e >> 10, r = (e & 1023) >> 3, cpos = e & 7;
-                        const int j = cpos ^ (r & 7);                 // logical 16-byte chunk within the 32 floats
-                        const int k0 = box * 32 + j * 4;              // first of 4 consecutive features
-                        const int64_t grow = row0 + r;
-                        const float rs = grow < n ? __ldg(xscale + grow) : 1.f;
-                        const float x0 = v[i].x * rs, x1 = v[i].y * rs, x2 = v[i].z * rs, x3 = v[i].w * rs;
-                        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
-                        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
-                        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y);
-                        const __half2 l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
-                        // fp16 tile [128 rows x 64 halves], SWIZZLE_128B: 16-byte chunk (k0 / 8) ^ (r % 8)
-                        const int off = r * 128 + (((k0 >> 3) ^ (r & 7)) << 4) + ((k0 & 7) << 1);
-                        uint2 hv, lv;
-                        hv.x = *reinterpret_cast<const uint32_t *>(&h01); hv.y = *reinterpret_cast<const uint32_t *>(&h23);
-                        lv.x = *reinterpret_cast<const uint32_t *>(&l01); lv.y = *reinterpret_cast<const uint32_t *>(&l23);
-                        *reinterpret_cast<uint2 *>(slot + off) = hv;
-                        *reinterpret_cast<uint2 *>(slot + HALF_SLOT + off) = lv;
-                    }
+                    if (conv_extra) convert_item<256>(slot, t, row0, n, xscale);
+                    else            convert_item<128>(slot, t, row0, n, xscale);
                     tc::fence_proxy_async();
                     mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
                 }
         }
-    } else if (warp >= EPI_WARP0 && warp < SCAT_WARP0) {
+    } else if (warp >= EPI_WARP0 && warp < (conv_extra ? EPI_WARP0 + 4 : SCAT_WARP0)) {
         // ===================== epilogue: TMEM -> registers -> running argmin ====================================
+        // resident mode: 8 warps, two per TMEM lane quarter, 128 columns each (h = column half);
+        // streaming mode: 4 warps (8-11), all 256 columns each
         const int q = warp & 3;
-        const int h = (warp - EPI_WARP0) >> 2;
+        const int h = conv_extra ? 0 : (warp - EPI_WARP0) >> 2;
+        const int ncols = conv_extra ? BN : BN / 2;
         const int row_in_tile = q * 32 + lane;
         const float winv0 = __ldg(wsinv);                    // 2^-b of the uniform codebook scale
-        float *wb = epi_stage + (warp - EPI_WARP0) * 256;    // this warp's private bias | inverse-scale slice
+        // this warp's private shared-memory slice: ncols bias values, then ncols inverse scales
+        float *wb = epi_stage + (warp - EPI_WARP0) * (conv_extra ? 512 : 256);
+        float *wsv = wb + ncols;
         uint32_t acc_it = 0, tile_it = 0;
         // row scale of the FIRST tile; later ones are fetched one tile ahead (no exposed global latency)
         float rs_next = 1.f;
@@ -302,6 +322,11 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         }
         float4 nb = __ldg(reinterpret_cast<const float4 *>(bias + h * (BN / 2)) + lane);
         float4 ns = __ldg(reinterpret_cast<const float4 *>(wsinv + h * (BN / 2)) + lane);
+        float4 nb2 = nb, ns2 = ns;                               // columns 128..255 (streaming mode only)
+        if (conv_extra) {
+            nb2 = __ldg(reinterpret_cast<const float4 *>(bias + 128) + lane);
+            ns2 = __ldg(reinterpret_cast<const float4 *>(wsinv + 128) + lane);
+        }
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
             const int64_t row = (int64_t)pt * (2 * BM) + (int64_t)rank * BM + row_in_tile;
             const float rs = rs_next;
@@ -317,12 +342,20 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const int col0 = nt * BN + h * (BN / 2);
                 __syncwarp();
                 reinterpret_cast<float4 *>(wb)[lane] = nb;
-                reinterpret_cast<float4 *>(wb + 128)[lane] = ns;
+                reinterpret_cast<float4 *>(wsv)[lane] = ns;
+                if (conv_extra) {
+                    reinterpret_cast<float4 *>(wb + 128)[lane] = nb2;
+                    reinterpret_cast<float4 *>(wsv + 128)[lane] = ns2;
+                }
                 __syncwarp();
                 {   // prefetch the next neuron tile's slice (wraps to tile 0 for the next row tile)
                     const int nn = (nt + 1 < num_n_tiles ? nt + 1 : 0) * BN + h * (BN / 2);
                     nb = __ldg(reinterpret_cast<const float4 *>(bias + nn) + lane);
                     ns = __ldg(reinterpret_cast<const float4 *>(wsinv + nn) + lane);
+                    if (conv_extra) {
+                        nb2 = __ldg(reinterpret_cast<const float4 *>(bias + nn + 128) + lane);
+                        ns2 = __ldg(reinterpret_cast<const float4 *>(wsinv + nn + 128) + lane);
+                    }
                 }
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 4, acc_it);   // EPI: starts waiting for the tile
                 tc::mbar_wait(tfull_bar(a), aph);
@@ -330,12 +363,12 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 5, acc_it);   // EPI: tile complete in TMEM
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
 #pragma unroll 1
-                for (int c = 0; c < BN / 2 / 32; ++c) {
+                for (int c = 0; c < ncols / 32; ++c) {
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait_dep(v);
                     if (uniform) rm.chunk_uniform(v, wb + c * 32, rsg, col0 + c * 32);
-                    else         rm.chunk(v, wb + c * 32, wb + 128 + c * 32, rs, col0 + c * 32);
+                    else         rm.chunk(v, wb + c * 32, wsv + c * 32, rs, col0 + c * 32);
                 }
                 tc::tc_fence_before();
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 6, acc_it);   // EPI: this warp drained its half
@@ -344,10 +377,12 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             float best; int bidx;
             rm.result(best, bidx);
             const int mb = (tile_it & 1) * BM;
-            if (h == 1) { mrg_v[mb + row_in_tile] = best; mrg_i[mb + row_in_tile] = bidx; }
-            asm volatile("bar.sync 1, 256;" ::: "memory");
+            if (!conv_extra) {       // two warps per row: merge the column halves through shared memory
+                if (h == 1) { mrg_v[mb + row_in_tile] = best; mrg_i[mb + row_in_tile] = bidx; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");
+            }
             if (h == 0) {
-                argmin_merge(best, bidx, mrg_v[mb + row_in_tile], mrg_i[mb + row_in_tile]);
+                if (!conv_extra) argmin_merge(best, bidx, mrg_v[mb + row_in_tile], mrg_i[mb + row_in_tile]);
                 if (row < n) {
                     if (bmu_out) bmu_out[row] = bidx;
                     if (best_out) best_out[row] = uniform ? best / rsg : best / rs;   // undo the scaling (exact)
