@@ -151,6 +151,9 @@ __device__ __forceinline__ void convert_item(uint8_t *slot, int t, int64_t row0,
     }
 }
 
+// STREAM = false: D <= 128, X tiles resident across neuron tiles, 4 converter + 8 epilogue warps.
+// STREAM = true : larger D, X tiles stream once per neuron tile, 8 converter + 4 epilogue warps.
+template <bool STREAM>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
@@ -186,14 +189,14 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const bool fused = acc.S != nullptr;
-    const bool resident = num_k_blocks <= RESIDENT_MAX_KB;   // A tiles live across the neuron tiles
+    constexpr bool resident = !STREAM;                       // A tiles live across the neuron tiles
     const bool uniform = gstat[2] != 0u;                     // one power-of-two scale for the whole codebook
     // Streaming mode (large D) converts one X chunk per MMA block, which 4 warps cannot sustain, while the
     // epilogue has a whole row of k blocks per tile to drain one accumulator: epilogue warps 12-15 join the
     // converter and warps 8-11 drain all 256 columns.
-    const bool conv_extra = !resident;
-    const int nconv = conv_extra ? 256 : 128;                // converter threads per CTA
-    const int nepi = conv_extra ? 128 : 256;                 // epilogue threads per CTA
+    constexpr bool conv_extra = STREAM;
+    constexpr int nconv = conv_extra ? 256 : 128;            // converter threads per CTA
+    constexpr int nepi = conv_extra ? 128 : 256;             // epilogue threads per CTA
     const int probe = (acc.dbg == 9 && blockIdx.x == 0) ? 1 : 0;
 
     if (threadIdx.x == 0) {
@@ -307,7 +310,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // streaming mode: 4 warps (8-11), all 256 columns each
         const int q = warp & 3;
         const int h = conv_extra ? 0 : (warp - EPI_WARP0) >> 2;
-        const int ncols = conv_extra ? BN : BN / 2;
+        constexpr int ncols = conv_extra ? BN : BN / 2;
         const int row_in_tile = q * 32 + lane;
         const float winv0 = __ldg(wsinv);                    // 2^-b of the uniform codebook scale
         // this warp's private shared-memory slice: ncols bias values, then ncols inverse scales
@@ -491,7 +494,8 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     if ((rc = make_map_2d_f16(&mlo, ws + L.w16lo_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, BNH))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     const int num_pair_tiles = (int)ceil_div(n, 2 * BM);
@@ -506,9 +510,15 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
     { const char *e = getenv("SOM_B200_DBG"); acc.dbg = e ? atoi(e) : 0; }
-    bmu_tc3_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
+    if (num_k_blocks <= RESIDENT_MAX_KB) {
+        bmu_tc3_kernel<false><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
         mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off), reinterpret_cast<const float *>(ws + L.wsinv_off),
         reinterpret_cast<const unsigned int *>(ws + L.gstat_off), xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+    } else {
+        bmu_tc3_kernel<true><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
+        mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off), reinterpret_cast<const float *>(ws + L.wsinv_off),
+        reinterpret_cast<const unsigned int *>(ws + L.gstat_off), xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+    }
     return check_cuda(cudaGetLastError(), "bmu_tc3_kernel launch");
 }
 
