@@ -322,26 +322,25 @@ def test_api_known_answers_from_reference_tests():
 
 def test_cuda_graph_replay_matches_eager_launches():
     """use_cuda_graph=True replays one captured graph per epoch with sigma / eta read from a device-side
-    schedule; it must land where the kernel-by-kernel path lands.  Small-integer samples make the per-BMU
-    sums exact in fp32 whatever the order of the atomics, so the two runs do not drift apart chaotically
-    the way free-running runs on real-valued data do."""
+    schedule; it must land where the kernel-by-kernel path lands.  The comparison is made fully
+    deterministic: small-integer samples make the per-BMU sums exact in fp32 whatever the order of the
+    atomics, and a 64-neuron map keeps the neighbourhood apply in one un-sliced CTA row (no atomics), so
+    the two runs cannot drift apart chaotically the way free-running runs do."""
     from xpysom_dask_b200 import XPySom
     rng = np.random.RandomState(21)
     centres = rng.randint(0, 8, size=(24, 32))
     data = (centres[rng.randint(24, size=8000)] + rng.randint(0, 2, size=(8000, 32))).astype(np.float32)
     for kw in (dict(), dict(topology="hexagonal", neighborhood_function="mexican_hat", decay_function="linear")):
-        a = XPySom(12, 11, 32, sigma=2.0, random_seed=4, use_cuda_graph=False, **kw)
-        b = XPySom(12, 11, 32, sigma=2.0, random_seed=4, use_cuda_graph=True, **kw)
+        a = XPySom(8, 8, 32, sigma=2.0, random_seed=4, use_cuda_graph=False, **kw)
+        b = XPySom(8, 8, 32, sigma=2.0, random_seed=4, use_cuda_graph=True, **kw)
         a.train(data, 6)
         b.train(data, 6)
-        assert b.quantization_error(data) == pytest.approx(a.quantization_error(data), rel=1e-3)
-        assert U.codebook_rel_err(b._weights, a._weights) < 1e-3
+        assert U.codebook_rel_err(b._weights, a._weights) < 1e-6
         # schedule bookkeeping: resuming mid-schedule through the graph path
-        a2 = XPySom(12, 11, 32, sigma=2.0, random_seed=4, use_cuda_graph=True, **kw)
+        a2 = XPySom(8, 8, 32, sigma=2.0, random_seed=4, use_cuda_graph=True, **kw)
         a2.train(data, 6, iter_beg=0, iter_end=3)
         a2.train(data, 6, iter_beg=3, iter_end=6)
-        assert a2.quantization_error(data) == pytest.approx(a.quantization_error(data), rel=1e-3)
-        assert U.codebook_rel_err(a2._weights, a._weights) < 1e-3
+        assert U.codebook_rel_err(a2._weights, a._weights) < 1e-6
 
 
 def test_train_host_c_abi_matches_class():
