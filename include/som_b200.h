@@ -106,6 +106,14 @@ int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float 
                  int32_t *bmu_dev, float *best_dev,
                  void *ws_dev, size_t ws_bytes, void *stream);
 
+/* Full distance matrix out_dev (n, K), for the callers that want it (activate xpysom.py:323-354,
+ * distance_from_weights :647-671, topographic_error :709-746).  mode 0: the activation distance as the
+ * reference defines it (euclidean = partial -2x.w+|w|^2, cosine = 1 - nan_to_num(sim), L1 / Linf / Lp sums);
+ * mode 1: the Euclidean distance sqrt(|x-w|^2) with nan_to_num (distances.py:33-43) whatever dist_kind. */
+int som_b200_distances(const float *x_dev, int64_t n, int d, int64_t ldx,
+                       const float *w_dev, int k, int dist_kind, float p, int mode,
+                       float *out_dev, void *ws_dev, size_t ws_bytes, void *stream);
+
 /* U (first half): S[bmu[r], :] += X[r, :], c[bmu[r]] += 1 for the n rows.
  * Replaces the sample side of g^T X and sum(g) in XPySom._update
  * (xpysom.py:434-441).  S and c are accumulated into (zero them per epoch). */

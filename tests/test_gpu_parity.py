@@ -343,6 +343,42 @@ def test_cuda_graph_replay_matches_eager_launches():
         assert U.codebook_rel_err(a2._weights, a._weights) < 1e-6
 
 
+def test_activate_distance_from_weights_topographic_error():
+    """tests.py:66-90 of the reference and its own outputs on seeded maps (golden api.npz)."""
+    from xpysom_dask_b200 import XPySom
+    g = U.load("api.npz")
+    som = XPySom(5, 5, 1, std_coeff=1)
+    som._weights = g["fake_w"].copy()
+    act = som.activate(np.array([5.0]))
+    assert act.argmin() == 13                                                   # tests.py:66-67
+    np.testing.assert_allclose(act.ravel(), np.asarray(g["activate_5"]).ravel(), rtol=1e-6)
+    d = g["dfw_data"]
+    dist = som.distance_from_weights(d, None)
+    w = som._weights.reshape(-1, 1)
+    for i in range(len(d)):
+        for j in range(len(w)):
+            assert dist[i][j] == np.linalg.norm(d[i] - w[j])                    # exact, tests.py:69-75
+    som._weights = g["topo_w"].copy()
+    assert som.topographic_error([[5]]) == 0.0                                  # tests.py:89
+    assert som.topographic_error([[15]]) == 1.0                                 # tests.py:90
+    s1 = XPySom(5, 5, 2, sigma=1.0, learning_rate=0.5, random_seed=1)
+    s1._weights = g["seed1_w_trained"].copy()
+    assert s1.topographic_error(g["seed1_data"]) == pytest.approx(float(g["seed1_topo"]), abs=0.011)
+    hq = XPySom(6, 6, 3, topology="hexagonal", random_seed=4)
+    np.testing.assert_array_equal(hq._weights, g["hexsq_w"])
+    assert hq.topographic_error(g["hex_data"]) == pytest.approx(float(g["hexsq_topo"]), abs=0.021)
+    with pytest.raises(IndexError):                      # the reference's (i, j) indexing of (gy, gx) grids
+        XPySom(6, 5, 3, topology="hexagonal", random_seed=3).topographic_error(g["hex_data"])
+    # every activation distance against the oracle's matrix
+    x = U.blobs(300, 20, seed=2)
+    for dist_name, p in (("euclidean", 2), ("cosine", 2), ("manhattan", 1), ("chebyshev", 0), ("norm_p", 3)):
+        sm = XPySom(7, 6, 20, activation_distance=dist_name, activation_distance_kwargs={"p": p}, random_seed=3)
+        ref_name = "norm_p_no_opt" if dist_name == "norm_p" else dist_name
+        want = so.activation_distance(ref_name, x, np.asarray(sm._weights, np.float32).reshape(42, 20), None, p)
+        got = sm.activate(x)
+        assert np.abs(got - want).max() / np.abs(want).max() < 2e-6, dist_name
+
+
 def test_train_host_c_abi_matches_class():
     """The whole-job C entry with HOST buffers (what the reference would bind) == the Python class.
     Teacher-forced, one epoch per call from the same W_t: free-running epochs amplify any BMU flip

@@ -165,6 +165,102 @@ bmu_simt_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx,
     }
 }
 
+// Distance MATRIX (n, K), for the callers that really want it (activate, distance_from_weights,
+// topographic_error: xpysom.py:323-354, 647-671, 709-746).  Same tiling as the BMU kernel; `mode` selects the
+// value written:  0 = the activation distance as the reference defines it (euclidean: partial
+// -2 x.w + |w|^2, distances.py:23; cosine: 1 - nan_to_num(x.w / sqrt(|x|^2 |w|^2)), distances.py:55-59;
+// manhattan / chebyshev / norm_p sums), 1 = Euclidean distance sqrt(max(0, |x|^2 - 2 x.w + |w|^2)) with
+// nan_to_num (distances.py:33-43), whatever DIST.
+template <int DIST>
+__global__ void __launch_bounds__(ST_THREADS, 2)
+dist_matrix_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, const float *__restrict__ W, int k,
+                   const float *__restrict__ wsq, float p, int mode, float *__restrict__ out) {
+    __shared__ __align__(16) float Xs[ST_DK][ST_LD];
+    __shared__ __align__(16) float Ws[ST_DK][ST_LD];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int lrow = tid >> 1, lcol = (tid & 1) * 8;
+    const int64_t row0 = (int64_t)blockIdx.x * ST_TM;
+    const int n0 = blockIdx.y * ST_TN;
+    float acc[8][8], xs[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) { xs[i] = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = 0.f; }
+    for (int d0 = 0; d0 < d; d0 += ST_DK) {
+        float xv[8], wv[8];
+        const int64_t gr = row0 + lrow;
+        const int gn = n0 + lrow, gc = d0 + lcol;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            xv[e] = (gr < n && gc + e < d) ? __ldg(X + gr * ldx + gc + e) : 0.f;
+            wv[e] = (gn < k && gc + e < d) ? __ldg(W + (int64_t)gn * d + gc + e) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { Xs[lcol + e][lrow] = xv[e]; Ws[lcol + e][lrow] = wv[e]; }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < ST_DK; ++kk) {
+            float a[8], b[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = Xs[kk][ty * 8 + i];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) b[j] = Ws[kk][j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4)];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                xs[i] = fmaf(a[i], a[i], xs[i]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (mode == 1) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    else simt_accum<DIST>(acc[i][j], a[i], b[j], p);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+        if (col >= k) continue;
+        const float ws = __ldg(wsq + col);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int64_t gr = row0 + ty * 8 + i;
+            if (gr >= n) continue;
+            float v;
+            if (mode == 1) {
+                v = sqrtf((fmaf(-2.f, acc[i][j], ws)) + xs[i]);             // (-2 x.w + |w|^2) + |x|^2, then sqrt
+                if (isnan(v)) v = 0.f;                                       // negative round-off -> NaN -> 0
+            } else if (DIST == SOM_DIST_EUCLIDEAN) {
+                v = fmaf(-2.f, acc[i][j], ws);
+            } else if (DIST == SOM_DIST_COSINE) {
+                float q = acc[i][j] / sqrtf(xs[i] * ws);
+                if (isnan(q)) q = 0.f;
+                else if (isinf(q)) q = q > 0.f ? 3.4028234664e38f : -3.4028234664e38f;
+                v = 1.f - q;
+            } else {
+                v = acc[i][j];
+            }
+            out[gr * (int64_t)k + col] = v;
+        }
+    }
+}
+
+inline int launch_dist_matrix(const float *X, int64_t n, int d, int64_t ldx, const float *W, int k, int dist_kind,
+                              float p, int mode, const float *wsq, float *out, cudaStream_t st) {
+    dim3 grid((unsigned)ceil_div(n, ST_TM), (unsigned)ceil_div(k, ST_TN));
+#define SOM_LAUNCH_DM(DK) dist_matrix_kernel<DK><<<grid, ST_THREADS, 0, st>>>(X, n, d, ldx, W, k, wsq, p, mode, out)
+    switch (dist_kind) {
+        case SOM_DIST_EUCLIDEAN: SOM_LAUNCH_DM(SOM_DIST_EUCLIDEAN); break;
+        case SOM_DIST_COSINE:    SOM_LAUNCH_DM(SOM_DIST_COSINE); break;
+        case SOM_DIST_MANHATTAN: SOM_LAUNCH_DM(SOM_DIST_MANHATTAN); break;
+        case SOM_DIST_CHEBYSHEV: SOM_LAUNCH_DM(SOM_DIST_CHEBYSHEV); break;
+        case SOM_DIST_NORM_P:    SOM_LAUNCH_DM(SOM_DIST_NORM_P); break;
+        default: set_error("unknown distance kind %d", dist_kind); return SOM_E_BADARG;
+    }
+#undef SOM_LAUNCH_DM
+    return check_cuda(cudaGetLastError(), "dist_matrix_kernel launch");
+}
+
 inline int launch_bmu_simt(const float *X, int64_t n, int d, int64_t ldx, const float *W, int k,
                            int dist_kind, float p, const float *aux, int32_t *bmu, float *best,
                            int sm_count, cudaStream_t st) {

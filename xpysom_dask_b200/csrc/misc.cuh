@@ -96,6 +96,16 @@ __global__ void codebook_split_kernel(const float *__restrict__ W, int k, int d,
     }
 }
 
+// |w_k|^2 per neuron (fp64 accumulation, rounded once), one warp per row
+__global__ void row_sq_kernel(const float *__restrict__ W, int k, int d, float *__restrict__ out) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= k) return;
+    double s = 0.0;
+    for (int c = lane; c < d; c += 32) { const double v = W[(int64_t)warp * d + c]; s += v * v; }
+    s = warp_sum(s);
+    if (lane == 0) out[warp] = (float)s;
+}
+
 // per-row power-of-two scale of the samples for the fp16-split kernel: xscale[r] = 2^a_r with
 // max_c |x[r,c]| * 2^a_r in [2^14, 2^15).  One warp per row; one HBM pass, done once per upload.
 __global__ void row_scale_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, float *__restrict__ xscale) {

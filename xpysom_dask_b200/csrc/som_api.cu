@@ -174,6 +174,24 @@ int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float 
                            bmu_dev, best_dev, di.sm, (cudaStream_t)stream);
 }
 
+int som_b200_distances(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int dist_kind,
+                       float p, int mode, float *out_dev, void *ws_dev, size_t ws_bytes, void *stream) {
+    SOM_REQUIRE(w_dev && ws_dev && out_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "distances: bad argument");
+    SOM_REQUIRE(known_dist(dist_kind) && (mode == 0 || mode == 1), SOM_E_BADARG, "distances: unknown kind / mode");
+    if (n == 0) return 0;
+    SOM_REQUIRE(x_dev, SOM_E_BADARG, "distances: x is NULL");
+    const WsLayout L = ws_layout(k, d);
+    SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "distances: workspace %zu < %zu bytes", ws_bytes, L.total);
+    // |w|^2 per neuron: aux holds it for every kind except cosine (1/|w|); bias holds it only for euclidean.
+    // Recompute into the amax slot, which no BMU kernel reads.
+    uint8_t *ws = static_cast<uint8_t *>(ws_dev);
+    float *wsq = reinterpret_cast<float *>(ws + L.amax_off);
+    row_sq_kernel<<<(unsigned)ceil_div(k, 8), 256, 0, (cudaStream_t)stream>>>(w_dev, k, d, wsq);
+    int rc = check_cuda(cudaGetLastError(), "row_sq_kernel launch");
+    if (rc) return rc;
+    return launch_dist_matrix(x_dev, n, d, ldx, w_dev, k, dist_kind, p, mode, wsq, out_dev, (cudaStream_t)stream);
+}
+
 int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const int32_t *bmu_dev, int k,
                         float *s_dev, float *c_dev, void *stream) {
     SOM_REQUIRE(s_dev && c_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "accumulate: bad argument");

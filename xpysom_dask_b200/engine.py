@@ -92,6 +92,18 @@ class CudaEngine:
         self.launches += 1
         return bmu_out
 
+    def distances(self, x, w, dist_kind, p, mode, ws):
+        """(n, K) distance matrix: mode 0 = activation distance, 1 = Euclidean distance (sqrt)."""
+        n, d = x.shape
+        k = w.shape[0]
+        out = self.empty(n, k)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_distances(self._p(x), n, d, x.stride(0), self._p(w), k, dist_kind, float(p),
+                                                   int(mode), self._p(out), self._p(ws), ws.numel(), self._stream()),
+                       "som_b200_distances")
+        self.launches += 2
+        return out
+
     def accumulate(self, x, bmu, k, s, c):
         n, d = x.shape
         with torch.cuda.device(self.device):

@@ -312,6 +312,48 @@ class XPySom:
         bmu = eng.bmu(x, w, dist_kind, p, _lib.ALGO[self._algo], ws, xscale=xscale)
         return bmu, x, w, eng
 
+    def _distance_matrix(self, data, mode):
+        eng = self._get_engine()
+        gx, gy, d = self._shape()
+        dist_kind, p = self._dist_kind()
+        w = self._weights_to_device(eng)
+        x = self._data_to_device(eng, data)
+        ws = eng.workspace(0, gx * gy, d)
+        return eng.distances(x, w, dist_kind, p, mode, ws)
+
+    def activate(self, x):
+        """Activation map of x: the (n, K) matrix of activation distances (xpysom.py:323-354)."""
+        return self._distance_matrix(x, 0).cpu().numpy()
+
+    def distance_from_weights(self, data, weights_gpu=None):
+        """d[i, j] = Euclidean distance between data[i] and the j-th weight (xpysom.py:647-671; the second
+        argument is ignored there as well)."""
+        return self._distance_matrix(data, 1).cpu().numpy()
+
+    def topographic_error(self, data):
+        """Share of samples whose best and second-best matching units are not adjacent (xpysom.py:709-746);
+        Euclidean distances whatever the activation distance, like the reference."""
+        self._check_input_len(data)
+        if np.prod(self._weights.shape) == 1:
+            warn('The topographic error is not defined for a 1-by-1 map.')
+            return np.nan
+        gx, gy, _ = self._shape()
+        n = len(data)
+        b2 = []
+        step = max(1, (1 << 26) // (gx * gy))           # bound the (rows, K) matrix to 256 MB
+        t = _as_f32_matrix(data)
+        for s0 in range(0, n, step):
+            dmat = self._distance_matrix(t[s0:s0 + step], 1)
+            b2.append(torch.topk(dmat, 2, dim=1, largest=False, sorted=True).indices.cpu().numpy())
+        b2 = np.concatenate(b2)
+        bx, by = np.unravel_index(b2, (gx, gy))
+        if self.topology == 'rectangular':
+            return ((np.abs(np.diff(bx)) > 1) | (np.abs(np.diff(by)) > 1)).mean().item()
+        # the reference indexes its (gy, gx) meshgrids with (i, j) here (xpysom.py:742-743); kept as is
+        ex, ey = self._xx[bx, by], self._yy[bx, by]
+        dxdy = np.hstack([np.diff(ex), np.diff(ey)])
+        return (np.linalg.norm(dxdy, axis=1) > 1.5).mean().item()
+
     def winner(self, x):
         """Coordinates of the winning neuron(s) (xpysom.py:370-408): a tuple for a
         1-D sample, a list of tuples for a 2-D batch."""
