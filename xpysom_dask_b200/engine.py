@@ -69,10 +69,10 @@ class CudaEngine:
                                                           ws.numel(), self._stream()), "som_b200_prepare_codebook")
         self.launches += 1
 
-    def prepare_samples(self, x):
+    def prepare_samples(self, x, out=None):
         """Per-row power-of-two scales for the fp16-split kernel (one pass over x)."""
         n, d = x.shape
-        xs = self.empty(max(n, 1))
+        xs = out if out is not None else self.empty(max(n, 1))
         with torch.cuda.device(self.device):
             _lib.check(self.lib.som_b200_prepare_samples(self._p(x), n, d, x.stride(0), self._p(xs), self._stream()),
                        "som_b200_prepare_samples")

@@ -182,6 +182,29 @@ class XPySom:
         view.copy_(t, non_blocking=True)
         return view
 
+    def _upload_in_chunks(self, eng, host):
+        """Host matrix -> device matrix (16-byte aligned rows) in up to 16 chunks on a side stream.
+        Returns the device view and [(row_begin, row_end, event recorded when the chunk has landed)]."""
+        n, d = host.shape
+        ld = (d + 3) // 4 * 4
+        buf = torch.empty((n, ld), dtype=torch.float32, device=eng.device)
+        x = buf[:, :d]
+        nchunks = int(min(16, max(2, host.numel() * 4 // (16 << 20))))
+        rows = -(-n // nchunks)
+        rows = (rows + 255) // 256 * 256           # whole 256-row tiles per chunk
+        copy_stream = torch.cuda.Stream(device=eng.device)
+        copy_stream.wait_stream(torch.cuda.current_stream(eng.device))
+        buf.record_stream(copy_stream)
+        chunks = []
+        with torch.cuda.stream(copy_stream):
+            for r0 in range(0, n, rows):
+                r1 = min(n, r0 + rows)
+                x[r0:r1].copy_(host[r0:r1], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(copy_stream)
+                chunks.append((r0, r1, ev))
+        return x, chunks
+
     def _check_input_len(self, data):
         """xpysom.py:361-367"""
         data_len = len(data[0])
@@ -209,7 +232,19 @@ class XPySom:
         group = self._group()
 
         w = self._weights_to_device(eng)
-        x = self._data_to_device(eng, data)
+        n_ep = iter_end - iter_beg
+        prof = self._profile_events if getattr(self, '_profile', False) else None
+        graphed = (self._use_cuda_graph and prof is None and not verbose and n_ep >= 3
+                   and getattr(eng, 'name', '') == 'cuda')
+        # Large host-resident samples are uploaded in chunks on a copy stream and the FIRST epoch consumes
+        # each chunk as it lands (the per-BMU sums accumulate over chunks), so the H2D copy overlaps compute.
+        chunks = None
+        host = _as_f32_matrix(data)
+        if (host.device.type == 'cpu' and getattr(eng, 'name', '') == 'cuda' and not graphed and n_ep >= 1
+                and host.shape[1] == d and host.numel() * 4 >= (32 << 20)):
+            x, chunks = self._upload_in_chunks(eng, host)
+        else:
+            x = self._data_to_device(eng, host)
         if x.shape[1] != d:
             raise ValueError('Received %d features, expected %d.' % (x.shape[1], d))
         n = x.shape[0]
@@ -221,9 +256,13 @@ class XPySom:
         ws = eng.workspace(0, K, d)
         bmu = eng.empty(n, dtype=torch.int32)
         # per-row power-of-two scales for the fp16-split contraction: once per upload, not per epoch
-        xscale = eng.prepare_samples(x) if self._wants_xscale(dist_kind) else None
+        if not self._wants_xscale(dist_kind):
+            xscale = None
+        elif chunks is None:
+            xscale = eng.prepare_samples(x)
+        else:
+            xscale = eng.empty(n)                  # filled chunk by chunk during the first epoch
         tables = eng.neigh_tables(gx, gy, d)
-        prof = self._profile_events if getattr(self, '_profile', False) else None
 
         def schedule(t):
             eta_t = self._decay_function(self._learning_rate, self._learning_rateN, t, num_epochs)
@@ -235,9 +274,6 @@ class XPySom:
                 import torch.distributed as dist
                 dist.all_reduce(sc, op=dist.ReduceOp.SUM, group=group)
 
-        n_ep = iter_end - iter_beg
-        graphed = (self._use_cuda_graph and prof is None and not verbose and n_ep >= 3
-                   and getattr(eng, 'name', '') == 'cuda')
         if graphed:
             # One CUDA graph of the whole epoch, replayed n_ep - 1 times: sigma / eta live in a device-side
             # schedule indexed by a device-side epoch counter, so the captured launches never change.
@@ -273,7 +309,16 @@ class XPySom:
                     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                     ev[0].record()
                 # K1/K2 + K3: distance + argmin + per-BMU sums (one fused kernel on the tensor-core path)
-                eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
+                if chunks is not None and t == iter_beg:
+                    cur = torch.cuda.current_stream(eng.device)
+                    for r0, r1, landed in chunks:
+                        cur.wait_event(landed)
+                        xs_c = None
+                        if xscale is not None:
+                            xs_c = eng.prepare_samples(x[r0:r1], out=xscale[r0:r1])
+                        eng.epoch_accumulate(x[r0:r1], w, dist_kind, p, algo, S, c, ws, bmu_out=bmu[r0:r1], xscale=xs_c)
+                else:
+                    eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
                 if prof is not None:
                     ev[1].record()
                     prof.append(ev)
