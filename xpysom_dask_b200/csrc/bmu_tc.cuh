@@ -125,7 +125,7 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 // EPI_ACC independent pairs over interleaved columns keep the ALU pipe busy instead.  Each pair sees
 // its columns in increasing order with a strict <, the final lexicographic merge restores numpy's
 // first-minimum rule.
-constexpr int EPI_ACC = 8;
+constexpr int EPI_ACC = 4;
 struct RunMin {
     float v[EPI_ACC];
     int   i[EPI_ACC];
