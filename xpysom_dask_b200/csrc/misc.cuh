@@ -107,16 +107,36 @@ __global__ void row_sq_kernel(const float *__restrict__ W, int k, int d, float *
 }
 
 // per-row power-of-two scale of the samples for the fp16-split kernel: xscale[r] = 2^a_r with
-// max_c |x[r,c]| * 2^a_r in [2^14, 2^15).  One warp per row; one HBM pass, done once per upload.
-__global__ void row_scale_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, float *__restrict__ xscale) {
+// max_c |x[r,c]| * 2^a_r in [2^14, 2^15).  One HBM pass, done once per upload.  VEC: 16-byte aligned rows,
+// a group of LPR lanes (power of two >= d/4, at most 32) owns a row and 128-bit loads keep many rows in
+// flight per warp; otherwise one warp per row with scalar loads.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+row_scale_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, float *__restrict__ xscale, int lpr) {
     const int lane = threadIdx.x & 31;
+    const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t r = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < n; r += warps) {
-        float amax = 0.f;
-        for (int c = lane; c < d; c += 32) amax = fmaxf(amax, fabsf(__ldg(X + r * ldx + c)));
+    if (VEC) {
+        const int d4 = d >> 2, rpw = 32 / lpr, sub = lane / lpr, c0 = lane % lpr;
+        for (int64_t r0 = warp * rpw; r0 < n; r0 += warps * rpw) {
+            const int64_t r = r0 + sub;
+            float amax = 0.f;
+            if (r < n)
+                for (int c4 = c0; c4 < d4; c4 += lpr) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(X + r * ldx) + c4);
+                    amax = fmaxf(amax, fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w))));
+                }
+            for (int o = lpr >> 1; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            if (c0 == 0 && r < n) xscale[r] = pow2_scale_for(amax);
+        }
+    } else {
+        for (int64_t r = warp; r < n; r += warps) {
+            float amax = 0.f;
+            for (int c = lane; c < d; c += 32) amax = fmaxf(amax, fabsf(__ldg(X + r * ldx + c)));
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
-        if (lane == 0) xscale[r] = pow2_scale_for(amax);
+            for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+            if (lane == 0) xscale[r] = pow2_scale_for(amax);
+        }
     }
 }
 

@@ -143,9 +143,14 @@ int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, 
     SOM_REQUIRE(n >= 0 && d > 0 && ldx >= d, SOM_E_BADARG, "prepare_samples: bad argument");
     if (n == 0) return 0;
     SOM_REQUIRE(x_dev && xscale_dev, SOM_E_BADARG, "prepare_samples: NULL pointer");
-    int64_t blocks = ceil_div(n, 8);
-    if (blocks > 148 * 32) blocks = 148 * 32;
-    row_scale_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, n, d, ldx, xscale_dev);
+    const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0);
+    int lpr = 1;
+    while (lpr < 32 && lpr < d / 4) lpr <<= 1;
+    int64_t blocks = ceil_div(n, vec ? 8 * (32 / lpr) : 8);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    if (blocks < 1) blocks = 1;
+    if (vec) row_scale_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, n, d, ldx, xscale_dev, lpr);
+    else     row_scale_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, n, d, ldx, xscale_dev, 32);
     return check_cuda(cudaGetLastError(), "row_scale_kernel launch");
 }
 
