@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;");
     const uint32_t base = slot;
-    float bv[8]; int bi[8];
+    float bv[8]; int bi[8]; int li[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
     for (int a = 0; a < 8; ++a) { bv[a] = 1e30f; bi[a] = 0; }
     uint32_t x = 0;
@@ -50,6 +50,35 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
         const uint32_t taddr = base + ((uint32_t)(q * 32) << 16) + (warps == 8 ? h * 128 : 0);
         t0 = clock64();
         for (int t = 0; t < tiles; ++t) {
+            if (MODE == 6) {
+                // immediate local index (j + 32 c) written by a predicated move; tile base fixed up once per tile
+                float old[8];
+#pragma unroll
+                for (int a = 0; a < 8; ++a) old[a] = bv[a];
+                const float rsg = 1.5f + threadIdx.x * 1e-3f;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    if (c * 32 >= ncols) break;
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    wait_dep(v);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * 128 + c * 32) % 256);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 b = b4[j4];
+                        const float bb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const int j = j4 * 4 + e;
+                            const float sc = fmaf(bb[e], rsg, __uint_as_float(v[j]));
+                            if (sc < bv[j & 7]) { bv[j & 7] = sc; li[j & 7] = c * 32 + j; }
+                        }
+                    }
+                }
+#pragma unroll
+                for (int a = 0; a < 8; ++a) if (bv[a] != old[a]) bi[a] = t;
+                continue;
+            }
 #pragma unroll 1
             for (int c = 0; c < ncols / 32; ++c) {
                 uint32_t v[32];
@@ -117,7 +146,7 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
     }
     float s = 0; int si = 0;
 #pragma unroll
-    for (int a = 0; a < 8; ++a) { s += bv[a]; si += bi[a]; }
+    for (int a = 0; a < 8; ++a) { s += bv[a]; si += bi[a] * 256 + li[a]; }
     if (sink && (x == 0x12345678 || s == 1.2345f)) sink[threadIdx.x] = s + si;
     if (threadIdx.x % 32 == 0 && warp < warps) cyc[blockIdx.x * 8 + warp] = t1 - t0;
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -150,6 +179,7 @@ int main() {
         run<1>("LDTM + smem bias + argmin", w);
         run<4>("scaled + vibmin argmin", w);
         run<5>("scaled(f32x2) + vibmin", w);
+        run<6>("uniform fma + imm-index", w);
     }
     return 0;
 }

@@ -46,7 +46,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {   // ~2 s at 2 GHz
+        if (clock64() - t0 > 40000000000LL) {   // ~20 s at 2 GHz (generous: profilers slow kernels down a lot)
             printf("som_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, bar, parity);
             __trap();

@@ -72,7 +72,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
     if (mbar_try_wait_cluster(bar, parity)) return;
     const long long t0 = clock64();
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > 4000000000LL) {
+        if (clock64() - t0 > 40000000000LL) {
             printf("som_b200(tc2): mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
                    (int)blockIdx.x, (int)threadIdx.x, bar, parity);
             __trap();
