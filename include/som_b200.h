@@ -145,7 +145,7 @@ int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy,
 /* minimum scratch (factor tables only: the direct K^2 D kernel is used) */
 size_t som_b200_neigh_table_floats(int gx, int gy);
 /* scratch that also holds the intermediates of the two-pass separable path (rectangular gaussian / bubble /
- * triangle on maps of >= 1024 neurons: 2 K (gx+gy) D flops instead of 2 K^2 D) */
+ * triangle on maps of >= 4096 neurons: 2 K (gx+gy) D flops instead of 2 K^2 D) */
 size_t som_b200_neigh_scratch_floats(int gx, int gy, int d);
 
 /* Graph-replay variant of som_b200_neigh_apply: sigma and the learning rate are read on the device,

@@ -176,12 +176,12 @@ def test_neigh_apply_matches_reference_tables(eng):
                                         ("triangle", True), ("mexican_hat", False)])
 @pytest.mark.parametrize("topology", ["rectangular", "hexagonal"])
 def test_neigh_apply_large_map_separable_path(eng, fn, compact, topology):
-    """Maps of >= 1024 neurons: rectangular product-form neighbourhoods take the two-pass separable path,
+    """Maps of >= 1024 neurons: rectangular product-form neighbourhoods of >= 4096 neurons take the two-pass separable path,
     everything else the direct kernel; both must agree with the oracle's H^T S."""
     from xpysom_dask_b200 import _lib
     if topology == "hexagonal" and fn == "triangle":
         pytest.skip("rejected by the reference")
-    gx, gy, d = 40, 30, 20
+    gx, gy, d = 70, 60, 12
     K = gx * gy
     rng = np.random.RandomState(1)
     S = rng.randn(K, d).astype(np.float32)

@@ -247,7 +247,7 @@ inline size_t neigh_separable_floats(int gx, int gy, int d) { return (size_t)gx 
 
 inline bool neigh_is_separable(int topology, int kind, int gx, int gy) {
     return topology == SOM_TOPO_RECTANGULAR && kind != SOM_NEIGH_MEXICAN_HAT && gx <= 512 && gy <= 512 &&
-           (int64_t)gx * gy >= 1024;            // small maps: the direct kernel is one launch and already tiny
+           (int64_t)gx * gy >= 4096;            // smaller maps: the direct kernel is one launch and already tiny
 }
 
 inline size_t neigh_table_floats(int gx, int gy) {
