@@ -90,6 +90,28 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
                 } else if (MODE == 3) {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) bv[j & 7] = fminf(bv[j & 7], __uint_as_float(v[j]));
+                } else if (MODE >= 7 && MODE <= 10) {
+                    // pipe-balanced updates: compare on the ALU pipe, index (a float) and optionally the value
+                    // written by predicated FMA-pipe instructions
+                    float *fi = reinterpret_cast<float *>(bi);
+                    const float basef = (float)(t * 256 + c * 32);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * 128 + c * 32) % 256);
+                    float one; asm volatile("mov.f32 %0, 0f3f800000;" : "=f"(one));
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        float sc = __uint_as_float(v[j]);
+                        if (MODE == 10) sc += reinterpret_cast<const float *>(b4)[j];
+                        const float jf = (float)j;
+                        if (MODE == 7)
+                            asm("{\n .reg .pred p;\n setp.lt.f32 p, %2, %0;\n @p add.f32 %1, %3, %4;\n selp.f32 %0, %2, %0, p;\n}"
+                                : "+f"(bv[j & 3]), "+f"(fi[j & 3]) : "f"(sc), "f"(basef), "f"(jf));
+                        else if (MODE == 8 || MODE == 10)
+                            asm("{\n .reg .pred p;\n setp.lt.f32 p, %2, %0;\n @p add.f32 %1, %3, %4;\n @p fma.rn.f32 %0, %2, %5, 0f80000000;\n}"
+                                : "+f"(bv[j & 3]), "+f"(fi[j & 3]) : "f"(sc), "f"(basef), "f"(jf), "f"(one));
+                        else
+                            asm("{\n .reg .pred p;\n setp.lt.f32 p, %2, %0;\n @p add.f32 %1, %3, %4;\n @p add.f32 %0, %2, 0f80000000;\n}"
+                                : "+f"(bv[j & 3]), "+f"(fi[j & 3]) : "f"(sc), "f"(basef), "f"(jf));
+                    }
                 } else if (MODE == 4 || MODE == 5) {
                     // scaled score (2 FMA-pipe ops) made non-negative, compared as unsigned bits with the
                     // DPX min-with-predicate: 1 ALU op for the value + 1 for the index
@@ -180,6 +202,10 @@ int main() {
         run<4>("scaled + vibmin argmin", w);
         run<5>("scaled(f32x2) + vibmin", w);
         run<6>("uniform fma + imm-index", w);
+        run<7>("setp+selp+fadd.idx", w);
+        run<8>("setp+@ffma.val+@fadd.idx", w);
+        run<9>("setp+@fadd.val+@fadd.idx", w);
+        run<10>("bias + setp+@ffma+@fadd", w);
     }
     return 0;
 }

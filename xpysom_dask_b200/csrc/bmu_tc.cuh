@@ -128,14 +128,24 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr) {
 constexpr int EPI_ACC = 4;
 struct RunMin {
     float v[EPI_ACC];
-    int   i[EPI_ACC];
+    float fi[EPI_ACC];      // winning column kept as a float (exact: k_pad < 2^24, checked by the launchers)
     __device__ __forceinline__ void reset() {
 #pragma unroll
-        for (int a = 0; a < EPI_ACC; ++a) { v[a] = INFINITY; i[a] = 0x7fffffff; }
+        for (int a = 0; a < EPI_ACC; ++a) { v[a] = INFINITY; fi[a] = -1.f; }
+    }
+    // One candidate.  The epilogue is bound by the ALU pipe (compare + two selects per score), so the index
+    // update is a predicated FADD instead: it runs on the FMA pipe, which is nearly idle here.
+    __device__ __forceinline__ void upd(int a, float sc, float basef, float jf) {
+        asm("{\n\t.reg .pred p;\n\t"
+            "setp.lt.f32 p, %2, %0;\n\t"
+            "@p add.f32 %1, %3, %4;\n\t"
+            "selp.f32 %0, %2, %0, p;\n\t}"
+            : "+f"(v[a]), "+f"(fi[a]) : "f"(sc), "f"(basef), "f"(jf));
     }
     // 32 accumulator columns (TMEM registers) + their bias (shared or global memory, 16-byte aligned)
     __device__ __forceinline__ void chunk(const uint32_t (&acc)[32], const float *bias32, int colbase) {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+        const float basef = (float)colbase;
         float4 bq[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) bq[j4] = b4[j4];
@@ -146,19 +156,31 @@ struct RunMin {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 4 + e;
-                const float sc = __uint_as_float(acc[j]) + bb[e];
-                const int a = j % EPI_ACC;
-                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
+                upd(j % EPI_ACC, __uint_as_float(acc[j]) + bb[e], basef, (float)j);
             }
         }
     }
-    __device__ __forceinline__ void result(float &best, int &bidx) const {
-        best = v[0]; bidx = i[0];
+    // bias already inside the accumulator (folded into the contraction): compare the raw accumulator
+    __device__ __forceinline__ void chunk_nobias(const uint32_t (&acc)[32], int colbase) {
+        const float basef = (float)colbase;
 #pragma unroll
-        for (int a = 1; a < EPI_ACC; ++a) argmin_merge(best, bidx, v[a], i[a]);
+        for (int j = 0; j < 32; ++j) upd(j % EPI_ACC, __uint_as_float(acc[j]), basef, (float)j);
+    }
+    __device__ __forceinline__ void result(float &best, int &bidx) const {
+        best = v[0]; bidx = fi[0] < 0.f ? 0x7fffffff : (int)fi[0];
+#pragma unroll
+        for (int a = 1; a < EPI_ACC; ++a) argmin_merge(best, bidx, v[a], fi[a] < 0.f ? 0x7fffffff : (int)fi[a]);
         if (bidx == 0x7fffffff) bidx = 0;      // every score was +inf / NaN: numpy's argmin would say 0
     }
 };
+
+// One lane of a converged warp.  The whole warp runs the producer / MMA loops (so every address stays in uniform
+// registers -- no per-instruction R2UR waterfall) and only the async instructions sit under the election.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 
 __device__ __forceinline__ float tf32_rna_dev(float v) {
     uint32_t r;

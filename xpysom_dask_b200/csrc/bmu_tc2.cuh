@@ -60,10 +60,14 @@ __device__ __forceinline__ uint32_t map_to_cta(uint32_t saddr, uint32_t rank) {
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
 }
+// Wait on a barrier of THIS CTA that threads of the peer CTA (and multicast tcgen05.commit) also arrive on.  The
+// default CTA-scope acquire is what the data needs: everything the waiter consumes afterwards goes through the
+// async proxy (tensor core reading SMEM the peer fenced with fence.proxy.async) or TMEM (tcgen05 fences).  A
+// cluster-scope acquire here compiles to CCTL.IVALL -- a full L1 invalidate of the SM, three times per tile.
 __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
-                 "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2, %3;\n\t"
+                 "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
                  "selp.u32 %0, 1, 0, p;\n\t}"
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(tc::kSuspendHintNs) : "memory");
     return ok != 0;
@@ -108,7 +112,7 @@ constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
-               int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
+               const unsigned int *__restrict__ gstat, int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
                int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -137,6 +141,12 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const bool fused = acc.S != nullptr;
+    // bias folded into the contraction by prepare_codebook (three spare feature columns of the last K block hold
+    // the TF32 pieces of the bias on the W'hi side, ones on the X side): the epilogue adds nothing
+    const bool fold = gstat[3] != 0u;
+    const int probe = (acc.dbg >= 9 && blockIdx.x == 0) ? 1 : 0;     // timeline probe (tools/bmu_probe.py)
+    const int xp_chunks = acc.dbg == 10 ? 1 : BN / 2 / 32;            // EXPERIMENT knobs (wrong results!)
+    const int xp_mma = acc.dbg == 11 ? 1 : 99;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
@@ -158,7 +168,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     if (warp == 0) {
         // ===================== TMA producer (each CTA loads its own rows and its half of W') ===========
-        if (lane == 0) {
+        {
             uint32_t it = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
                 for (int nt = 0; nt < num_n_tiles; ++nt)
@@ -166,59 +176,89 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
                         tc::mbar_wait(empty_bar(s), ph ^ 1);
                         const uint32_t st = smem_base + s * STAGE_BYTES;
-                        if (leader) tc::mbar_expect_tx(bfull_bar(s), 4 * BH_BYTES);   // hi+lo halves of both CTAs
-                        tc::mbar_expect_tx(xfull_bar(s), A_BYTES);
-                        tc::tma_load_2d(st, &map_x, kb * BK, pt * (2 * BM) + (int)rank * BM, xfull_bar(s));
-                        tma_load_2d_2sm(st + 2 * A_BYTES,            &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
-                        tma_load_2d_2sm(st + 2 * A_BYTES + BH_BYTES, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                        if (tc::elect_one()) {
+                            if (leader) tc::mbar_expect_tx(bfull_bar(s), 4 * BH_BYTES);   // hi+lo halves of both CTAs
+                            tc::mbar_expect_tx(xfull_bar(s), A_BYTES);
+                            tc::tma_load_2d(st, &map_x, kb * BK, pt * (2 * BM) + (int)rank * BM, xfull_bar(s));
+                            tma_load_2d_2sm(st + 2 * A_BYTES,            &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                            tma_load_2d_2sm(st + 2 * A_BYTES + BH_BYTES, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                        }
+                        __syncwarp();
                     }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer: one thread of the LEADER CTA drives both tensor cores ========
-        if (leader && lane == 0) {
+        if (leader) {
             uint32_t it = 0, acc_it = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
                 for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                     const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
+                    tc::dbg_stamp(probe, 0, acc_it);
                     mbar_wait_cluster(tempty_bar(a), aph ^ 1);
                     tc::tc_fence_after();
+                    tc::dbg_stamp(probe, 1, acc_it);
                     const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                         const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
                         mbar_wait_cluster(bfull_bar(s), ph);
                         mbar_wait_cluster(ready_bar(s), ph);
                         tc::tc_fence_after();
+                        if (kb == 0) tc::dbg_stamp(probe, 2, acc_it);
                         const uint32_t st = smem_base + s * STAGE_BYTES;
                         const uint64_t a_hi = tc::make_smem_desc(st), a_lo = tc::make_smem_desc(st + A_BYTES);
                         const uint64_t b_hi = tc::make_smem_desc(st + 2 * A_BYTES);
                         const uint64_t b_lo = tc::make_smem_desc(st + 2 * A_BYTES + BH_BYTES);
+                        // only the 8-column steps that hold real features are issued (the rest of the block is the
+                        // TMA zero fill); the folded bias columns d..d+2 live in the hi*hi term alone
+                        const int dl = acc.d - kb * BK;
+                        const int kk_x = dl >= BK ? BK / UMMA_K : (dl + UMMA_K - 1) / UMMA_K;
+                        const int kk_h = (fold && kb == num_k_blocks - 1) ? (dl + 3 + UMMA_K - 1) / UMMA_K : kk_x;
+                        if (tc::elect_one()) {
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                             const uint64_t off = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                            umma_tf32_2sm(tmem_d, a_lo + off, b_hi + off, kIdesc2, (kb | kk) != 0);
-                            umma_tf32_2sm(tmem_d, a_hi + off, b_lo + off, kIdesc2, 1);
-                            umma_tf32_2sm(tmem_d, a_hi + off, b_hi + off, kIdesc2, 1);
+                            if (kk < kk_x && kk < xp_mma) {
+                                umma_tf32_2sm(tmem_d, a_lo + off, b_hi + off, kIdesc2, (kb | kk) != 0);
+                                umma_tf32_2sm(tmem_d, a_hi + off, b_lo + off, kIdesc2, 1);
+                            }
+                            if (kk < kk_h && kk < xp_mma) umma_tf32_2sm(tmem_d, a_hi + off, b_hi + off, kIdesc2, 1);
                         }
+                        if (acc.dbg == 12) tc::dbg_stamp(probe, 3, acc_it);
                         umma_commit_2sm(empty_bar(s));
+                        if (acc.dbg == 12) tc::dbg_stamp(probe, 4, acc_it);
+                        if (kb == num_k_blocks - 1) {
+                            umma_commit_2sm(tfull_bar(a));
+                            tc::dbg_stamp(probe, acc.dbg == 12 ? 5 : 3, acc_it);
+                        }
+                        }
+                        __syncwarp();
                     }
-                    umma_commit_2sm(tfull_bar(a));
                 }
         }
     } else if (warp < EPI_WARP0) {
         // ===================== converter: split the local X chunk into TF32 hi / lo =====================
         const int t = threadIdx.x - CONV_WARP0 * 32;
+        // Folded bias: this thread's float4s (e = t + 128 i) all sit at 16-byte chunk (t & 7) of rows with the same
+        // r & 7, i.e. at the SAME feature columns under the 128-byte swizzle: decide once which lanes hold d..d+2.
+        const int o = acc.d - ((num_k_blocks - 1) * BK + ((((t & 7) ^ ((t >> 3) & 7))) << 2));
+        const bool f0 = o <= 0 && o >= -2, f1 = o <= 1 && o >= -1, f2 = o <= 2 && o >= 0, f3 = o <= 3 && o >= 1;
+        const bool any_f = fold && (f0 || f1 || f2 || f3);
         uint32_t it = 0;
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
             for (int nt = 0; nt < num_n_tiles; ++nt)
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                     const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                    const bool ones = any_f && kb == num_k_blocks - 1;
                     tc::mbar_wait(xfull_bar(s), ph);
                     float4 *ahi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
                     float4 *alo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + A_BYTES);
 #pragma unroll
                     for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
                         const int e = t + 128 * i;
-                        const float4 v = ahi[e];
+                        float4 v = ahi[e];
+                        if (ones) {          // zero-filled features d..d+2 become 1 (hi = 1, lo = 0 after the split)
+                            v.x = f0 ? 1.f : v.x; v.y = f1 ? 1.f : v.y; v.z = f2 ? 1.f : v.z; v.w = f3 ? 1.f : v.w;
+                        }
                         float4 h, l;
                         h.x = tc::tf32_rna_dev(v.x); h.y = tc::tf32_rna_dev(v.y); h.z = tc::tf32_rna_dev(v.z); h.w = tc::tf32_rna_dev(v.w);
                         l.x = tc::tf32_rna_dev(v.x - h.x); l.y = tc::tf32_rna_dev(v.y - h.y);
@@ -248,18 +288,22 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 reinterpret_cast<float4 *>(bs)[lane] = nb;
                 __syncwarp();
                 nb = __ldg(reinterpret_cast<const float4 *>(bias + (nt + 1 < num_n_tiles ? nt + 1 : 0) * BN + h * (BN / 2)) + lane);
+                if (warp == EPI_WARP0 && lane == 0 && acc.dbg != 12) tc::dbg_stamp(probe, 4, acc_it);
                 tc::mbar_wait(tfull_bar(a), aph);
                 tc::tc_fence_after();
+                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, acc.dbg == 12 ? 6 : 5, acc_it);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
 #pragma unroll 1
-                for (int c = 0; c < BN / 2 / 32; ++c) {
+                for (int c = 0; c < xp_chunks; ++c) {
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait_dep(v);
-                    rm.chunk(v, bs + c * 32, col0 + c * 32);
+                    if (fold) rm.chunk_nobias(v, col0 + c * 32);
+                    else      rm.chunk(v, bs + c * 32, col0 + c * 32);
                 }
                 tc::tc_fence_before();
                 mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, acc.dbg == 12 ? 7 : 6, acc_it);
             }
             float best; int bidx;
             rm.result(best, bidx);
@@ -376,8 +420,9 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
-    acc.dbg = 0;
+    { const char *e = getenv("SOM_B200_DBG"); acc.dbg = e ? atoi(e) : 0; }
     bmu_tc2_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off),
+                                                               reinterpret_cast<const unsigned int *>(ws + L.gstat_off),
                                                                n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
     return check_cuda(cudaGetLastError(), "bmu_tc2_kernel launch");
 }

@@ -82,6 +82,7 @@ struct RunMinScaled : tc::RunMin {
     // uniform codebook scale: sc = acc + bias_k * rsg  (one FFMA per score, one shared-memory operand)
     __device__ __forceinline__ void chunk_uniform(const uint32_t (&acc)[32], const float *bias32, float rsg, int colbase) {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias32);
+        const float basef = (float)colbase;
         float4 bq[8];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) bq[j4] = b4[j4];
@@ -91,9 +92,7 @@ struct RunMinScaled : tc::RunMin {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 4 + e;
-                const float sc = fmaf(bb[e], rsg, __uint_as_float(acc[j]));
-                const int a = j % tc::EPI_ACC;
-                if (sc < v[a]) { v[a] = sc; i[a] = colbase + j; }
+                upd(j % tc::EPI_ACC, fmaf(bb[e], rsg, __uint_as_float(acc[j])), basef, (float)j);
             }
         }
     }
@@ -102,6 +101,7 @@ struct RunMinScaled : tc::RunMin {
         const float4 *b4 = reinterpret_cast<const float4 *>(bias32);     // shared memory, broadcast reads
         const float4 *s4 = reinterpret_cast<const float4 *>(winv32);
         const uint64_t rs2 = pack2(rs, rs);
+        const float basef = (float)colbase;
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
             const float4 b = b4[j4], s = s4[j4];
@@ -111,8 +111,7 @@ struct RunMinScaled : tc::RunMin {
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 4 + e;
-                const int a = j % tc::EPI_ACC;
-                if (sc[e] < v[a]) { v[a] = sc[e]; i[a] = colbase + j; }
+                upd(j % tc::EPI_ACC, sc[e], basef, (float)j);
             }
         }
     }
@@ -271,8 +270,11 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         const uint32_t sta = a_base + sa * SLOT_BYTES, stb = b_base + sb * SLOT_BYTES;
                         const uint64_t a_hi = tc::make_smem_desc(sta), a_lo = tc::make_smem_desc(sta + HALF_SLOT);
                         const uint64_t b_hi = tc::make_smem_desc(stb), b_lo = tc::make_smem_desc(stb + HALF_SLOT);
+                        const int dl = acc.d - kb * BK;          // real features in this block; the rest is zero fill
+                        const int kk_n = dl >= BK ? BK / UMMA_K : (dl + UMMA_K - 1) / UMMA_K;
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                            if (kk >= kk_n) break;
                             const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);    // +32 B along K
                             umma_f16_2sm(tmem_d, a_lo + off, b_hi + off, kIdescF16, (kb | kk) != 0);
                             umma_f16_2sm(tmem_d, a_hi + off, b_lo + off, kIdescF16, 1);

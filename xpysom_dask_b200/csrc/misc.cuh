@@ -65,8 +65,8 @@ __global__ void codebook_stats_kernel(const float *__restrict__ W, int k, int d,
 __global__ void codebook_split_kernel(const float *__restrict__ W, int k, int d, int dist_kind, int k_pad, int d_pad,
                                       float *__restrict__ whi, float *__restrict__ wlo, int d_pad64,
                                       __half *__restrict__ w16hi, __half *__restrict__ w16lo, float *__restrict__ wsinv,
-                                      const float *__restrict__ aux, const float *__restrict__ amax,
-                                      unsigned int *__restrict__ gstat) {
+                                      const float *__restrict__ aux, const float *__restrict__ bias,
+                                      const float *__restrict__ amax, unsigned int *__restrict__ gstat) {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= k_pad) return;
@@ -77,13 +77,21 @@ __global__ void codebook_split_kernel(const float *__restrict__ W, int k, int d,
     const unsigned int nmin = gstat[1];
     const float gmin = nmin ? __uint_as_float(~nmin) : gmax;
     const bool uniform = !(gmax > 0.f) || gmin >= gmax * (1.f / 4096.f);
-    if (warp == 0 && lane == 0) gstat[2] = uniform ? 1u : 0u;
+    // TF32 copies: when the last 32-feature block has three spare columns, the epilogue bias is FOLDED into the
+    // contraction: columns d, d+1, d+2 of W'hi carry the three TF32 pieces of bias_k (33 mantissa bits, more than
+    // the fp32 accumulator keeps) and the kernel sets the matching X columns to 1; gstat[3] = 1 tells it so.
+    const bool fold = d_pad - d >= 3;
+    if (warp == 0 && lane == 0) { gstat[2] = uniform ? 1u : 0u; gstat[3] = fold ? 1u : 0u; }
+    const float bk = bias[warp];                       // |w|^2, 0 (cosine) or +inf (padding neuron)
+    float b0 = tf32_rna(bk), b1 = 0.f, b2 = 0.f;
+    if (isfinite(bk)) { b1 = tf32_rna(bk - b0); b2 = tf32_rna((bk - b0) - b1); }
     for (int c = lane; c < d_pad; c += 32) {
         float v = 0.f;
         if (real && c < d) v = W[(int64_t)warp * d + c] * scale;
-        const float hi = tf32_rna(v);
+        float hi = tf32_rna(v), lo = tf32_rna(v - hi);
+        if (fold && c >= d && c < d + 3) { hi = c == d ? b0 : (c == d + 1 ? b1 : b2); lo = 0.f; }
         whi[(int64_t)warp * d_pad + c] = hi;
-        wlo[(int64_t)warp * d_pad + c] = tf32_rna(v - hi);
+        wlo[(int64_t)warp * d_pad + c] = lo;
     }
     const float ps = pow2_scale_for(uniform ? gmax : amax[warp]);
     if (lane == 0) wsinv[warp] = 1.f / ps;              // exact: ps is a power of two

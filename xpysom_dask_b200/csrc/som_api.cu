@@ -135,7 +135,8 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
     codebook_split_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
         w_dev, k, d, dist_kind, L.k_pad, L.d_pad, reinterpret_cast<float *>(ws + L.whi_off),
         reinterpret_cast<float *>(ws + L.wlo_off), L.d_pad64, reinterpret_cast<__half *>(ws + L.w16hi_off),
-        reinterpret_cast<__half *>(ws + L.w16lo_off), reinterpret_cast<float *>(ws + L.wsinv_off), aux, amax, gstat);
+        reinterpret_cast<__half *>(ws + L.w16lo_off), reinterpret_cast<float *>(ws + L.wsinv_off), aux,
+        reinterpret_cast<const float *>(ws + L.bias_off), amax, gstat);
     return check_cuda(cudaGetLastError(), "codebook_split_kernel launch");
 }
 
