@@ -216,7 +216,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
     if (warp == 0) {
         // ===================== B producer: this CTA's half of W'hi / W'lo per (row tile, neuron tile, k block) ====
-        if (lane == 0) {
+        // (the whole warp runs the loop, one elected lane issues: addresses stay in uniform registers)
+        {
             uint32_t it = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
                 for (int nt = 0; nt < num_n_tiles; ++nt)
@@ -224,14 +225,17 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         const int s = it % NB; const uint32_t ph = (it / NB) & 1;
                         tc::mbar_wait(bempty_bar(s), ph ^ 1);
                         const uint32_t st = b_base + s * SLOT_BYTES;
-                        if (leader) tc::mbar_expect_tx(bfull_bar(s), 2 * SLOT_BYTES);
-                        tma_load_2d_2sm(st,             &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
-                        tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                        if (tc::elect_one()) {
+                            if (leader) tc::mbar_expect_tx(bfull_bar(s), 2 * SLOT_BYTES);
+                            tma_load_2d_2sm(st,             &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                            tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                        }
+                        __syncwarp();
                     }
         }
     } else if (warp == APROD_WARP) {
         // ===================== A producer: raw fp32 X chunks [128 rows x 64 features] ==========================
-        if (lane == 0) {
+        {
             uint32_t ia = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs) {
                 const int reps = resident ? 1 : num_n_tiles;
@@ -240,16 +244,19 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         const int s = ia % NA; const uint32_t ph = (ia / NA) & 1;
                         tc::mbar_wait(aempty_bar(s), ph ^ 1);
                         const uint32_t st = a_base + s * SLOT_BYTES;
-                        tc::mbar_expect_tx(afull_bar(s), SLOT_BYTES);
                         const int row0 = pt * (2 * BM) + (int)rank * BM;
-                        tc::tma_load_2d(st,             &map_x, kb * BK,      row0, afull_bar(s));
-                        tc::tma_load_2d(st + HALF_SLOT, &map_x, kb * BK + 32, row0, afull_bar(s));
+                        if (tc::elect_one()) {
+                            tc::mbar_expect_tx(afull_bar(s), SLOT_BYTES);
+                            tc::tma_load_2d(st,             &map_x, kb * BK,      row0, afull_bar(s));
+                            tc::tma_load_2d(st + HALF_SLOT, &map_x, kb * BK + 32, row0, afull_bar(s));
+                        }
+                        __syncwarp();
                     }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) ==========================================================
-        if (leader && lane == 0) {
+        if (leader) {
             uint32_t it = 0, acc_it = 0, tile_it = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it)
                 for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
@@ -272,19 +279,24 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         const uint64_t b_hi = tc::make_smem_desc(stb), b_lo = tc::make_smem_desc(stb + HALF_SLOT);
                         const int dl = acc.d - kb * BK;          // real features in this block; the rest is zero fill
                         const int kk_n = dl >= BK ? BK / UMMA_K : (dl + UMMA_K - 1) / UMMA_K;
+                        if (tc::elect_one()) {
 #pragma unroll
-                        for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                            if (kk >= kk_n) break;
-                            const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);    // +32 B along K
-                            umma_f16_2sm(tmem_d, a_lo + off, b_hi + off, kIdescF16, (kb | kk) != 0);
-                            umma_f16_2sm(tmem_d, a_hi + off, b_lo + off, kIdescF16, 1);
-                            umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, kIdescF16, 1);
+                            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                                if (kk >= kk_n) break;
+                                const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);    // +32 B along K
+                                umma_f16_2sm(tmem_d, a_lo + off, b_hi + off, kIdescF16, (kb | kk) != 0);
+                                umma_f16_2sm(tmem_d, a_hi + off, b_lo + off, kIdescF16, 1);
+                                umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, kIdescF16, 1);
+                            }
+                            umma_commit_2sm(bempty_bar(sb));
+                            if (!resident || nt == num_n_tiles - 1) umma_commit_2sm(aempty_bar(sa));
+                            if (kb == num_k_blocks - 1) {
+                                umma_commit_2sm(tfull_bar(a));
+                                tc::dbg_stamp(probe, 3, acc_it);     // MMA: all MMAs of the tile issued + committed
+                            }
                         }
-                        umma_commit_2sm(bempty_bar(sb));
-                        if (!resident || nt == num_n_tiles - 1) umma_commit_2sm(aempty_bar(sa));
+                        __syncwarp();
                     }
-                    umma_commit_2sm(tfull_bar(a));
-                    tc::dbg_stamp(probe, 3, acc_it);                 // MMA: all MMAs of the tile issued + committed
                 }
         }
     } else if ((warp >= CONV_WARP0 && warp < EPI_WARP0) || (conv_extra && warp >= EPI_WARP0 + 4 && warp < SCAT_WARP0)) {
