@@ -38,7 +38,7 @@ torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / reps
 print(algo, "n=%d d=%d K=%d fused=%s: %.3f ms, %.1f TFLOP/s algorithmic, %.3e elements/s"
       % (n, d, k, fused, ms, 2.0 * n * k * d / ms / 1e9, n * k / ms * 1e3))
-if int(os.environ.get("SOM_B200_DBG", "0")) >= 9:
+if os.environ.get("SOM_B200_DBG") == "9":
     import ctypes
     import numpy as np
     buf = np.zeros(8 * 64, dtype=np.int64)
@@ -47,4 +47,4 @@ if int(os.environ.get("SOM_B200_DBG", "0")) >= 9:
     t0 = t[4:, 0].min()
     print("tile |  MMA: wait_acc  acc_free  ops_ready  committed |  EPI: wait  tile_ready  drained   (cycles, leader CTA 0)")
     for i in range(8, 40):
-        print("%4d | %9d %9d %9d %9d | %9d %9d %9d %9d" % ((i,) + tuple(int(v - t0) for v in t[i, :8])))
+        print("%4d | %9d %9d %9d %9d | %9d %9d %9d" % ((i,) + tuple(int(v - t0) for v in t[i, :7])))

@@ -176,6 +176,123 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "r"(512));
 }
 
+
+// ---- epilogue (setp + selp + predicated fadd index) with a CONCURRENT tensor-core stream ----------------
+// warps 0-7 drain TMEM columns 0..255 as above; warp 8 keeps issuing kind::tf32 / kind::f16 MMAs (M=128, N=256, one
+// K step each) into columns 256..511, nmma per "tile", to see whether accumulator traffic slows tcgen05.ld down.
+__device__ __forceinline__ uint64_t desc128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+template <int F16>
+__global__ void __launch_bounds__(288, 1) kc(int tiles, int nmma, int epi_on, long long *cyc, float *sink) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    __shared__ uint32_t slot;
+    __shared__ __align__(8) unsigned long long bar;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint8_t *ops = (uint8_t *)(((uintptr_t)sm + 1023) & ~(uintptr_t)1023);
+    for (int i = threadIdx.x; i < 49152 / 4; i += blockDim.x) ((uint32_t *)ops)[i] = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&bar)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&slot)), "r"(512));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;");
+    const uint32_t base = slot;
+    float bv[4], fi[4];
+#pragma unroll
+    for (int a = 0; a < 4; ++a) { bv[a] = 1e30f; fi[a] = 0; }
+    long long t0 = clock64(), t1 = t0;
+    if (warp < 8) {
+        if (epi_on) {
+            const int q = warp & 3, h = warp >> 2;
+            const uint32_t taddr = base + ((uint32_t)(q * 32) << 16) + h * 128;
+            for (int t = 0; t < tiles; ++t) {
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(taddr + c * 32, v);
+                    wait_dep(v);
+                    const float basef = (float)(t * 256 + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(v[j]); const float jf = (float)j;
+                        asm("{\n .reg .pred p;\n setp.lt.f32 p, %2, %0;\n @p add.f32 %1, %3, %4;\n selp.f32 %0, %2, %0, p;\n}"
+                            : "+f"(bv[j & 3]), "+f"(fi[j & 3]) : "f"(sc), "f"(basef), "f"(jf));
+                    }
+                }
+            }
+            t1 = clock64();
+        }
+    } else if (nmma > 0) {
+        const uint32_t sa = (uint32_t)__cvta_generic_to_shared(ops), sb = sa + 16384;
+        const uint64_t ad = desc128(sa), bd = desc128(sb);
+        const uint32_t idesc = F16 ? ((1u << 4) | ((256u >> 3) << 17) | ((128u >> 4) << 24))
+                                   : ((1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24));
+        const uint32_t barp = (uint32_t)__cvta_generic_to_shared(&bar);
+        for (int t = 0; t < tiles; ++t) {
+            uint32_t pred;
+            asm volatile("{\n .reg .pred p;\n elect.sync _|p, 0xffffffff;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(pred));
+            if (pred) {
+                for (int m = 0; m < nmma; ++m) {
+                    if (F16)
+                        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}"
+                                     :: "r"(base + 256), "l"(ad), "l"(bd), "r"(idesc), "r"(m) : "memory");
+                    else
+                        asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}"
+                                     :: "r"(base + 256), "l"(ad), "l"(bd), "r"(idesc), "r"(m) : "memory");
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(barp) : "memory");
+            }
+            __syncwarp();
+            // wait for this tile's MMAs (keeps exactly one tile in flight, like a 2-buffer pipeline would)
+            uint32_t ok = 0;
+            while (!ok)
+                asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}"
+                             : "=r"(ok) : "r"(barp), "r"((uint32_t)(t & 1)) : "memory");
+        }
+        t1 = clock64();
+    }
+    float s = 0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) s += bv[a] + fi[a];
+    if (sink && s == 1.2345f) sink[threadIdx.x] = s;
+    if (lane == 0) cyc[blockIdx.x * 9 + warp] = t1 - t0;
+    asm volatile("tcgen05.fence::before_thread_sync;");
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "r"(512));
+}
+
+template <int F16>
+void runc(const char *name, int nmma, int epi_on) {
+    long long *cyc; float *sink;
+    cudaMalloc(&cyc, 148 * 9 * 8); cudaMalloc(&sink, 4096);
+    cudaMemset(cyc, 0, 148 * 9 * 8);
+    const int tiles = 200;
+    cudaFuncSetAttribute(kc<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, 51200);
+    kc<F16><<<148, 288, 51200>>>(tiles, nmma, epi_on, cyc, sink);
+    kc<F16><<<148, 288, 51200>>>(tiles, nmma, epi_on, cyc, sink);
+    cudaError_t e = cudaDeviceSynchronize();
+    long long h[148 * 9];
+    cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
+    long long me = 0, mm = 0;
+    for (int b = 0; b < 148; ++b) { for (int w = 0; w < 8; ++w) me = h[b * 9 + w] > me ? h[b * 9 + w] : me; mm = h[b * 9 + 8] > mm ? h[b * 9 + 8] : mm; }
+    printf("%-34s nmma=%2d epi=%d: epilogue %7.1f cyc/tile, MMA stream %7.1f cyc/tile (%.1f per MMA)  [%s]\n", name, nmma, epi_on,
+           (double)me / tiles, (double)mm / tiles, nmma ? (double)mm / tiles / nmma : 0.0, cudaGetErrorString(e));
+    cudaFree(cyc); cudaFree(sink);
+}
+
 template <int MODE>
 void run(const char *name, int warps) {
     long long *cyc; float *sink;
@@ -194,6 +311,16 @@ void run(const char *name, int warps) {
 }
 
 int main() {
+    runc<0>("epilogue alone", 0, 1);
+    runc<0>("tf32 MMAs alone", 7, 0);
+    runc<0>("tf32 MMAs alone", 12, 0);
+    runc<1>("f16 MMAs alone", 12, 0);
+    runc<0>("epilogue + tf32 MMAs", 7, 1);
+    runc<0>("epilogue + tf32 MMAs", 12, 1);
+    runc<1>("epilogue + f16 MMAs", 12, 1);
+    runc<1>("epilogue + f16 MMAs", 3, 1);
+    return 0;
+
     for (int w = 4; w <= 8; w += 4) {
         run<0>("LDTM only", w);
         run<3>("LDTM + value-only min", w);

@@ -41,15 +41,22 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
                  : "=r"(ok) : "r"(bar), "r"(parity), "r"(kSuspendHintNs) : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (-> CUDA error on the host), never hang the GPU.
+// Bounded wait: a protocol bug must trap (-> CUDA error on the host), never hang the GPU.  The clock is looked at
+// only every 1024 failed polls: a sleeping waiter is woken by EVERY arrival on its barrier, and each wake-up costs
+// issue slots that the epilogue warps need.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
+    long long t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 40000000000LL) {   // ~20 s at 2 GHz (generous: profilers slow kernels down a lot)
-            printf("som_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
-                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-            __trap();
+        if ((++polls & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 40000000000LL) {   // ~20 s at 2 GHz (generous: profilers slow kernels down a lot)
+                printf("som_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
+                       (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+                __trap();
+            }
         }
     }
 }

@@ -74,12 +74,17 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t par
 }
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait_cluster(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t polls = 0;
+    long long t0 = 0;
     while (!mbar_try_wait_cluster(bar, parity)) {
-        if (clock64() - t0 > 40000000000LL) {
-            printf("som_b200(tc2): mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
-                   (int)blockIdx.x, (int)threadIdx.x, bar, parity);
-            __trap();
+        if ((++polls & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 40000000000LL) {
+                printf("som_b200(tc2): mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
+                       (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+                __trap();
+            }
         }
     }
 }
@@ -144,18 +149,16 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     // bias folded into the contraction by prepare_codebook (three spare feature columns of the last K block hold
     // the TF32 pieces of the bias on the W'hi side, ones on the X side): the epilogue adds nothing
     const bool fold = gstat[3] != 0u;
-    const int probe = (acc.dbg >= 9 && blockIdx.x == 0) ? 1 : 0;     // timeline probe (tools/bmu_probe.py)
-    const int xp_chunks = acc.dbg == 10 ? 1 : BN / 2 / 32;            // EXPERIMENT knobs (wrong results!)
-    const int xp_mma = acc.dbg == 11 ? 1 : 99;
+    const int probe = (acc.dbg == 9 && blockIdx.x == 0) ? 1 : 0;     // timeline probe (tools/bmu_probe.py)
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < STAGES; ++s) {
             tc::mbar_init(xfull_bar(s), 1); tc::mbar_init(bfull_bar(s), 1);
-            tc::mbar_init(ready_bar(s), 256); tc::mbar_init(empty_bar(s), 1);
+            tc::mbar_init(ready_bar(s), 2 * 4); tc::mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS);
-            tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS / 32);
+            tc::mbar_init(bfullq_bar(a), 4); tc::mbar_init(bemptyq_bar(a), 4);
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
@@ -194,14 +197,15 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                     const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
                     tc::dbg_stamp(probe, 0, acc_it);
-                    mbar_wait_cluster(tempty_bar(a), aph ^ 1);
-                    tc::tc_fence_after();
-                    tc::dbg_stamp(probe, 1, acc_it);
                     const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                         const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait_cluster(bfull_bar(s), ph);
-                        mbar_wait_cluster(ready_bar(s), ph);
+                        mbar_wait_cluster(bfull_bar(s), ph);           // operands first: they are ready long before
+                        mbar_wait_cluster(ready_bar(s), ph);           // the accumulator is, so these return at once
+                        if (kb == 0) {
+                            mbar_wait_cluster(tempty_bar(a), aph ^ 1);  // both CTAs' epilogues drained this accumulator
+                            tc::dbg_stamp(probe, 1, acc_it);
+                        }
                         tc::tc_fence_after();
                         if (kb == 0) tc::dbg_stamp(probe, 2, acc_it);
                         const uint32_t st = smem_base + s * STAGE_BYTES;
@@ -217,18 +221,16 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                         for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                             const uint64_t off = (uint64_t)((kk * UMMA_K * 4) >> 4);
-                            if (kk < kk_x && kk < xp_mma) {
+                            if (kk < kk_x) {
                                 umma_tf32_2sm(tmem_d, a_lo + off, b_hi + off, kIdesc2, (kb | kk) != 0);
                                 umma_tf32_2sm(tmem_d, a_hi + off, b_lo + off, kIdesc2, 1);
                             }
-                            if (kk < kk_h && kk < xp_mma) umma_tf32_2sm(tmem_d, a_hi + off, b_hi + off, kIdesc2, 1);
+                            if (kk < kk_h) umma_tf32_2sm(tmem_d, a_hi + off, b_hi + off, kIdesc2, 1);
                         }
-                        if (acc.dbg == 12) tc::dbg_stamp(probe, 3, acc_it);
                         umma_commit_2sm(empty_bar(s));
-                        if (acc.dbg == 12) tc::dbg_stamp(probe, 4, acc_it);
                         if (kb == num_k_blocks - 1) {
                             umma_commit_2sm(tfull_bar(a));
-                            tc::dbg_stamp(probe, acc.dbg == 12 ? 5 : 3, acc_it);
+                            tc::dbg_stamp(probe, 3, acc_it);
                         }
                         }
                         __syncwarp();
@@ -266,7 +268,8 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         ahi[e] = h; alo[e] = l;
                     }
                     tc::fence_proxy_async();
-                    mbar_arrive_cluster(map_to_cta(ready_bar(s), 0));       // the leader's barrier counts both CTAs
+                    __syncwarp();                                           // one arrival per warp: every arrival
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(ready_bar(s), 0));   // wakes the sleeping waiter
                 }
     } else if (warp < SCAT_WARP0) {
         // ===================== epilogue: TMEM -> registers -> running argmin =====================
@@ -288,13 +291,13 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 reinterpret_cast<float4 *>(bs)[lane] = nb;
                 __syncwarp();
                 nb = __ldg(reinterpret_cast<const float4 *>(bias + (nt + 1 < num_n_tiles ? nt + 1 : 0) * BN + h * (BN / 2)) + lane);
-                if (warp == EPI_WARP0 && lane == 0 && acc.dbg != 12) tc::dbg_stamp(probe, 4, acc_it);
+                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 4, acc_it);
                 tc::mbar_wait(tfull_bar(a), aph);
                 tc::tc_fence_after();
-                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, acc.dbg == 12 ? 6 : 5, acc_it);
+                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 5, acc_it);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
 #pragma unroll 1
-                for (int c = 0; c < xp_chunks; ++c) {
+                for (int c = 0; c < BN / 2 / 32; ++c) {
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait_dep(v);
@@ -302,8 +305,9 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     else      rm.chunk(v, bs + c * 32, col0 + c * 32);
                 }
                 tc::tc_fence_before();
-                mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
-                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, acc.dbg == 12 ? 7 : 6, acc_it);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+                if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 6, acc_it);
             }
             float best; int bidx;
             rm.result(best, bidx);
@@ -322,7 +326,8 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                     tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
                     bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
-                    tc::mbar_arrive(bfullq_bar(b));
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(bfullq_bar(b));
                 }
             }
         }
@@ -368,7 +373,8 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
                     }
                 }
-                tc::mbar_arrive(bemptyq_bar(b));
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
             }
         }
     }

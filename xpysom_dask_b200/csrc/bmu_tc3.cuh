@@ -199,11 +199,11 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int probe = (acc.dbg == 9 && blockIdx.x == 0) ? 1 : 0;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 2 * nconv); tc::mbar_init(aempty_bar(s), 1); }
+        for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 2 * nconv / 32); tc::mbar_init(aempty_bar(s), 1); }
         for (int s = 0; s < NB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * nepi);
-            tc::mbar_init(bfullq_bar(a), 128); tc::mbar_init(bemptyq_bar(a), 128);
+            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * nepi / 32);
+            tc::mbar_init(bfullq_bar(a), 4); tc::mbar_init(bemptyq_bar(a), 4);
         }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
@@ -261,10 +261,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it)
                 for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                     const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
-                    tc::dbg_stamp(probe, 0, acc_it);                 // MMA: starts waiting for the accumulator
-                    mbar_wait_cluster(tempty_bar(a), aph ^ 1);
-                    tc::tc_fence_after();
-                    tc::dbg_stamp(probe, 1, acc_it);                 // MMA: accumulator free
+                    tc::dbg_stamp(probe, 0, acc_it);                 // MMA: starts waiting for the tile's inputs
                     const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                         const uint32_t ia = resident ? (tile_it * (uint32_t)num_k_blocks + kb) : it;
@@ -272,6 +269,10 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         const int sb = it % NB; const uint32_t phb = (it / NB) & 1;
                         mbar_wait_cluster(aready_bar(sa), pha);       // hi/lo tiles of both CTAs written
                         mbar_wait_cluster(bfull_bar(sb), phb);        // W' halves of both CTAs landed
+                        if (kb == 0) {                                // operands first, then the accumulator
+                            mbar_wait_cluster(tempty_bar(a), aph ^ 1);
+                            tc::dbg_stamp(probe, 1, acc_it);         // MMA: accumulator free
+                        }
                         tc::tc_fence_after();
                         if (kb == 0) tc::dbg_stamp(probe, 2, acc_it);    // MMA: operands of the first k block ready
                         const uint32_t sta = a_base + sa * SLOT_BYTES, stb = b_base + sb * SLOT_BYTES;
@@ -315,7 +316,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     if (conv_extra) convert_item<256>(slot, t, row0, n, xscale);
                     else            convert_item<128>(slot, t, row0, n, xscale);
                     tc::fence_proxy_async();
-                    mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
+                    __syncwarp();                                           // one arrival per warp (see bmu_tc2.cuh)
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
                 }
         }
     } else if (warp >= EPI_WARP0 && warp < (conv_extra ? EPI_WARP0 + 4 : SCAT_WARP0)) {
@@ -389,7 +391,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 }
                 tc::tc_fence_before();
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 6, acc_it);   // EPI: this warp drained its half
-                mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
             }
             float best; int bidx;
             rm.result(best, bidx);
@@ -408,7 +411,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                     tc::mbar_wait(bemptyq_bar(b), bph ^ 1);
                     bmu_s[b * BM + row_in_tile] = (row < n) ? bidx : -1;
-                    tc::mbar_arrive(bfullq_bar(b));
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(bfullq_bar(b));
                 }
             }
         }
@@ -454,7 +458,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
                     }
                 }
-                tc::mbar_arrive(bemptyq_bar(b));
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
             }
         }
     }
