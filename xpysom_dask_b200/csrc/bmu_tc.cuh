@@ -48,11 +48,33 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     uint32_t polls = 0;
     long long t0 = 0;
-    while (!mbar_try_wait(bar, parity)) {
-        if ((++polls & 1023u) == 0) {
+    for (;;) {
+        if (mbar_try_wait(bar, parity) || mbar_try_wait(bar, parity) || mbar_try_wait(bar, parity) ||
+            mbar_try_wait(bar, parity)) return;
+        if ((++polls & 255u) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
             if (now - t0 > 40000000000LL) {   // ~20 s at 2 GHz (generous: profilers slow kernels down a lot)
+                printf("som_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
+                       (int)blockIdx.x, (int)threadIdx.x, bar, parity);
+                __trap();
+            }
+        }
+    }
+}
+// Wait of a warp that is OFF the critical path (scatter warps, TMA producers running stages ahead): the suspend
+// hint of try_wait is not honoured for long (ncu: one poll every ~50 cycles), so back off explicitly and leave
+// the issue slots to the epilogue warps.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+    if (mbar_try_wait(bar, parity)) return;
+    uint32_t polls = 0;
+    long long t0 = 0;
+    while (!mbar_try_wait(bar, parity)) {
+        __nanosleep(sleep_ns);
+        if ((++polls & 1023u) == 0) {
+            const long long now = clock64();
+            if (t0 == 0) t0 = now;
+            if (now - t0 > 40000000000LL) {
                 printf("som_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
                        (int)blockIdx.x, (int)threadIdx.x, bar, parity);
                 __trap();
@@ -140,13 +162,15 @@ struct RunMin {
 #pragma unroll
         for (int a = 0; a < EPI_ACC; ++a) { v[a] = INFINITY; fi[a] = -1.f; }
     }
-    // One candidate.  The epilogue is bound by the ALU pipe (compare + two selects per score), so the index
-    // update is a predicated FADD instead: it runs on the FMA pipe, which is nearly idle here.
+    // One candidate.  The kernels are bound by the ALU pipe (ncu: 80 % busy with the FMA pipe at 20 %), and a
+    // compare + two selects per score would all be ALU work.  Only the compare stays there: the index is written
+    // by a predicated FADD (base + immediate) and the value by a predicated FADD of -0.0 (an exact copy for every
+    // input, -0.0 and denormals included), both on the FMA pipe.
     __device__ __forceinline__ void upd(int a, float sc, float basef, float jf) {
         asm("{\n\t.reg .pred p;\n\t"
             "setp.lt.f32 p, %2, %0;\n\t"
             "@p add.f32 %1, %3, %4;\n\t"
-            "selp.f32 %0, %2, %0, p;\n\t}"
+            "@p add.f32 %0, %2, 0f80000000;\n\t}"
             : "+f"(v[a]), "+f"(fi[a]) : "f"(sc), "f"(basef), "f"(jf));
     }
     // 32 accumulator columns (TMEM registers) + their bias (shared or global memory, 16-byte aligned)

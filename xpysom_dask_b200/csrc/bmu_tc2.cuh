@@ -340,7 +340,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             uint32_t tile_it = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
                 const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
-                tc::mbar_wait(bfullq_bar(b), bph);
+                tc::mbar_wait_relaxed(bfullq_bar(b), bph, 400);
                 const int *bm = bmu_s + b * BM;
                 const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
                 { const int mine = bm[t]; if (mine >= 0) atomicAdd(acc.cnt + mine, 1); }
