@@ -37,7 +37,7 @@ using tc::FusedAcc;
 using tc::smem_u32;
 using namespace tc2;   // cluster / 2-SM wrappers
 
-constexpr int BM = 128, BN = 256, BNH = 128;
+constexpr int BM = 128;                  // sample rows per CTA (TMEM lanes); the neuron-tile width is the TBN template argument
 constexpr int BK = 64;                   // features per block: 128 bytes of fp16
 constexpr int UMMA_K = 16;
 constexpr int NA = 3, NB = 3;
@@ -47,7 +47,8 @@ constexpr int NUM_THREADS = 640;
 constexpr int APROD_WARP = 2, CONV_WARP0 = 4, EPI_WARP0 = 8, SCAT_WARP0 = 16;
 constexpr int EPI_THREADS = 256;
 constexpr int RESIDENT_MAX_KB = 2;       // D <= 128: X tiles resident across neuron tiles
-constexpr int NUM_BARS = 3 * NA + 2 * NB + 4 + 4;
+constexpr int MAX_ACC = 4;                 // accumulator stages in TMEM: 512 columns / neuron-tile width
+constexpr int NUM_BARS = 3 * NA + 2 * NB + 2 * MAX_ACC + 4;
 constexpr int EPI_STAGE_BYTES = 8 * 2 * 128 * 4;   // per epilogue warp: 128 bias + 128 inverse-scale floats
 constexpr int SMEM_BYTES = (NA + NB) * SLOT_BYTES + EPI_STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
 
@@ -58,7 +59,7 @@ __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, ui
                  :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 // D = f32 (bit 4), A = B = f16 (format 0), K-major, N >> 3 at bit 17, M >> 4 at bit 24 (M = 256 over the pair)
-constexpr uint32_t kIdescF16 = (1u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+__host__ __device__ constexpr uint32_t idesc_f16(int n) { return (1u << 4) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(256 >> 4) << 24); }
 
 // packed fp32x2 arithmetic (sm_100): one instruction for two lanes of a register pair
 __device__ __forceinline__ uint64_t pack2(float lo, float hi) {
@@ -152,7 +153,11 @@ __device__ __forceinline__ void convert_item(uint8_t *slot, int t, int64_t row0,
 
 // STREAM = false: D <= 128, X tiles resident across neuron tiles, 4 converter + 8 epilogue warps.
 // STREAM = true : larger D, X tiles stream once per neuron tile, 8 converter + 4 epilogue warps.
-template <bool STREAM>
+// TBN = neuron-tile width: 256 (two accumulator stages in TMEM, the default) or 128 (four stages, so the MMAs of up
+// to three tiles queue while the epilogue drains one).  Measured on B200: the four-stage variant is 20-30 % SLOWER
+// (config 2: 0.44 vs 0.36 ms) -- the per-tile hand-off cost, not its latency, is what the short tiles pay for --
+// so it is kept only as the SOM_B200_TBN=128 experiment.
+template <bool STREAM, int TBN>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
@@ -177,9 +182,12 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     auto bfull_bar  = [&](int s) { return bar0 + 8u * (3 * NA + s); };            // leader: both W' halves landed
     auto bempty_bar = [&](int s) { return bar0 + 8u * (3 * NA + NB + s); };       // local: B slot consumed
     auto tfull_bar  = [&](int a) { return bar0 + 8u * (3 * NA + 2 * NB + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * NA + 2 * NB + 2 + a); };
-    auto bfullq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * NB + 4 + b); };
-    auto bemptyq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * NB + 6 + b); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * NA + 2 * NB + MAX_ACC + a); };
+    auto bfullq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * NB + 2 * MAX_ACC + b); };
+    auto bemptyq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * NB + 2 * MAX_ACC + 2 + b); };
+    constexpr int TBNH = TBN / 2;                            // this CTA's share of a neuron tile (B rows)
+    constexpr int NACC = 512 / TBN;                          // accumulator stages
+    constexpr uint32_t kIdescF16 = idesc_f16(TBN);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + NUM_BARS);
     __shared__ unsigned int last_cta;
 
@@ -201,10 +209,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 2 * nconv / 32); tc::mbar_init(aempty_bar(s), 1); }
         for (int s = 0; s < NB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
-        for (int a = 0; a < 2; ++a) {
-            tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * nepi / 32);
-            tc::mbar_init(bfullq_bar(a), 4); tc::mbar_init(bemptyq_bar(a), 4);
-        }
+        for (int a = 0; a < NACC; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * nepi / 32); }
+        for (int b = 0; b < 2; ++b) { tc::mbar_init(bfullq_bar(b), 4); tc::mbar_init(bemptyq_bar(b), 4); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
     }
@@ -226,9 +232,9 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         tc::mbar_wait(bempty_bar(s), ph ^ 1);
                         const uint32_t st = b_base + s * SLOT_BYTES;
                         if (tc::elect_one()) {
-                            if (leader) tc::mbar_expect_tx(bfull_bar(s), 2 * SLOT_BYTES);
-                            tma_load_2d_2sm(st,             &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
-                            tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                            if (leader) tc::mbar_expect_tx(bfull_bar(s), 4 * TBNH * 128);   // hi + lo of both CTAs
+                            tma_load_2d_2sm(st,             &map_whi, kb * BK, nt * TBN + (int)rank * TBNH, bfull_bar(s));
+                            tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nt * TBN + (int)rank * TBNH, bfull_bar(s));
                         }
                         __syncwarp();
                     }
@@ -260,9 +266,9 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             uint32_t it = 0, acc_it = 0, tile_it = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it)
                 for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
-                    const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
+                    const int a = acc_it % NACC; const uint32_t aph = (acc_it / NACC) & 1;
                     tc::dbg_stamp(probe, 0, acc_it);                 // MMA: starts waiting for the tile's inputs
-                    const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
+                    const uint32_t tmem_d = tmem_base + (uint32_t)(a * TBN);
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                         const uint32_t ia = resident ? (tile_it * (uint32_t)num_k_blocks + kb) : it;
                         const int sa = ia % NA; const uint32_t pha = (ia / NA) & 1;
@@ -326,7 +332,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         // streaming mode: 4 warps (8-11), all 256 columns each
         const int q = warp & 3;
         const int h = conv_extra ? 0 : (warp - EPI_WARP0) >> 2;
-        constexpr int ncols = conv_extra ? BN : BN / 2;
+        constexpr int ncols = conv_extra ? TBN : TBN / 2;
+        const bool ld_lane = lane < ncols / 4 || conv_extra;       // lanes that stage this warp's bias slice
         const int row_in_tile = q * 32 + lane;
         const float winv0 = __ldg(wsinv);                    // 2^-b of the uniform codebook scale
         // this warp's private shared-memory slice: ncols bias values, then ncols inverse scales
@@ -339,8 +346,11 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int64_t row = (int64_t)pair * (2 * BM) + (int64_t)rank * BM + row_in_tile;
             if (pair < num_pair_tiles && row < n) rs_next = __ldg(xscale + row);
         }
-        float4 nb = __ldg(reinterpret_cast<const float4 *>(bias + h * (BN / 2)) + lane);
-        float4 ns = __ldg(reinterpret_cast<const float4 *>(wsinv + h * (BN / 2)) + lane);
+        float4 nb = make_float4(0.f, 0.f, 0.f, 0.f), ns = nb;
+        if (ld_lane) {
+            nb = __ldg(reinterpret_cast<const float4 *>(bias + h * (TBN / 2)) + lane);
+            ns = __ldg(reinterpret_cast<const float4 *>(wsinv + h * (TBN / 2)) + lane);
+        }
         float4 nb2 = nb, ns2 = ns;                               // columns 128..255 (streaming mode only)
         if (conv_extra) {
             nb2 = __ldg(reinterpret_cast<const float4 *>(bias + 128) + lane);
@@ -357,20 +367,24 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const float rsg = rs / winv0;
             RunMinScaled rm; rm.reset();
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
-                const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
-                const int col0 = nt * BN + h * (BN / 2);
+                const int a = acc_it % NACC; const uint32_t aph = (acc_it / NACC) & 1;
+                const int col0 = nt * TBN + h * (TBN / 2);
                 __syncwarp();
-                reinterpret_cast<float4 *>(wb)[lane] = nb;
-                reinterpret_cast<float4 *>(wsv)[lane] = ns;
+                if (ld_lane) {
+                    reinterpret_cast<float4 *>(wb)[lane] = nb;
+                    reinterpret_cast<float4 *>(wsv)[lane] = ns;
+                }
                 if (conv_extra) {
                     reinterpret_cast<float4 *>(wb + 128)[lane] = nb2;
                     reinterpret_cast<float4 *>(wsv + 128)[lane] = ns2;
                 }
                 __syncwarp();
                 {   // prefetch the next neuron tile's slice (wraps to tile 0 for the next row tile)
-                    const int nn = (nt + 1 < num_n_tiles ? nt + 1 : 0) * BN + h * (BN / 2);
-                    nb = __ldg(reinterpret_cast<const float4 *>(bias + nn) + lane);
-                    ns = __ldg(reinterpret_cast<const float4 *>(wsinv + nn) + lane);
+                    const int nn = (nt + 1 < num_n_tiles ? nt + 1 : 0) * TBN + h * (TBN / 2);
+                    if (ld_lane) {
+                        nb = __ldg(reinterpret_cast<const float4 *>(bias + nn) + lane);
+                        ns = __ldg(reinterpret_cast<const float4 *>(wsinv + nn) + lane);
+                    }
                     if (conv_extra) {
                         nb2 = __ldg(reinterpret_cast<const float4 *>(bias + nn + 128) + lane);
                         ns2 = __ldg(reinterpret_cast<const float4 *>(wsinv + nn + 128) + lane);
@@ -380,7 +394,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 tc::mbar_wait(tfull_bar(a), aph);
                 tc::tc_fence_after();
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 5, acc_it);   // EPI: tile complete in TMEM
-                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TBN + h * (TBN / 2));
 #pragma unroll 1
                 for (int c = 0; c < ncols / 32; ++c) {
                     uint32_t v[32];
@@ -506,20 +520,24 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     SOM_REQUIRE(tc::shape_ok(X, n, d, ldx), SOM_E_SHAPE,
                 "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
     SOM_REQUIRE(xscale != nullptr, SOM_E_BADARG, "the fp16-split kernel needs the per-row scales (som_b200_prepare_samples)");
+    const int num_k_blocks = L.d_pad64 / BK;
+    const bool resident = num_k_blocks <= RESIDENT_MAX_KB;
+    int tbn = 256;      // SOM_B200_TBN=128: four-accumulator-stage experiment (resident mode only; slower, see above)
+    { const char *e = getenv("SOM_B200_TBN"); if (e && resident && atoi(e) == 128) tbn = 128; }
     CUtensorMap mx, mhi, mlo;
     int rc;
     if ((rc = tc::make_map_2d(&mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)ldx * 4, 32, BM))) return rc;
-    if ((rc = make_map_2d_f16(&mhi, ws + L.w16hi_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, BNH))) return rc;
-    if ((rc = make_map_2d_f16(&mlo, ws + L.w16lo_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, BNH))) return rc;
+    if ((rc = make_map_2d_f16(&mhi, ws + L.w16hi_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, tbn / 2))) return rc;
+    if ((rc = make_map_2d_f16(&mlo, ws + L.w16lo_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, tbn / 2))) return rc;
     static bool attr_set = false;
     if (!attr_set) {
-        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attr_set = true;
     }
     const int num_pair_tiles = (int)ceil_div(n, 2 * BM);
-    const int num_n_tiles = L.k_pad / BN;
-    const int num_k_blocks = L.d_pad64 / BK;
+    const int num_n_tiles = L.k_pad / tbn;
     int pairs = sm_count / 2;
     if (pairs > num_pair_tiles) pairs = num_pair_tiles;
     if (pairs < 1) pairs = 1;
@@ -529,15 +547,18 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
     { const char *e = getenv("SOM_B200_DBG"); acc.dbg = e ? atoi(e) : 0; }
-    if (num_k_blocks <= RESIDENT_MAX_KB) {
-        bmu_tc3_kernel<false><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
-        mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off), reinterpret_cast<const float *>(ws + L.wsinv_off),
-        reinterpret_cast<const unsigned int *>(ws + L.gstat_off), xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
-    } else {
-        bmu_tc3_kernel<true><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
-        mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off), reinterpret_cast<const float *>(ws + L.wsinv_off),
-        reinterpret_cast<const unsigned int *>(ws + L.gstat_off), xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
-    }
+    const float *bias_p = reinterpret_cast<const float *>(ws + L.bias_off);
+    const float *wsinv_p = reinterpret_cast<const float *>(ws + L.wsinv_off);
+    const unsigned int *gstat_p = reinterpret_cast<const unsigned int *>(ws + L.gstat_off);
+    if (resident && tbn == 128)
+        bmu_tc3_kernel<false, 128><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
+            mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+    else if (resident)
+        bmu_tc3_kernel<false, 256><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
+            mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+    else
+        bmu_tc3_kernel<true, 256><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
+            mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
     return check_cuda(cudaGetLastError(), "bmu_tc3_kernel launch");
 }
 
