@@ -26,7 +26,11 @@ def eng():
 
 def _gpu_bmu(eng, x, w, dist, p, algo):
     from xpysom_dask_b200 import _lib
-    xd = torch.from_numpy(x).cuda()
+    n, d = x.shape
+    ld = (d + 3) // 4 * 4                      # TMA needs a 16-byte row stride (the host class pads the same way)
+    buf = torch.full((n, ld), 7.0, dtype=torch.float32, device="cuda")     # garbage in the padding on purpose
+    buf[:, :d] = torch.from_numpy(x).cuda()
+    xd = buf[:, :d]
     wd = torch.from_numpy(np.ascontiguousarray(w.reshape(-1, w.shape[-1]), dtype=np.float32)).cuda()
     ws = eng.workspace(0, wd.shape[0], wd.shape[1])
     eng.prepare_codebook(wd, _lib.DIST[dist], p, ws)
@@ -59,6 +63,22 @@ def test_bmu_contraction_distances(eng, n, d, gx, gy, dist, algo):
     r = U.bmu_parity(spec, x, w, bmu)
     print("\n[bmu %s/%s n=%d d=%d K=%d] near-tie rate %.2e, raw mismatch %.2e, worst mismatching rel gap %.2e"
           % (dist, algo, n, d, gx * gy, r["near_tie_rate"], r["mismatch_rate"], r["worst_rel_gap"]))
+    assert r["bad"] == 0, r
+
+
+# feature counts around the edges of the tensor-core K blocks: the TF32 kernel folds the bias into columns
+# d..d+2 of the last 32-feature block when it has 3 spare columns (29: yes, crossing a 16-byte chunk; 30: no;
+# 33 / 61: fold in a second block), both kernels skip the 8 / 16-column MMA steps that hold only padding
+@pytest.mark.parametrize("d", [5, 8, 13, 17, 29, 30, 31, 33, 47, 61, 62, 65, 129])
+@pytest.mark.parametrize("dist", ["euclidean", "cosine"])
+@pytest.mark.parametrize("algo", ["tc", "tc16"])
+def test_bmu_tensor_core_block_edges(eng, d, dist, algo):
+    n, gx, gy = 1777, 19, 15                     # K = 285: one full and one ragged 256-neuron tile
+    x = U.blobs(n, d, seed=3 * d)
+    spec = so.SomSpec(gx=gx, gy=gy, dim=d, activation_distance=dist, random_seed=d)
+    w = so.init_weights(spec).astype(np.float32) * 0.5 + 0.5 * U.uniform(gx * gy, d, 7).reshape(gx, gy, d)
+    bmu = _gpu_bmu(eng, x, w, dist, 2.0, algo)
+    r = U.bmu_parity(spec, x, w, bmu)
     assert r["bad"] == 0, r
 
 

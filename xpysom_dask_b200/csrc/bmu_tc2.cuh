@@ -119,6 +119,7 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
                const unsigned int *__restrict__ gstat, int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
                int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
+    pdl_wait(); pdl_trigger();        // programmatic dependent launch (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -427,10 +428,10 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
     { const char *e = getenv("SOM_B200_DBG"); acc.dbg = e ? atoi(e) : 0; }
-    bmu_tc2_kernel<<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(mx, mhi, mlo, reinterpret_cast<const float *>(ws + L.bias_off),
-                                                               reinterpret_cast<const unsigned int *>(ws + L.gstat_off),
-                                                               n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
-    return check_cuda(cudaGetLastError(), "bmu_tc2_kernel launch");
+    return check_cuda(launch_pdl(bmu_tc2_kernel, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, st, mx, mhi, mlo,
+                                 reinterpret_cast<const float *>(ws + L.bias_off),
+                                 reinterpret_cast<const unsigned int *>(ws + L.gstat_off), n, num_pair_tiles, num_n_tiles,
+                                 num_k_blocks, bmu, best, acc), "bmu_tc2_kernel launch");
 }
 
 }  // namespace tc2

@@ -164,6 +164,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                const float *__restrict__ wsinv, const unsigned int *__restrict__ gstat,
                const float *__restrict__ xscale, int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
                int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
+    pdl_wait(); pdl_trigger();        // programmatic dependent launch (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -550,16 +551,18 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     const float *bias_p = reinterpret_cast<const float *>(ws + L.bias_off);
     const float *wsinv_p = reinterpret_cast<const float *>(ws + L.wsinv_off);
     const unsigned int *gstat_p = reinterpret_cast<const unsigned int *>(ws + L.gstat_off);
+    const dim3 grid(2 * pairs), block(NUM_THREADS);
+    cudaError_t e;
     if (resident && tbn == 128)
-        bmu_tc3_kernel<false, 128><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
-            mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+        e = launch_pdl(bmu_tc3_kernel<false, 128>, grid, block, SMEM_BYTES, st, mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n,
+                       num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
     else if (resident)
-        bmu_tc3_kernel<false, 256><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
-            mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+        e = launch_pdl(bmu_tc3_kernel<false, 256>, grid, block, SMEM_BYTES, st, mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n,
+                       num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
     else
-        bmu_tc3_kernel<true, 256><<<2 * pairs, NUM_THREADS, SMEM_BYTES, st>>>(
-            mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n, num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
-    return check_cuda(cudaGetLastError(), "bmu_tc3_kernel launch");
+        e = launch_pdl(bmu_tc3_kernel<true, 256>, grid, block, SMEM_BYTES, st, mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n,
+                       num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+    return check_cuda(e, "bmu_tc3_kernel launch");
 }
 
 }  // namespace tc3

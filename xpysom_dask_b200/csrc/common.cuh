@@ -106,4 +106,25 @@ __device__ __forceinline__ void argmin_merge(float &v, int &i, float ov, int oi)
     if (ov < v || (ov == v && oi < i)) { v = ov; i = oi; }
 }
 
+
+// ---- programmatic dependent launch -------------------------------------------------------------------
+// The epoch is a serial chain of short kernels around the BMU kernel (stats -> split -> BMU -> tables -> apply ->
+// merge); launched with the programmatic-stream-serialization attribute, each one is made resident while its
+// predecessor is still running and blocks in pdl_wait() until that grid has completed and flushed, which hides
+// the launch latency between them (~6 us per boundary at config 2).  Every kernel launched through launch_pdl
+// MUST call pdl_wait() before its first global-memory access.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 }  // namespace somb200

@@ -28,6 +28,7 @@ __device__ __forceinline__ float codebook_row_scale(int dist_kind, double s) {
 __global__ void codebook_stats_kernel(const float *__restrict__ W, int k, int d, int dist_kind, int k_pad,
                                       float *__restrict__ aux, float *__restrict__ bias, float *__restrict__ amax,
                                       unsigned int *__restrict__ gstat) {
+    pdl_wait(); pdl_trigger();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= k_pad) return;
@@ -67,6 +68,7 @@ __global__ void codebook_split_kernel(const float *__restrict__ W, int k, int d,
                                       __half *__restrict__ w16hi, __half *__restrict__ w16lo, float *__restrict__ wsinv,
                                       const float *__restrict__ aux, const float *__restrict__ bias,
                                       const float *__restrict__ amax, unsigned int *__restrict__ gstat) {
+    pdl_wait(); pdl_trigger();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const int lane = threadIdx.x & 31;
     if (warp >= k_pad) return;
@@ -151,6 +153,7 @@ row_scale_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, flo
 // M: W <- den != 0 ? num/den : W      (xpysom.py:451-455)
 __global__ void merge_kernel(float *__restrict__ W, const float *__restrict__ num, const float *__restrict__ den,
                              int k, int d) {
+    pdl_wait(); pdl_trigger();
     const int64_t tot = (int64_t)k * d;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
         const float dn = __ldg(den + e / d);

@@ -49,6 +49,7 @@ __host__ __device__ inline int hex_shift(int j, int gy) { return ((gy - 1 - j) &
 __global__ void neigh_tables_kernel(int gx, int gy, int kind, int compact, int shifted,
                                     double sigma, double dd, float *tx, float *ty, float *mx, float *my,
                                     const double *sched, const int *epoch, double std_coeff) {
+    pdl_wait(); pdl_trigger();
     if (sched != nullptr) {          // schedule read on the device (graph replay)
         sigma = sched[2 * (*epoch)];
         dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
@@ -106,6 +107,7 @@ constexpr int NB_M = 64, NB_N = 64, NB_K = 16, NB_THREADS = 256;
 __global__ void __launch_bounds__(NB_THREADS)
 neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__restrict__ c,
                    float *__restrict__ num, float *__restrict__ den, int b_per_slice) {
+    pdl_wait(); pdl_trigger();
     __shared__ __align__(16) float Hs[NB_K][NB_M + 4];
     __shared__ __align__(16) float Ss[NB_K][NB_N + 4];
     __shared__ float cs[NB_K];
@@ -202,6 +204,7 @@ constexpr int AX_THREADS = 128, AX_J = 16;
 __global__ void __launch_bounds__(AX_THREADS)
 axis_contract_kernel(const float *__restrict__ in, const float *__restrict__ M, int ldm, int A, int B, int J, int64_t C,
                      float scale, const double *__restrict__ sched, const int *__restrict__ epoch, float *__restrict__ out) {
+    pdl_wait(); pdl_trigger();
     if (sched != nullptr) scale = (float)sched[2 * (*epoch) + 1];      // eta of the current epoch (graph replay)
     extern __shared__ float Ms[];                         // [B][AX_J] slice of M for this block's j range
     const int a = blockIdx.z, j0 = blockIdx.y * AX_J;
@@ -238,8 +241,8 @@ inline int launch_axis_contract(const float *in, const float *M, int ldm, int A,
                                 const double *sched, const int *epoch, float *out, cudaStream_t st) {
     dim3 grid((unsigned)ceil_div(C, AX_THREADS), (unsigned)ceil_div(J, AX_J), (unsigned)A);
     const size_t smem = (size_t)B * AX_J * sizeof(float);
-    axis_contract_kernel<<<grid, AX_THREADS, smem, st>>>(in, M, ldm, A, B, J, C, scale, sched, epoch, out);
-    return check_cuda(cudaGetLastError(), "axis_contract_kernel launch");
+    return check_cuda(launch_pdl(axis_contract_kernel, grid, dim3(AX_THREADS), smem, st, in, M, ldm, A, B, J, C, scale, sched,
+                                 epoch, out), "axis_contract_kernel launch");
 }
 
 // scratch (floats) after the factor tables: the (gx, gy, D) and (gx, gy) intermediates of the separable path
@@ -272,9 +275,9 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
     float *tx = tables, *ty = tx + nxe, *mx = ty + nye, *my = mx + nxe;
     P.tx = tx; P.ty = ty; P.mx = mx; P.my = my;
     const int tot = (int)(nxe + nye);
-    neigh_tables_kernel<<<(tot + 255) / 256, 256, 0, st>>>(gx, gy, kind, P.compact, P.shifted, sigma, dd, tx, ty, mx, my,
-                                                           sched, epoch, std_coeff);
-    int rc = check_cuda(cudaGetLastError(), "neigh_tables_kernel launch");
+    int rc = check_cuda(launch_pdl(neigh_tables_kernel, dim3((tot + 255) / 256), dim3(256), 0, st, gx, gy, kind, P.compact,
+                                   P.shifted, sigma, dd, tx, ty, mx, my, sched, epoch, std_coeff),
+                        "neigh_tables_kernel launch");
     if (rc) return rc;
     const int K = gx * gy;
     if (scratch != nullptr && neigh_is_separable(topology, kind, gx, gy)) {
@@ -304,8 +307,8 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
         if (rc) return rc;
     }
     dim3 grid((unsigned)ceil_div(K, NB_M), (unsigned)ceil_div(d, NB_N), (unsigned)slices);
-    neigh_apply_kernel<<<grid, NB_THREADS, 0, st>>>(P, S, c, num, den, b_per_slice);
-    return check_cuda(cudaGetLastError(), "neigh_apply_kernel launch");
+    return check_cuda(launch_pdl(neigh_apply_kernel, grid, dim3(NB_THREADS), 0, st, P, S, c, num, den, b_per_slice),
+                      "neigh_apply_kernel launch");
 }
 
 }  // namespace somb200

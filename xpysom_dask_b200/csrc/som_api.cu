@@ -128,16 +128,17 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
     const int blocks = (int)ceil_div(L.k_pad, warps_per_block);
     float *aux = reinterpret_cast<float *>(ws + L.aux_off), *amax = reinterpret_cast<float *>(ws + L.amax_off);
     unsigned int *gstat = reinterpret_cast<unsigned int *>(ws + L.gstat_off);
-    codebook_stats_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
-        w_dev, k, d, dist_kind, L.k_pad, aux, reinterpret_cast<float *>(ws + L.bias_off), amax, gstat);
-    int rc = check_cuda(cudaGetLastError(), "codebook_stats_kernel launch");
+    int rc = check_cuda(launch_pdl(codebook_stats_kernel, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, w_dev, k, d,
+                                   dist_kind, L.k_pad, aux, reinterpret_cast<float *>(ws + L.bias_off), amax, gstat),
+                        "codebook_stats_kernel launch");
     if (rc || !split) return rc;
-    codebook_split_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
-        w_dev, k, d, dist_kind, L.k_pad, L.d_pad, reinterpret_cast<float *>(ws + L.whi_off),
-        reinterpret_cast<float *>(ws + L.wlo_off), L.d_pad64, reinterpret_cast<__half *>(ws + L.w16hi_off),
-        reinterpret_cast<__half *>(ws + L.w16lo_off), reinterpret_cast<float *>(ws + L.wsinv_off), aux,
-        reinterpret_cast<const float *>(ws + L.bias_off), amax, gstat);
-    return check_cuda(cudaGetLastError(), "codebook_split_kernel launch");
+    return check_cuda(launch_pdl(codebook_split_kernel, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, w_dev, k, d,
+                                 dist_kind, L.k_pad, L.d_pad, reinterpret_cast<float *>(ws + L.whi_off),
+                                 reinterpret_cast<float *>(ws + L.wlo_off), L.d_pad64,
+                                 reinterpret_cast<__half *>(ws + L.w16hi_off), reinterpret_cast<__half *>(ws + L.w16lo_off),
+                                 reinterpret_cast<float *>(ws + L.wsinv_off), aux,
+                                 reinterpret_cast<const float *>(ws + L.bias_off), amax, gstat),
+                      "codebook_split_kernel launch");
 }
 
 int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, void *stream) {
@@ -309,7 +310,7 @@ int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev, int
     const int64_t tot = (int64_t)k * d;
     int blocks = (int)ceil_div(tot, 256);
     if (blocks > 148 * 16) blocks = 148 * 16;
-    merge_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(w_dev, num_dev, den_dev, k, d);
+    SOM_CUDA(launch_pdl(merge_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, w_dev, num_dev, den_dev, k, d));
     return check_cuda(cudaGetLastError(), "merge_kernel launch");
 }
 
