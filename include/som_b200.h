@@ -162,6 +162,20 @@ int som_b200_epoch_advance(int *epoch_dev, void *stream);
 int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev,
                    int k, int d, void *stream);
 
+/* ---- sharded path: the one exchange step -------------------------------------------------------
+ * The reference sums the per-block partial updates with Dask (`sum(...)` over the delayed `_update`
+ * results, xpysom.py:574-583).  With one process per GPU that sum is ONE all-reduce of [S | c]
+ * (K*D + K floats) per epoch.  For the small buffers of most maps an NCCL all-reduce is pure latency,
+ * so the library offers a one-shot all-reduce over NVLink peer memory (single node, CUDA IPC):
+ * every rank creates a communicator, the 64-byte handles are exchanged by the host (any transport),
+ * every rank connects, and from then on som_b200_peer_allreduce sums `floats` values in place on the
+ * caller's stream, in rank order (bitwise identical on all ranks).  Larger buffers / several nodes:
+ * keep using NCCL. */
+int som_b200_peer_create(int64_t max_floats, int world, int rank, void **comm_out, void *handle_out_64_bytes);
+int som_b200_peer_connect(void *comm, const void *all_handles_world_x_64_bytes);
+int som_b200_peer_allreduce(void *comm, float *data_dev, int64_t floats, void *stream);
+int som_b200_peer_destroy(void *comm);
+
 /* quantization / quantization_error support (xpysom.py:620-707): for each row,
  * q_dev (n,D) <- W[bmu[r]] if q_dev != NULL, and err_dev (n) <- ||x_r - W[bmu[r]]||_2
  * if err_dev != NULL. */

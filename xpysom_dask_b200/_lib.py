@@ -48,6 +48,11 @@ SIGNATURES = {
                                                   ctypes.c_void_p]),
     "som_b200_epoch_advance": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "som_b200_merge": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "som_b200_peer_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                            ctypes.c_void_p]),
+    "som_b200_peer_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
+    "som_b200_peer_allreduce": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "som_b200_peer_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "som_b200_quantize": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int,
                                          c_i32p, c_f32p, c_f32p, ctypes.c_void_p]),
     "som_b200_distance_map": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,

@@ -13,6 +13,7 @@
 #include "bmu_tc3.cuh"
 #include "accumulate.cuh"
 #include "neigh.cuh"
+#include "peer.cuh"
 #include "misc.cuh"
 
 namespace somb200 {
@@ -313,6 +314,23 @@ int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev, int
     SOM_CUDA(launch_pdl(merge_kernel, dim3(blocks), dim3(256), 0, (cudaStream_t)stream, w_dev, num_dev, den_dev, k, d));
     return check_cuda(cudaGetLastError(), "merge_kernel launch");
 }
+
+int som_b200_peer_create(int64_t max_floats, int world, int rank, void **comm_out, void *handle_out_64_bytes) {
+    PeerComm *c = nullptr;
+    const int rc = peer_create(max_floats, world, rank, &c, handle_out_64_bytes);
+    if (rc == 0) *comm_out = c;
+    return rc;
+}
+
+int som_b200_peer_connect(void *comm, const void *all_handles) {
+    return peer_connect(static_cast<PeerComm *>(comm), all_handles);
+}
+
+int som_b200_peer_allreduce(void *comm, float *data_dev, int64_t floats, void *stream) {
+    return peer_allreduce(static_cast<PeerComm *>(comm), data_dev, floats, (cudaStream_t)stream);
+}
+
+int som_b200_peer_destroy(void *comm) { return peer_destroy(static_cast<PeerComm *>(comm)); }
 
 int som_b200_quantize(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k,
                       const int32_t *bmu_dev, float *q_dev, float *err_dev, void *stream) {
