@@ -172,9 +172,9 @@ def run_gpu(args, wl, rank, world, local_rank):
     # ---- device-resident throughput: K epochs in ONE train() call ------------------------
     som.train(x_dev, TOTAL_EPOCHS, iter_beg=0, iter_end=args.warmup)             # warm-up epochs
     sampler = ClockSampler(local_rank)
-    barrier()
     if rank == 0:
-        sampler.start()
+        sampler.start()       # BEFORE the barrier: spawning nvidia-smi takes ~1 ms, which the other ranks would
+    barrier()                 # otherwise spend waiting for rank 0 inside their first all-reduce of the timed region
     launches0 = eng.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()

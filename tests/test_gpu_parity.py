@@ -363,6 +363,31 @@ def test_cuda_graph_replay_matches_eager_launches():
         assert U.codebook_rel_err(a2._weights, a._weights) < 1e-6
 
 
+def test_row_scales_cached_per_device_tensor_and_refreshed_on_in_place_change():
+    """The per-row power-of-two scales are computed once per uploaded / caller-owned device tensor, not per
+    train() call; an in-place change of the tensor (torch's version counter) must recompute them."""
+    from xpysom_dask_b200 import XPySom
+    x = torch.rand(6000, 48, device="cuda")
+    som = XPySom(6, 6, 48, sigma=1.5, random_seed=1)
+    eng = som._get_engine()
+    calls = []
+    orig = eng.prepare_samples
+    eng.prepare_samples = lambda *a, **k: (calls.append(1), orig(*a, **k))[1]
+    som.train(x, 4, iter_beg=0, iter_end=2)
+    som.train(x, 4, iter_beg=2, iter_end=3)
+    assert len(calls) == 1
+    x.mul_(1024.0)                                   # same storage, new contents: stale scales would overflow fp16
+    w_before = som._weights.copy()
+    som.train(x, 4, iter_beg=3, iter_end=4)
+    assert len(calls) == 2
+    ref = XPySom(6, 6, 48, sigma=1.5, random_seed=1)
+    ref._weights = w_before.copy()
+    ref.train(x.clone(), 4, iter_beg=3, iter_end=4)
+    assert U.codebook_rel_err(som._weights, ref._weights) < 1e-5
+    som.train(x.cpu().numpy(), 4, iter_beg=3, iter_end=4)      # host input: a fresh upload every call
+    assert len(calls) == 3
+
+
 def test_activate_distance_from_weights_topographic_error():
     """tests.py:66-90 of the reference and its own outputs on seeded maps (golden api.npz)."""
     from xpysom_dask_b200 import XPySom

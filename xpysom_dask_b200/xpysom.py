@@ -23,6 +23,7 @@ from collections import Counter, defaultdict
 from warnings import warn
 
 import os
+import weakref
 
 import numpy as np
 import torch
@@ -276,7 +277,15 @@ class XPySom:
         if not self._wants_xscale(dist_kind):
             xscale = None
         elif chunks is None:
-            xscale = eng.prepare_samples(x)
+            # a device tensor that has not been written since the last call keeps its scales (one pass over the
+            # samples per upload, not per train() call); torch's version counter catches in-place changes
+            # (the cache holds a weak reference: a freed tensor whose address is reused cannot hit it)
+            cached = getattr(self, '_xscale_cache', None)
+            if cached is not None and cached[0]() is x and cached[1] == x._version:
+                xscale = cached[2]
+            else:
+                xscale = eng.prepare_samples(x)
+                self._xscale_cache = (weakref.ref(x), x._version, xscale) if x is data else None
         else:
             xscale = eng.empty(n)                  # filled chunk by chunk during the first epoch
         tables = eng.neigh_tables(gx, gy, d)
@@ -531,6 +540,7 @@ class XPySom:
         state['_engine'] = None            # device handles are rebuilt on demand
         state['_process_group'] = None
         state.pop('_peer_cache', None)
+        state.pop('_xscale_cache', None)
         state['_profile_events'] = []
         state['xp'] = None
         return state
