@@ -221,6 +221,32 @@ def test_neigh_apply_large_map_separable_path(eng, fn, compact, topology):
         assert e1 < 1e-5 and e2 < 1e-5, (fn, compact, topology, sigma, e1, e2)
 
 
+@pytest.mark.parametrize("fn,compact,topology", [("mexican_hat", False, "hexagonal"), ("mexican_hat", True, "hexagonal"),
+                                                 ("gaussian", True, "hexagonal"), ("bubble", False, "rectangular")])
+def test_neigh_apply_wide_tile_variant(eng, fn, compact, topology):
+    """More than 64 features on maps of >= 512 neurons run the 128 x 128-tile instantiation of the direct kernel
+    (8 x 8 outputs per thread); ragged K and D, empty BMUs, sliced reduction (atomics) included."""
+    from xpysom_dask_b200 import _lib
+    gx, gy, d = 27, 23, 100                      # K = 621: 4 full + 1 ragged 128-neuron tile, d = 100 of 128
+    K = gx * gy
+    rng = np.random.RandomState(5)
+    S = rng.randn(K, d).astype(np.float32)
+    c = rng.randint(0, 9, size=K).astype(np.float32)
+    S[c == 0] = 0
+    spec = so.SomSpec(gx=gx, gy=gy, dim=d, sigma=1.0, neighborhood_function=fn, topology=topology, compact_support=compact)
+    for sigma in (5.1, 0.9):
+        H = so.neighborhood_table(spec, sigma).astype(np.float64)
+        Sd, cd = torch.from_numpy(S).cuda(), torch.from_numpy(c).cuda()
+        num, den = eng.empty(K, d), eng.empty(K)
+        eng.neigh_apply(Sd, cd, gx, gy, d, _lib.TOPO[topology], _lib.NEIGH[fn], sigma, 0.5, 0.5, compact, num, den,
+                        eng.neigh_tables(gx, gy, d))
+        torch.cuda.synchronize()
+        num_ref, den_ref = 0.5 * H.T @ S.astype(np.float64), 0.5 * H.T @ c.astype(np.float64)
+        e1 = np.abs(num.cpu().numpy() - num_ref).max() / np.abs(num_ref).max()
+        e2 = np.abs(den.cpu().numpy() - den_ref).max() / np.abs(den_ref).max()
+        assert e1 < 1e-5 and e2 < 1e-5, (fn, compact, topology, sigma, e1, e2)
+
+
 def test_neigh_apply_skips_empty_bmus(eng):
     case = dict(gx=6, gy=5, topology="rectangular", fn="gaussian", compact=False)
     S = np.zeros((30, 4), np.float32); c = np.zeros(30, np.float32)

@@ -102,86 +102,107 @@ __device__ __forceinline__ float neigh_eval(const NeighParams &P, float inv_d, f
     return expf(-p * inv_d) * (1.f - two_over_d * p);
 }
 
-constexpr int NB_M = 64, NB_N = 64, NB_K = 16, NB_THREADS = 256;
+// Tile = (16 RM) neurons x (16 RN) features per CTA of 256 threads, RM x RN outputs per thread, 16 BMUs per step.
+// <4, 4> (64 x 64) keeps small maps / few features busy; <8, 8> (128 x 128) has 4x the FMAs per H evaluation and
+// per shared-memory byte, which is what the non-separable maps with many features need (config 5: hexagonal
+// mexican hat, K = 2500, D = 128: 2 K^2 D = 1.6 GFLOP per epoch).
+constexpr int NB_K = 16, NB_THREADS = 256;
 
+template <int RM, int RN>
 __global__ void __launch_bounds__(NB_THREADS)
 neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__restrict__ c,
                    float *__restrict__ num, float *__restrict__ den, int b_per_slice) {
     pdl_wait(); pdl_trigger();
-    __shared__ __align__(16) float Hs[NB_K][NB_M + 4];
-    __shared__ __align__(16) float Ss[NB_K][NB_N + 4];
+    constexpr int TM = 16 * RM, TN = 16 * RN;
+    __shared__ __align__(16) float Hs[NB_K][TM + 4];
+    __shared__ __align__(16) float Ss[NB_K][TN + 4];
     __shared__ float cs[NB_K];
     const int K = P.gx * P.gy, D = P.d;
     float inv_d, two_over_d, eta;
     neigh_resolve(P, inv_d, two_over_d, eta);
-    const int k0 = blockIdx.x * NB_M, n0 = blockIdx.y * NB_N;
+    const int k0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 
-    // this thread generates H entries for b = b0 + (tid >> 4), k = k0 + (tid & 15) * 4 + {0..3}
-    const int hb = tid >> 4, hk = (tid & 15) * 4;
-    int ki[4], kj[4];
+    // this thread generates H entries for b = b0 + (tid >> 4), k = k0 + (tid & 15) * RM + {0..RM-1}
+    const int hb = tid >> 4, hk = (tid & 15) * RM, hn = (tid & 15) * RN;
+    int ki[RM], kj[RM];
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
+    for (int e = 0; e < RM; ++e) {
         int kk = k0 + hk + e; if (kk >= K) kk = K - 1;
         ki[e] = kk / P.gy; kj[e] = kk % P.gy;
     }
-    // and loads S entries for b = b0 + (tid >> 4), cols n0 + (tid & 15) * 4 + {0..3}
-    float acc[4][4];
+    // and loads S entries for b = b0 + (tid >> 4), cols n0 + (tid & 15) * RN + {0..RN-1}
+    float acc[RM][RN];
 #pragma unroll
-    for (int a = 0; a < 4; ++a)
+    for (int a = 0; a < RM; ++a)
 #pragma unroll
-        for (int b = 0; b < 4; ++b) acc[a][b] = 0.f;
-    float dacc[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int b = 0; b < RN; ++b) acc[a][b] = 0.f;
+    float dacc[RM];
+#pragma unroll
+    for (int a = 0; a < RM; ++a) dacc[a] = 0.f;
 
     // gridDim.z slices the reduction over BMUs so that small maps still fill the GPU
     const int b_begin = blockIdx.z * b_per_slice;
     const int b_end = min(K, b_begin + b_per_slice);
     for (int b0 = b_begin; b0 < b_end; b0 += NB_K) {
         const int b = b0 + hb;
-        float h4[4] = {0.f, 0.f, 0.f, 0.f}, s4[4] = {0.f, 0.f, 0.f, 0.f};
+        float hv[RM], sv[RN];
+#pragma unroll
+        for (int e = 0; e < RM; ++e) hv[e] = 0.f;
+#pragma unroll
+        for (int e = 0; e < RN; ++e) sv[e] = 0.f;
         float cb = 0.f;
         if (b < b_end) {
             cb = __ldg(c + b);
             if (cb != 0.f) {   // an empty BMU contributes nothing (S[b] = 0 as well)
                 const int bi = b / P.gy, bj = b % P.gy;
 #pragma unroll
-                for (int e = 0; e < 4; ++e) h4[e] = neigh_eval(P, inv_d, two_over_d, bi, bj, ki[e], kj[e]);
+                for (int e = 0; e < RM; ++e) hv[e] = neigh_eval(P, inv_d, two_over_d, bi, bj, ki[e], kj[e]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int col = n0 + hk + e;
-                    s4[e] = col < D ? __ldg(S + (int64_t)b * D + col) : 0.f;
+                for (int e = 0; e < RN; ++e) {
+                    const int col = n0 + hn + e;
+                    sv[e] = col < D ? __ldg(S + (int64_t)b * D + col) : 0.f;
                 }
             }
         }
         __syncthreads();
 #pragma unroll
-        for (int e = 0; e < 4; ++e) { Hs[hb][hk + e] = h4[e]; Ss[hb][hk + e] = s4[e]; }
+        for (int e = 0; e < RM; ++e) Hs[hb][hk + e] = hv[e];
+#pragma unroll
+        for (int e = 0; e < RN; ++e) Ss[hb][hn + e] = sv[e];
         if (hk == 0) cs[hb] = cb;
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < NB_K; ++kk) {
-            const float4 hv = *reinterpret_cast<const float4 *>(&Hs[kk][ty * 4]);
-            const float4 sv = *reinterpret_cast<const float4 *>(&Ss[kk][tx * 4]);
-            const float h[4] = {hv.x, hv.y, hv.z, hv.w};
-            const float s[4] = {sv.x, sv.y, sv.z, sv.w};
+            float h[RM], s[RN];
 #pragma unroll
-            for (int a = 0; a < 4; ++a)
+            for (int a = 0; a < RM; a += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(&Hs[kk][ty * RM + a]);
+                h[a] = v.x; h[a + 1] = v.y; h[a + 2] = v.z; h[a + 3] = v.w;
+            }
 #pragma unroll
-                for (int bb = 0; bb < 4; ++bb) acc[a][bb] = fmaf(h[a], s[bb], acc[a][bb]);
+            for (int bb = 0; bb < RN; bb += 4) {
+                const float4 v = *reinterpret_cast<const float4 *>(&Ss[kk][tx * RN + bb]);
+                s[bb] = v.x; s[bb + 1] = v.y; s[bb + 2] = v.z; s[bb + 3] = v.w;
+            }
+#pragma unroll
+            for (int a = 0; a < RM; ++a)
+#pragma unroll
+                for (int bb = 0; bb < RN; ++bb) acc[a][bb] = fmaf(h[a], s[bb], acc[a][bb]);
             if (tx == 0) {
                 const float cv = cs[kk];
 #pragma unroll
-                for (int a = 0; a < 4; ++a) dacc[a] = fmaf(h[a], cv, dacc[a]);
+                for (int a = 0; a < RM; ++a) dacc[a] = fmaf(h[a], cv, dacc[a]);
             }
         }
     }
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int kk = k0 + ty * 4 + a;
+    for (int a = 0; a < RM; ++a) {
+        const int kk = k0 + ty * RM + a;
         if (kk >= K) continue;
 #pragma unroll
-        for (int bb = 0; bb < 4; ++bb) {
-            const int col = n0 + tx * 4 + bb;
+        for (int bb = 0; bb < RN; ++bb) {
+            const int col = n0 + tx * RN + bb;
             if (col < D) {                                                    // g = h * eta (xpysom.py:434)
                 if (gridDim.z == 1) num[(int64_t)kk * D + col] = acc[a][bb] * eta;
                 else                atomicAdd(num + (int64_t)kk * D + col, acc[a][bb] * eta);
@@ -291,7 +312,9 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
         if ((rc = launch_axis_contract(T, TX, gx, 1, gx, gx, (int64_t)gy * d, P.eta, sched, epoch, num, st))) return rc;
         return launch_axis_contract(Tc, TX, gx, 1, gx, gx, gy, P.eta, sched, epoch, den, st);
     }
-    const int gxy = (int)(ceil_div(K, NB_M) * ceil_div(d, NB_N));
+    const bool big = d > 64 && K >= 512;                         // 128 x 128 tiles, 8 x 8 per thread
+    const int tm = big ? 128 : 64, tn = big ? 128 : 64;
+    const int gxy = (int)(ceil_div(K, tm) * ceil_div(d, tn));
     int slices = (2 * sm_count + gxy - 1) / gxy;                 // aim for >= 2 CTAs per SM
     const int max_slices = (int)ceil_div(K, 4 * NB_K);           // at least 64 BMUs per slice
     if (slices > max_slices) slices = max_slices;
@@ -306,9 +329,12 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
         rc = check_cuda(cudaMemsetAsync(den, 0, (size_t)K * sizeof(float), st), "memset den");
         if (rc) return rc;
     }
-    dim3 grid((unsigned)ceil_div(K, NB_M), (unsigned)ceil_div(d, NB_N), (unsigned)slices);
-    return check_cuda(launch_pdl(neigh_apply_kernel, grid, dim3(NB_THREADS), 0, st, P, S, c, num, den, b_per_slice),
-                      "neigh_apply_kernel launch");
+    dim3 grid((unsigned)ceil_div(K, tm), (unsigned)ceil_div(d, tn), (unsigned)slices);
+    if (big)
+        return check_cuda(launch_pdl(neigh_apply_kernel<8, 8>, grid, dim3(NB_THREADS), 0, st, P, S, c, num, den, b_per_slice),
+                          "neigh_apply_kernel<8,8> launch");
+    return check_cuda(launch_pdl(neigh_apply_kernel<4, 4>, grid, dim3(NB_THREADS), 0, st, P, S, c, num, den, b_per_slice),
+                      "neigh_apply_kernel<4,4> launch");
 }
 
 }  // namespace somb200
