@@ -14,7 +14,13 @@
 //     both CTAs at once;
 //   * four extra "scatter" warps per CTA take the finished BMUs of a 128-row tile and issue the
 //     S[bmu] += x reductions (red.global.add.v4.f32), so the ~1 element/clk/SM RED throughput
-//     overlaps with the MMA and the argmin epilogue instead of stalling them.
+//     overlaps with the MMA and the argmin epilogue instead of stalling them;
+//   * the bias is folded into the contraction when the last 32-feature block has three spare columns
+//     (W'hi[:, d..d+2] = the TF32 pieces of bias_k, prepared by codebook_split_kernel; the converter sets
+//     X[:, d..d+2] = 1), so the epilogue only compares; 8-column MMA steps that hold nothing but the TMA
+//     zero fill are not issued (D = 16: 7 MMAs per tile instead of 12);
+//   * the producer and MMA warps run their loops with all 32 lanes and issue under elect.sync, which keeps
+//     every descriptor in uniform registers (a `lane == 0` branch costs an R2UR waterfall per instruction).
 //
 // Warp roles per CTA (576 threads): 0 TMA producer | 1 MMA issuer (leader CTA only) + TMEM alloc |
 // 2-5 converter (X -> TF32 hi/lo) | 6-13 epilogue (TMEM -> argmin; two warps per TMEM lane quarter,
