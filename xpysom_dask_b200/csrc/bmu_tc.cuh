@@ -205,6 +205,21 @@ struct RunMin {
     }
 };
 
+// Experiment knobs are read from the environment once per process (SOM_B200_DBG: timeline probe of
+// tools/bmu_probe.py; SOM_B200_TBN: neuron-tile width of the resident fp16 kernel).
+inline int env_int(const char *name) {
+    const char *e = getenv(name);
+    return e ? atoi(e) : 0;
+}
+// cudaFuncSetAttribute is per device: remember which devices have the large dynamic-shared-memory opt-in.
+inline bool first_launch_on_device(bool (&done)[64]) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+}
+
 // One lane of a converged warp.  The whole warp runs the producer / MMA loops (so every address stays in uniform
 // registers -- no per-instruction R2UR waterfall) and only the async instructions sit under the election.
 __device__ __forceinline__ bool elect_one() {

@@ -410,6 +410,8 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 
 inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, const WsLayout &L, uint8_t *ws,
                           int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
+    SOM_REQUIRE(L.k_pad < (1 << 24), SOM_E_SHAPE,
+                "tensor-core BMU kernels track the winning neuron as an exact fp32 integer: at most 2^24 neurons (k=%d)", k);
     SOM_REQUIRE(tc::shape_ok(X, n, d, ldx), SOM_E_SHAPE,
                 "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
     CUtensorMap mx, mhi, mlo;
@@ -417,11 +419,9 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     if ((rc = tc::make_map_2d(&mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)ldx * 4, BK, BM))) return rc;
     if ((rc = tc::make_map_2d(&mhi, ws + L.whi_off, (uint64_t)L.d_pad, (uint64_t)L.k_pad, (uint64_t)L.d_pad * 4, BK, BNH))) return rc;
     if ((rc = tc::make_map_2d(&mlo, ws + L.wlo_off, (uint64_t)L.d_pad, (uint64_t)L.k_pad, (uint64_t)L.d_pad * 4, BK, BNH))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (tc::first_launch_on_device(attr_set))
         SOM_CUDA(cudaFuncSetAttribute(bmu_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
-    }
     const int num_pair_tiles = (int)ceil_div(n, 2 * BM);
     const int num_n_tiles = L.k_pad / BN;
     const int num_k_blocks = L.d_pad / BK;
@@ -433,7 +433,8 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
-    { const char *e = getenv("SOM_B200_DBG"); acc.dbg = e ? atoi(e) : 0; }
+    static const int dbg = tc::env_int("SOM_B200_DBG");
+    acc.dbg = dbg;
     return check_cuda(launch_pdl(bmu_tc2_kernel, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, st, mx, mhi, mlo,
                                  reinterpret_cast<const float *>(ws + L.bias_off),
                                  reinterpret_cast<const unsigned int *>(ws + L.gstat_off), n, num_pair_tiles, num_n_tiles,

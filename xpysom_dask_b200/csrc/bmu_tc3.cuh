@@ -518,24 +518,26 @@ inline int make_map_2d_f16(CUtensorMap *m, const void *base, uint64_t inner, uin
 
 inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const float *xscale, int k, const WsLayout &L,
                           uint8_t *ws, int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
+    SOM_REQUIRE(L.k_pad < (1 << 24), SOM_E_SHAPE,
+                "tensor-core BMU kernels track the winning neuron as an exact fp32 integer: at most 2^24 neurons (k=%d)", k);
     SOM_REQUIRE(tc::shape_ok(X, n, d, ldx), SOM_E_SHAPE,
                 "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
     SOM_REQUIRE(xscale != nullptr, SOM_E_BADARG, "the fp16-split kernel needs the per-row scales (som_b200_prepare_samples)");
     const int num_k_blocks = L.d_pad64 / BK;
     const bool resident = num_k_blocks <= RESIDENT_MAX_KB;
     int tbn = 256;      // SOM_B200_TBN=128: four-accumulator-stage experiment (resident mode only; slower, see above)
-    { const char *e = getenv("SOM_B200_TBN"); if (e && resident && atoi(e) == 128) tbn = 128; }
+    static const int tbn_env = tc::env_int("SOM_B200_TBN");
+    if (resident && tbn_env == 128) tbn = 128;
     CUtensorMap mx, mhi, mlo;
     int rc;
     if ((rc = tc::make_map_2d(&mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)ldx * 4, 32, BM))) return rc;
     if ((rc = make_map_2d_f16(&mhi, ws + L.w16hi_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, tbn / 2))) return rc;
     if ((rc = make_map_2d_f16(&mlo, ws + L.w16lo_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, tbn / 2))) return rc;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static bool attr_set[64] = {};
+    if (tc::first_launch_on_device(attr_set)) {
         SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        attr_set = true;
     }
     const int num_pair_tiles = (int)ceil_div(n, 2 * BM);
     const int num_n_tiles = L.k_pad / tbn;
@@ -547,7 +549,8 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
     acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
-    { const char *e = getenv("SOM_B200_DBG"); acc.dbg = e ? atoi(e) : 0; }
+    static const int dbg = tc::env_int("SOM_B200_DBG");
+    acc.dbg = dbg;
     const float *bias_p = reinterpret_cast<const float *>(ws + L.bias_off);
     const float *wsinv_p = reinterpret_cast<const float *>(ws + L.wsinv_off);
     const unsigned int *gstat_p = reinterpret_cast<const unsigned int *>(ws + L.gstat_off);
