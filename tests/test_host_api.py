@@ -93,3 +93,33 @@ def test_pca_and_random_init_and_pickle():
         XPySom(3, 3, 1).pca_weights_init(np.zeros((4, 1)))
     with pytest.raises(ValueError):
         s.quantization_error(np.zeros((4, 3)))                              # wrong feature count, :361-367
+
+
+def test_input_adapters_numpy_list_torch_dlpack():
+    """train / winner accept what the reference accepts (lists, numpy of any dtype, xpysom.py:485-510) plus
+    torch tensors and any DLPack exporter (CuPy, the reference's GPU input); everything becomes a 2-D fp32
+    matrix, 1-D samples become one row, anything else is rejected."""
+    import torch
+    from xpysom_dask_b200.xpysom import _as_f32_matrix
+
+    class DlpackOnly:                      # stands in for a CuPy / JAX array: only the DLPack protocol
+        def __init__(self, t):
+            self._t = t
+
+        def __dlpack__(self, *a, **k):
+            return self._t.__dlpack__(*a, **k)
+
+        def __dlpack_device__(self):
+            return self._t.__dlpack_device__()
+
+    base = np.arange(12, dtype=np.float64).reshape(4, 3)
+    for data in (base, base.tolist(), base.astype(np.int32), torch.from_numpy(base),
+                 DlpackOnly(torch.from_numpy(base.astype(np.float32)))):
+        t = _as_f32_matrix(data)
+        assert t.dtype == torch.float32 and tuple(t.shape) == (4, 3)
+        np.testing.assert_array_equal(t.numpy(), base.astype(np.float32))
+    shared = torch.arange(6, dtype=torch.float32).reshape(2, 3)
+    assert _as_f32_matrix(DlpackOnly(shared)).data_ptr() == shared.data_ptr()        # no copy
+    assert tuple(_as_f32_matrix([1.0, 2.0, 3.0]).shape) == (1, 3)
+    with pytest.raises(ValueError):
+        _as_f32_matrix(np.zeros((2, 2, 2)))

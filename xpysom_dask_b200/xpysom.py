@@ -42,6 +42,10 @@ _DEFAULT_N_PARALLEL = 148 * 2048     # SMs x max threads/SM on B200: the rule of
 
 def _as_f32_matrix(data):
     """Any array-like / torch tensor -> 2-D float32 torch tensor (no copy when possible)."""
+    if not isinstance(data, (torch.Tensor, np.ndarray)) and hasattr(data, '__dlpack__'):
+        # device arrays of other libraries (CuPy -- the reference's own GPU input, xpysom.py:487-510 -- JAX, ...)
+        # come in through DLPack without a copy
+        data = torch.from_dlpack(data)
     if isinstance(data, torch.Tensor):
         t = data
         if t.dtype != torch.float32:
