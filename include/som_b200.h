@@ -162,6 +162,20 @@ int som_b200_epoch_advance(int *epoch_dev, void *stream);
 int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev,
                    int k, int d, void *stream);
 
+/* Everything between two BMU searches in one call: som_b200_neigh_apply (K4) + som_b200_merge (M) +
+ * som_b200_prepare_codebook of the NEW codebook (Q, xpysom.py:529-539, for the next epoch) + S, c cleared
+ * (xpysom.py:516-527).  On small maps (direct neighbourhood kernel with 64x64 tiles: at most 64 features or
+ * fewer than 512 neurons, K*D <= 2^20) this is ONE cooperative kernel with grid-wide barriers between the
+ * phases instead of ten stream operations (csrc/epoch_tail.cuh); otherwise it issues the separate launches.
+ * Same results either way.  The workspace must have been prepared before (som_b200_prepare_codebook), as it
+ * is for the BMU search that precedes this call.  The caller's epoch becomes:
+ * som_b200_epoch_accumulate -> (all-reduce of [S | c]) -> som_b200_epoch_tail. */
+int som_b200_epoch_tail(float *s_dev, float *c_dev, float *w_dev, int gx, int gy, int d,
+                        int topology, int neigh_kind, double sigma, double eta, double std_coeff,
+                        int compact_support, int dist_kind, float p,
+                        float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats,
+                        void *ws_dev, size_t ws_bytes, void *stream);
+
 /* ---- sharded path: the one exchange step -------------------------------------------------------
  * The reference sums the per-block partial updates with Dask (`sum(...)` over the delayed `_update`
  * results, xpysom.py:574-583).  With one process per GPU that sum is ONE all-reduce of [S | c]

@@ -66,6 +66,14 @@ class OracleEngine:
         num.copy_(torch.from_numpy((H.T @ s.numpy().reshape(gx * gy, d).astype(np.float64)).astype(np.float32).ravel()))
         den.copy_(torch.from_numpy((H.T @ c.numpy().astype(np.float64)).astype(np.float32)))
 
+    def epoch_tail(self, s, c, w, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, dist_kind, p,
+                   num, den, tables, ws):
+        self.neigh_apply(s, c, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, num, den, tables)
+        self.merge(w, num, den)
+        self.prepare_codebook(w, dist_kind, p, ws)
+        s.zero_()
+        c.zero_()
+
     def merge(self, w, num, den):
         k, d = w.shape
         out = so.merge(w.numpy(), num.numpy().reshape(k, d), den.numpy().reshape(k, 1))

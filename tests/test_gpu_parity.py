@@ -247,6 +247,49 @@ def test_neigh_apply_wide_tile_variant(eng, fn, compact, topology):
         assert e1 < 1e-5 and e2 < 1e-5, (fn, compact, topology, sigma, e1, e2)
 
 
+@pytest.mark.parametrize("gx,gy,d,fn,topology,dist", [
+    (32, 32, 64, "gaussian", "rectangular", "euclidean"),       # config-2 map: fused kernel, 64x64 tiles, sliced
+    (27, 23, 100, "mexican_hat", "hexagonal", "cosine"),        # wide features: the entry issues the separate launches
+    (27, 23, 50, "mexican_hat", "hexagonal", "cosine"),         # fused, hexagonal mexican hat, ragged K and D
+    (7, 7, 4, "bubble", "rectangular", "manhattan"),            # tiny map, SIMT distance (no operand copies)
+    (40, 40, 16, "triangle", "rectangular", "euclidean"),       # config-3 map
+    (70, 60, 12, "gaussian", "rectangular", "euclidean"),       # separable path: the entry falls back to separate launches
+])
+def test_epoch_tail_matches_separate_launches(eng, gx, gy, d, fn, topology, dist):
+    """som_b200_epoch_tail (one cooperative kernel on small maps) == neigh_apply + merge + prepare_codebook + clearing
+    S and c: same codebook, a workspace that finds the same BMUs, clean accumulators."""
+    from xpysom_dask_b200 import _lib
+    K = gx * gy
+    rng = np.random.RandomState(gx + d)
+    S = rng.randn(K, d).astype(np.float32)
+    c = rng.randint(0, 7, size=K).astype(np.float32)
+    S[c == 0] = 0
+    W0 = rng.rand(K, d).astype(np.float32)
+    X = torch.from_numpy(rng.rand(3000, (d + 3) // 4 * 4).astype(np.float32)).cuda()[:, :d]
+    dk, tk, nk = _lib.DIST[dist], _lib.TOPO[topology], _lib.NEIGH[fn]
+    res = []
+    for fused in (False, True):
+        Sd, cd, w = torch.from_numpy(S).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(W0).cuda()
+        num, den = eng.empty(K, d), eng.empty(K)
+        ws, tables = eng.workspace(0, K, d), eng.neigh_tables(gx, gy, d)
+        eng.prepare_codebook(w, dk, 2.0, ws)          # as in training: the tail follows a BMU search on a prepared workspace
+        if fused:
+            eng.epoch_tail(Sd, cd, w, gx, gy, d, tk, nk, 2.3, 0.4, 0.5, False, dk, 2.0, num, den, tables, ws)
+        else:
+            eng.neigh_apply(Sd, cd, gx, gy, d, tk, nk, 2.3, 0.4, 0.5, False, num, den, tables)
+            eng.merge(w, num, den)
+            eng.prepare_codebook(w, dk, 2.0, ws)
+            Sd.zero_(); cd.zero_()
+        xs = eng.prepare_samples(X) if dist in ("euclidean", "cosine") else None
+        bmu = eng.bmu(X, w, dk, 2.0, _lib.ALGO["auto"], ws, xscale=xs)
+        torch.cuda.synchronize()
+        res.append((w.cpu().numpy(), bmu.cpu().numpy(), float(Sd.abs().max()), float(cd.abs().max())))
+    (wa, ba, _, _), (wb, bb, smax, cmax) = res
+    assert U.codebook_rel_err(wb, wa) < 2e-6
+    assert smax == 0.0 and cmax == 0.0
+    assert (ba != bb).mean() < 2e-3          # codebooks differ in the last bits (order of the sliced sums): near-ties only
+
+
 def test_neigh_apply_skips_empty_bmus(eng):
     case = dict(gx=6, gy=5, topology="rectangular", fn="gaussian", compact=False)
     S = np.zeros((30, 4), np.float32); c = np.zeros(30, np.float32)

@@ -30,7 +30,8 @@ struct WsLayout {
     size_t w16lo_off; // k_pad x d_pad64 halves: fp16 "lo" part
     size_t wsinv_off; // k_pad floats: 2^-b_k, the inverse of the per-neuron power-of-two scale
     size_t cnt_off;   // k_pad int32: exact per-BMU counts of the fused kernel (zero between launches)
-    size_t done_off;  // one uint32: CTAs-finished ticket of the fused kernel (zero between launches)
+    size_t done_off;  // one uint32: CTAs-finished ticket of the fused kernel (zero between launches); the grid
+                      // barrier of epoch_tail_kernel lives at +256 (arrivals) and +320 (generation)
     size_t gstat_off; // codebook statistics of the current prepare: [0] bits of max_k amax_k, [1] ~bits of the
                       // smallest non-zero amax_k (both via atomicMax, zeroed by prepare), [2] uniform-scale flag
     size_t amax_off;  // k_pad floats: amax_k = max_c |w'_k[c]|

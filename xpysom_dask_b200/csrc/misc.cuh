@@ -25,6 +25,31 @@ __device__ __forceinline__ float codebook_row_scale(int dist_kind, double s) {
     return 0.f;
 }
 
+// one warp: statistics of neuron `row` from the values its lanes hold (lane l: columns l, l + 32, ...),
+// s = partial sum of squares (fp64), m = partial max |w|
+__device__ __forceinline__ void codebook_stats_row(int row, bool real, double s, float m, int lane, int dist_kind,
+                                                   float *__restrict__ aux, float *__restrict__ bias,
+                                                   float *__restrict__ amax, unsigned int *__restrict__ gstat) {
+    s = warp_sum(s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (lane != 0) return;
+    const float wsq = (float)s;
+    float a = 0.f, b = INFINITY;
+    if (real) {
+        if (dist_kind == SOM_DIST_EUCLIDEAN) { a = wsq; b = wsq; }
+        else if (dist_kind == SOM_DIST_COSINE) { a = -codebook_row_scale(dist_kind, s); b = 0.f; }
+        else { a = wsq; b = 0.f; }
+    }
+    aux[row] = a; bias[row] = b;
+    const float am = real ? m * fabsf(codebook_row_scale(dist_kind, s)) : 0.f;
+    amax[row] = am;
+    if (am > 0.f && isfinite(am)) {
+        atomicMax(gstat + 0, __float_as_uint(am));
+        atomicMax(gstat + 1, ~__float_as_uint(am));
+    }
+}
+
 __global__ void codebook_stats_kernel(const float *__restrict__ W, int k, int d, int dist_kind, int k_pad,
                                       float *__restrict__ aux, float *__restrict__ bias, float *__restrict__ amax,
                                       unsigned int *__restrict__ gstat) {
@@ -37,24 +62,7 @@ __global__ void codebook_stats_kernel(const float *__restrict__ W, int k, int d,
     float m = 0.f;
     if (real)
         for (int c = lane; c < d; c += 32) { const float v = W[(int64_t)warp * d + c]; s += (double)v * v; m = fmaxf(m, fabsf(v)); }
-    s = warp_sum(s);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (lane != 0) return;
-    const float wsq = (float)s;
-    float a = 0.f, b = INFINITY;
-    if (real) {
-        if (dist_kind == SOM_DIST_EUCLIDEAN) { a = wsq; b = wsq; }
-        else if (dist_kind == SOM_DIST_COSINE) { a = -codebook_row_scale(dist_kind, s); b = 0.f; }
-        else { a = wsq; b = 0.f; }
-    }
-    aux[warp] = a; bias[warp] = b;
-    const float am = real ? m * fabsf(codebook_row_scale(dist_kind, s)) : 0.f;
-    amax[warp] = am;
-    if (am > 0.f && isfinite(am)) {
-        atomicMax(gstat + 0, __float_as_uint(am));
-        atomicMax(gstat + 1, ~__float_as_uint(am));
-    }
+    codebook_stats_row(warp, real, s, m, lane, dist_kind, aux, bias, amax, gstat);
 }
 
 // Q, pass 2: operand copies of the scaled codebook for the tensor-core kernels.
@@ -63,18 +71,20 @@ __global__ void codebook_stats_kernel(const float *__restrict__ W, int k, int d,
 //                2^12 of the largest one, ONE power of two serves the whole codebook (b_k = b, gstat[2] = 1) and
 //                the epilogue needs a single fused multiply-add per score; otherwise each neuron gets its own
 //                b_k (exact, undone per column in the epilogue) so that tiny neurons keep their 22 bits.
-__global__ void codebook_split_kernel(const float *__restrict__ W, int k, int d, int dist_kind, int k_pad, int d_pad,
-                                      float *__restrict__ whi, float *__restrict__ wlo, int d_pad64,
-                                      __half *__restrict__ w16hi, __half *__restrict__ w16lo, float *__restrict__ wsinv,
-                                      const float *__restrict__ aux, const float *__restrict__ bias,
-                                      const float *__restrict__ amax, unsigned int *__restrict__ gstat) {
-    pdl_wait(); pdl_trigger();
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= k_pad) return;
-    const bool real = warp < k;
+struct SplitOut {
+    float *whi, *wlo;            // (k_pad, d_pad) TF32 hi / lo
+    __half *w16hi, *w16lo;       // (k_pad, d_pad64) fp16 hi / lo
+    float *wsinv;                // (k_pad)
+    int d_pad, d_pad64;
+};
+
+// one warp: the operand copies of neuron `row`.  (No __restrict__ here on purpose: epoch_tail_kernel writes W, aux,
+// bias and amax earlier in the SAME launch, so these loads must not go through the non-coherent path.)
+__device__ __forceinline__ void codebook_split_row(const float *W, int row, bool real, int lane, int d, int dist_kind,
+                                                   const SplitOut &O, const float *aux, const float *bias, const float *amax,
+                                                   unsigned int *gstat) {
     float scale = 0.f;
-    if (real) scale = dist_kind == SOM_DIST_EUCLIDEAN ? -2.f : -aux[warp];     // aux = 1/|w| for cosine
+    if (real) scale = dist_kind == SOM_DIST_EUCLIDEAN ? -2.f : -aux[row];     // aux = 1/|w| for cosine
     const float gmax = __uint_as_float(gstat[0]);
     const unsigned int nmin = gstat[1];
     const float gmin = nmin ? __uint_as_float(~nmin) : gmax;
@@ -82,28 +92,38 @@ __global__ void codebook_split_kernel(const float *__restrict__ W, int k, int d,
     // TF32 copies: when the last 32-feature block has three spare columns, the epilogue bias is FOLDED into the
     // contraction: columns d, d+1, d+2 of W'hi carry the three TF32 pieces of bias_k (33 mantissa bits, more than
     // the fp32 accumulator keeps) and the kernel sets the matching X columns to 1; gstat[3] = 1 tells it so.
-    const bool fold = d_pad - d >= 3;
-    if (warp == 0 && lane == 0) { gstat[2] = uniform ? 1u : 0u; gstat[3] = fold ? 1u : 0u; }
-    const float bk = bias[warp];                       // |w|^2, 0 (cosine) or +inf (padding neuron)
+    const bool fold = O.d_pad - d >= 3;
+    if (row == 0 && lane == 0) { gstat[2] = uniform ? 1u : 0u; gstat[3] = fold ? 1u : 0u; }
+    const float bk = bias[row];                        // |w|^2, 0 (cosine) or +inf (padding neuron)
     float b0 = tf32_rna(bk), b1 = 0.f, b2 = 0.f;
     if (isfinite(bk)) { b1 = tf32_rna(bk - b0); b2 = tf32_rna((bk - b0) - b1); }
-    for (int c = lane; c < d_pad; c += 32) {
+    for (int c = lane; c < O.d_pad; c += 32) {
         float v = 0.f;
-        if (real && c < d) v = W[(int64_t)warp * d + c] * scale;
+        if (real && c < d) v = W[(int64_t)row * d + c] * scale;
         float hi = tf32_rna(v), lo = tf32_rna(v - hi);
         if (fold && c >= d && c < d + 3) { hi = c == d ? b0 : (c == d + 1 ? b1 : b2); lo = 0.f; }
-        whi[(int64_t)warp * d_pad + c] = hi;
-        wlo[(int64_t)warp * d_pad + c] = lo;
+        O.whi[(int64_t)row * O.d_pad + c] = hi;
+        O.wlo[(int64_t)row * O.d_pad + c] = lo;
     }
-    const float ps = pow2_scale_for(uniform ? gmax : amax[warp]);
-    if (lane == 0) wsinv[warp] = 1.f / ps;              // exact: ps is a power of two
-    for (int c = lane; c < d_pad64; c += 32) {
+    const float ps = pow2_scale_for(uniform ? gmax : amax[row]);
+    if (lane == 0) O.wsinv[row] = 1.f / ps;             // exact: ps is a power of two
+    for (int c = lane; c < O.d_pad64; c += 32) {
         float v = 0.f;
-        if (real && c < d) v = W[(int64_t)warp * d + c] * scale * ps;
+        if (real && c < d) v = W[(int64_t)row * d + c] * scale * ps;
         const __half hi = __float2half_rn(v);
-        w16hi[(int64_t)warp * d_pad64 + c] = hi;
-        w16lo[(int64_t)warp * d_pad64 + c] = __float2half_rn(v - __half2float(hi));
+        O.w16hi[(int64_t)row * O.d_pad64 + c] = hi;
+        O.w16lo[(int64_t)row * O.d_pad64 + c] = __float2half_rn(v - __half2float(hi));
     }
+}
+
+__global__ void codebook_split_kernel(const float *__restrict__ W, int k, int d, int dist_kind, int k_pad, SplitOut O,
+                                      const float *__restrict__ aux, const float *__restrict__ bias,
+                                      const float *__restrict__ amax, unsigned int *__restrict__ gstat) {
+    pdl_wait(); pdl_trigger();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= k_pad) return;
+    codebook_split_row(W, warp, warp < k, lane, d, dist_kind, O, aux, bias, amax, gstat);
 }
 
 // |w_k|^2 per neuron (fp64 accumulation, rounded once), one warp per row

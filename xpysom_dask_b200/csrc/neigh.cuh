@@ -45,17 +45,11 @@ __device__ __forceinline__ void neigh_resolve(const NeighParams &P, float &inv_d
 // hexagonal rule of xpysom.py:201-206: rows (gy-1-j) even are shifted by -0.5
 __host__ __device__ inline int hex_shift(int j, int gy) { return ((gy - 1 - j) & 1) == 0 ? 1 : 0; }
 
-// one thread per table entry; all arithmetic in fp64, stored as fp32
-__global__ void neigh_tables_kernel(int gx, int gy, int kind, int compact, int shifted,
-                                    double sigma, double dd, float *tx, float *ty, float *mx, float *my,
-                                    const double *sched, const int *epoch, double std_coeff) {
-    pdl_wait(); pdl_trigger();
-    if (sched != nullptr) {          // schedule read on the device (graph replay)
-        sigma = sched[2 * (*epoch)];
-        dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
-    }
+// one thread per table entry (grid-stride over `nthr` threads); all arithmetic in fp64, stored as fp32
+__device__ __forceinline__ void neigh_tables_fill(int gx, int gy, int kind, int compact, int shifted, double sigma, double dd,
+                                                  float *tx, float *ty, float *mx, float *my, int tid, int nthr) {
     const int nxe = 3 * gx * gx, nye = gy * gy;
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < nxe + nye; e += gridDim.x * blockDim.x) {
+    for (int e = tid; e < nxe + nye; e += nthr) {
         const bool isx = e < nxe;
         int q = 1, c, nn;
         if (isx) { q = e / (gx * gx); c = (e / gx) % gx; nn = e % gx; }
@@ -86,17 +80,30 @@ __global__ void neigh_tables_kernel(int gx, int gy, int kind, int compact, int s
     }
 }
 
+__global__ void neigh_tables_kernel(int gx, int gy, int kind, int compact, int shifted,
+                                    double sigma, double dd, float *tx, float *ty, float *mx, float *my,
+                                    const double *sched, const int *epoch, double std_coeff) {
+    pdl_wait(); pdl_trigger();
+    if (sched != nullptr) {          // schedule read on the device (graph replay)
+        sigma = sched[2 * (*epoch)];
+        dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
+    }
+    neigh_tables_fill(gx, gy, kind, compact, shifted, sigma, dd, tx, ty, mx, my, blockIdx.x * blockDim.x + threadIdx.x,
+                      gridDim.x * blockDim.x);
+}
+
 __device__ __forceinline__ float neigh_eval(const NeighParams &P, float inv_d, float two_over_d, int bi, int bj, int i, int j) {
     const int q = P.shifted ? (hex_shift(bj, P.gy) - hex_shift(j, P.gy) + 1) : 1;
     const int xe = (q * P.gx + bi) * P.gx + i;
     const int ye = bj * P.gy + j;
-    const float fx = __ldg(P.tx + xe), fy = __ldg(P.ty + ye);
+    // (plain loads, not __ldg: epoch_tail_kernel fills the tables earlier in the same launch)
+    const float fx = P.tx[xe], fy = P.ty[ye];
     if (P.kind != SOM_NEIGH_MEXICAN_HAT) return fx * fy;
     float px = fx;
     if (P.compact) {
         // neighborhoods.py:69-71 / 91-93: px is multiplied by both windows, py by none.
-        const float wy = P.mex_rect_quirk ? __ldg(P.my + bj * P.gy + i) : __ldg(P.my + ye);
-        px *= __ldg(P.mx + xe) * wy;
+        const float wy = P.mex_rect_quirk ? P.my[bj * P.gy + i] : P.my[ye];
+        px *= P.mx[xe] * wy;
     }
     const float p = px + fy;
     return expf(-p * inv_d) * (1.f - two_over_d * p);
@@ -108,19 +115,17 @@ __device__ __forceinline__ float neigh_eval(const NeighParams &P, float inv_d, f
 // mexican hat, K = 2500, D = 128: 2 K^2 D = 1.6 GFLOP per epoch).
 constexpr int NB_K = 16, NB_THREADS = 256;
 
+// One output tile: neurons [k0, k0 + 16 RM) x features [n0, n0 + 16 RN), BMUs [b_begin, b_end).  `atomic`: several
+// BMU slices add into the same tile; `with_den`: this tile also produces den (one tile per neuron range does).
 template <int RM, int RN>
-__global__ void __launch_bounds__(NB_THREADS)
-neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__restrict__ c,
-                   float *__restrict__ num, float *__restrict__ den, int b_per_slice) {
-    pdl_wait(); pdl_trigger();
+__device__ __forceinline__ void neigh_apply_tile(const NeighParams &P, float inv_d, float two_over_d, float eta,
+                                                 const float *S, const float *c, float *num, float *den,
+                                                 int k0, int n0, int b_begin, int b_end, bool atomic, bool with_den) {
     constexpr int TM = 16 * RM, TN = 16 * RN;
     __shared__ __align__(16) float Hs[NB_K][TM + 4];
     __shared__ __align__(16) float Ss[NB_K][TN + 4];
     __shared__ float cs[NB_K];
     const int K = P.gx * P.gy, D = P.d;
-    float inv_d, two_over_d, eta;
-    neigh_resolve(P, inv_d, two_over_d, eta);
-    const int k0 = blockIdx.x * TM, n0 = blockIdx.y * TN;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 
     // this thread generates H entries for b = b0 + (tid >> 4), k = k0 + (tid & 15) * RM + {0..RM-1}
@@ -141,9 +146,6 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
 #pragma unroll
     for (int a = 0; a < RM; ++a) dacc[a] = 0.f;
 
-    // gridDim.z slices the reduction over BMUs so that small maps still fill the GPU
-    const int b_begin = blockIdx.z * b_per_slice;
-    const int b_end = min(K, b_begin + b_per_slice);
     for (int b0 = b_begin; b0 < b_end; b0 += NB_K) {
         const int b = b0 + hb;
         float hv[RM], sv[RN];
@@ -153,7 +155,7 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
         for (int e = 0; e < RN; ++e) sv[e] = 0.f;
         float cb = 0.f;
         if (b < b_end) {
-            cb = __ldg(c + b);
+            cb = c[b];         // (plain loads: epoch_tail_kernel clears S and c later in the same launch)
             if (cb != 0.f) {   // an empty BMU contributes nothing (S[b] = 0 as well)
                 const int bi = b / P.gy, bj = b % P.gy;
 #pragma unroll
@@ -161,7 +163,7 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
 #pragma unroll
                 for (int e = 0; e < RN; ++e) {
                     const int col = n0 + hn + e;
-                    sv[e] = col < D ? __ldg(S + (int64_t)b * D + col) : 0.f;
+                    sv[e] = col < D ? S[(int64_t)b * D + col] : 0.f;
                 }
             }
         }
@@ -204,15 +206,31 @@ neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__re
         for (int bb = 0; bb < RN; ++bb) {
             const int col = n0 + tx * RN + bb;
             if (col < D) {                                                    // g = h * eta (xpysom.py:434)
-                if (gridDim.z == 1) num[(int64_t)kk * D + col] = acc[a][bb] * eta;
-                else                atomicAdd(num + (int64_t)kk * D + col, acc[a][bb] * eta);
+                if (!atomic) num[(int64_t)kk * D + col] = acc[a][bb] * eta;
+                else         atomicAdd(num + (int64_t)kk * D + col, acc[a][bb] * eta);
             }
         }
-        if (tx == 0 && blockIdx.y == 0) {
-            if (gridDim.z == 1) den[kk] = dacc[a] * eta;
-            else                atomicAdd(den + kk, dacc[a] * eta);
+        if (tx == 0 && with_den) {
+            if (!atomic) den[kk] = dacc[a] * eta;
+            else         atomicAdd(den + kk, dacc[a] * eta);
         }
     }
+    __syncthreads();       // the shared tiles may be reused by the caller's next tile
+}
+
+template <int RM, int RN>
+__global__ void __launch_bounds__(NB_THREADS)
+neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__restrict__ c,
+                   float *__restrict__ num, float *__restrict__ den, int b_per_slice) {
+    pdl_wait(); pdl_trigger();
+    float inv_d, two_over_d, eta;
+    neigh_resolve(P, inv_d, two_over_d, eta);
+    // gridDim.z slices the reduction over BMUs so that small maps still fill the GPU
+    const int K = P.gx * P.gy;
+    const int b_begin = blockIdx.z * b_per_slice;
+    const int b_end = min(K, b_begin + b_per_slice);
+    neigh_apply_tile<RM, RN>(P, inv_d, two_over_d, eta, S, c, num, den, blockIdx.x * 16 * RM, blockIdx.y * 16 * RN, b_begin, b_end,
+                             gridDim.z != 1, blockIdx.y == 0);
 }
 
 // ---- separable path -------------------------------------------------------------------------------
@@ -278,12 +296,10 @@ inline size_t neigh_table_floats(int gx, int gy) {
     return (size_t)2 * ((size_t)3 * gx * gx + (size_t)gy * gy) + 64;
 }
 
-inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, int d, int topology, int kind,
-                              double sigma, double eta, double std_coeff, int compact,
-                              float *num, float *den, float *tables, float *scratch, int sm_count, cudaStream_t st,
-                              const double *sched = nullptr, const int *epoch = nullptr) {
-    NeighParams P;
-    P.sched = sched; P.epoch = epoch; P.std_coeff = std_coeff;
+// host: everything of NeighParams that does not depend on a device-side schedule; the factor tables live in `tables`
+inline void neigh_params(NeighParams &P, int gx, int gy, int d, int topology, int kind, double sigma, double eta,
+                         double std_coeff, int compact, float *tables) {
+    P.sched = nullptr; P.epoch = nullptr; P.std_coeff = std_coeff;
     P.gx = gx; P.gy = gy; P.d = d; P.topology = topology; P.kind = kind; P.compact = compact ? 1 : 0;
     // bubble and triangle use integer grid indices on both topologies (xpysom.py:266-269, 277-278)
     P.shifted = (topology == SOM_TOPO_HEXAGONAL && (kind == SOM_NEIGH_GAUSSIAN || kind == SOM_NEIGH_MEXICAN_HAT)) ? 1 : 0;
@@ -293,8 +309,19 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
     P.two_over_d = (float)(2.0 / dd);
     P.eta = (float)eta;
     const size_t nxe = (size_t)3 * gx * gx, nye = (size_t)gy * gy;
+    P.tx = tables; P.ty = tables + nxe; P.mx = tables + nxe + nye; P.my = tables + 2 * nxe + nye;
+}
+
+inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, int d, int topology, int kind,
+                              double sigma, double eta, double std_coeff, int compact,
+                              float *num, float *den, float *tables, float *scratch, int sm_count, cudaStream_t st,
+                              const double *sched = nullptr, const int *epoch = nullptr) {
+    NeighParams P;
+    neigh_params(P, gx, gy, d, topology, kind, sigma, eta, std_coeff, compact, tables);
+    P.sched = sched; P.epoch = epoch;
+    const double dd = 2.0 * std_coeff * std_coeff * sigma * sigma;   // neighborhoods.py:19
+    const size_t nxe = (size_t)3 * gx * gx, nye = (size_t)gy * gy;
     float *tx = tables, *ty = tx + nxe, *mx = ty + nye, *my = mx + nxe;
-    P.tx = tx; P.ty = ty; P.mx = mx; P.my = my;
     const int tot = (int)(nxe + nye);
     int rc = check_cuda(launch_pdl(neigh_tables_kernel, dim3((tot + 255) / 256), dim3(256), 0, st, gx, gy, kind, P.compact,
                                    P.shifted, sigma, dd, tx, ty, mx, my, sched, epoch, std_coeff),

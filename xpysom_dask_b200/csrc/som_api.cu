@@ -15,6 +15,7 @@
 #include "neigh.cuh"
 #include "peer.cuh"
 #include "misc.cuh"
+#include "epoch_tail.cuh"
 
 namespace somb200 {
 
@@ -115,6 +116,15 @@ size_t som_b200_neigh_scratch_floats(int gx, int gy, int d) {
     return neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d);
 }
 
+static SplitOut split_out(const WsLayout &L, uint8_t *ws) {
+    SplitOut O;
+    O.whi = reinterpret_cast<float *>(ws + L.whi_off); O.wlo = reinterpret_cast<float *>(ws + L.wlo_off);
+    O.w16hi = reinterpret_cast<__half *>(ws + L.w16hi_off); O.w16lo = reinterpret_cast<__half *>(ws + L.w16lo_off);
+    O.wsinv = reinterpret_cast<float *>(ws + L.wsinv_off);
+    O.d_pad = L.d_pad; O.d_pad64 = L.d_pad64;
+    return O;
+}
+
 int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, float p,
                               void *ws_dev, size_t ws_bytes, void *stream) {
     (void)p;
@@ -134,11 +144,8 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
                         "codebook_stats_kernel launch");
     if (rc || !split) return rc;
     return check_cuda(launch_pdl(codebook_split_kernel, dim3(blocks), dim3(threads), 0, (cudaStream_t)stream, w_dev, k, d,
-                                 dist_kind, L.k_pad, L.d_pad, reinterpret_cast<float *>(ws + L.whi_off),
-                                 reinterpret_cast<float *>(ws + L.wlo_off), L.d_pad64,
-                                 reinterpret_cast<__half *>(ws + L.w16hi_off), reinterpret_cast<__half *>(ws + L.w16lo_off),
-                                 reinterpret_cast<float *>(ws + L.wsinv_off), aux,
-                                 reinterpret_cast<const float *>(ws + L.bias_off), amax, gstat),
+                                 dist_kind, L.k_pad, split_out(L, ws), aux, reinterpret_cast<const float *>(ws + L.bias_off),
+                                 amax, gstat),
                       "codebook_split_kernel launch");
 }
 
@@ -242,27 +249,32 @@ int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
     return som_b200_accumulate(x_dev, n, d, ldx, bmu, k, s_dev, c_dev, stream);
 }
 
-int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy, int d, int topology,
-                         int neigh_kind, double sigma, double eta, double std_coeff, int compact_support,
-                         float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats, void *stream) {
-    SOM_REQUIRE(s_dev && c_dev && num_dev && den_dev && tables_dev && gx > 0 && gy > 0 && d > 0, SOM_E_BADARG,
-                "neigh_apply: bad argument");
+static int neigh_check(int topology, int neigh_kind, int gx, int gy, int compact_support) {
     SOM_REQUIRE(topology == SOM_TOPO_RECTANGULAR || topology == SOM_TOPO_HEXAGONAL, SOM_E_BADARG,
-                "neigh_apply: unknown topology %d", topology);
+                "unknown topology %d", topology);
     SOM_REQUIRE(neigh_kind >= SOM_NEIGH_GAUSSIAN && neigh_kind <= SOM_NEIGH_TRIANGLE, SOM_E_BADARG,
-                "neigh_apply: unknown neighbourhood %d", neigh_kind);
+                "unknown neighbourhood %d", neigh_kind);
     // combinations the reference itself rejects
     SOM_REQUIRE(!(neigh_kind == SOM_NEIGH_TRIANGLE && topology == SOM_TOPO_HEXAGONAL), SOM_E_SHAPE,
                 "triangle is not available on a hexagonal map (xpysom.py:272-279)");
     SOM_REQUIRE(!(neigh_kind == SOM_NEIGH_MEXICAN_HAT && compact_support && topology == SOM_TOPO_RECTANGULAR && gx != gy),
                 SOM_E_SHAPE, "mexican_hat with compact_support broadcasts (n,gx)*(n,gy) in the reference "
                 "(neighborhoods.py:69-71): needs gx == gy");
+    return 0;
+}
+
+int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy, int d, int topology,
+                         int neigh_kind, double sigma, double eta, double std_coeff, int compact_support,
+                         float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats, void *stream) {
+    SOM_REQUIRE(s_dev && c_dev && num_dev && den_dev && tables_dev && gx > 0 && gy > 0 && d > 0, SOM_E_BADARG,
+                "neigh_apply: bad argument");
+    int rc = neigh_check(topology, neigh_kind, gx, gy, compact_support);
+    if (rc) return rc;
     SOM_REQUIRE(sigma != 0.0 && std_coeff != 0.0, SOM_E_BADARG, "neigh_apply: sigma and std_coeff must be non-zero");
     SOM_REQUIRE(tables_floats >= neigh_table_floats(gx, gy), SOM_E_WORKSPACE,
                 "neigh_apply: scratch of %zu floats < %zu", tables_floats, neigh_table_floats(gx, gy));
     DevInfo di;
-    int rc = device_info(di);
-    if (rc) return rc;
+    if ((rc = device_info(di))) return rc;
     // the two-pass separable path needs room for its intermediates after the factor tables
     float *scratch = tables_floats >= neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d)
                          ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
@@ -278,24 +290,87 @@ int som_b200_neigh_apply_sched(const float *s_dev, const float *c_dev, int gx, i
                                size_t tables_floats, void *stream) {
     SOM_REQUIRE(s_dev && c_dev && num_dev && den_dev && tables_dev && sched_dev && epoch_dev && gx > 0 && gy > 0 && d > 0,
                 SOM_E_BADARG, "neigh_apply_sched: bad argument");
-    SOM_REQUIRE(topology == SOM_TOPO_RECTANGULAR || topology == SOM_TOPO_HEXAGONAL, SOM_E_BADARG,
-                "neigh_apply_sched: unknown topology %d", topology);
-    SOM_REQUIRE(neigh_kind >= SOM_NEIGH_GAUSSIAN && neigh_kind <= SOM_NEIGH_TRIANGLE, SOM_E_BADARG,
-                "neigh_apply_sched: unknown neighbourhood %d", neigh_kind);
-    SOM_REQUIRE(!(neigh_kind == SOM_NEIGH_TRIANGLE && topology == SOM_TOPO_HEXAGONAL), SOM_E_SHAPE,
-                "triangle is not available on a hexagonal map (xpysom.py:272-279)");
-    SOM_REQUIRE(!(neigh_kind == SOM_NEIGH_MEXICAN_HAT && compact_support && topology == SOM_TOPO_RECTANGULAR && gx != gy),
-                SOM_E_SHAPE, "mexican_hat with compact_support needs gx == gy (neighborhoods.py:69-71)");
+    int rc = neigh_check(topology, neigh_kind, gx, gy, compact_support);
+    if (rc) return rc;
     SOM_REQUIRE(std_coeff != 0.0, SOM_E_BADARG, "neigh_apply_sched: std_coeff must be non-zero");
     SOM_REQUIRE(tables_floats >= neigh_table_floats(gx, gy), SOM_E_WORKSPACE,
                 "neigh_apply_sched: scratch of %zu floats < %zu", tables_floats, neigh_table_floats(gx, gy));
     DevInfo di;
-    int rc = device_info(di);
-    if (rc) return rc;
+    if ((rc = device_info(di))) return rc;
     float *scratch = tables_floats >= neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d)
                          ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
     return launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, 1.0, 1.0, std_coeff, compact_support,
                               num_dev, den_dev, tables_dev, scratch, di.sm, (cudaStream_t)stream, sched_dev, epoch_dev);
+}
+
+// Fused epoch tail (epoch_tail.cuh) when the map is small enough for one co-resident grid; otherwise the same
+// work as separate launches.  Either way, on return (stream order): W holds the merged codebook, the workspace
+// holds its statistics and operand copies (as after som_b200_prepare_codebook), and S, c are zero.
+int som_b200_epoch_tail(float *s_dev, float *c_dev, float *w_dev, int gx, int gy, int d, int topology, int neigh_kind,
+                        double sigma, double eta, double std_coeff, int compact_support, int dist_kind, float p,
+                        float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats,
+                        void *ws_dev, size_t ws_bytes, void *stream) {
+    SOM_REQUIRE(s_dev && c_dev && w_dev && num_dev && den_dev && tables_dev && ws_dev, SOM_E_BADARG, "epoch_tail: NULL pointer");
+    SOM_REQUIRE(gx > 0 && gy > 0 && d > 0 && sigma != 0.0 && std_coeff != 0.0, SOM_E_BADARG, "epoch_tail: bad argument");
+    SOM_REQUIRE(known_dist(dist_kind), SOM_E_BADARG, "epoch_tail: unknown distance kind %d", dist_kind);
+    const int K = gx * gy;
+    const WsLayout L = ws_layout(K, d);
+    SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "epoch_tail: workspace %zu < %zu bytes", ws_bytes, L.total);
+    SOM_REQUIRE(tables_floats >= neigh_table_floats(gx, gy), SOM_E_WORKSPACE, "epoch_tail: tables buffer too small");
+    int rc = neigh_check(topology, neigh_kind, gx, gy, compact_support);
+    if (rc) return rc;
+    DevInfo di;
+    if ((rc = device_info(di))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *ws = static_cast<uint8_t *>(ws_dev);
+    const bool has_scratch = tables_floats >= neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d);
+    const bool separable = has_scratch && neigh_is_separable(topology, neigh_kind, gx, gy);
+    // Measured on B200 (same box, bench.py --steps 10): fused 0.426 vs 0.438 ms per epoch at config 2, 0.996 vs 1.003 at
+    // config 3; with the 128x128 apply tiles (more than 64 features) the persistent grid LOSES 2.5 % at config 5, so
+    // those maps keep the separate launches.  SOM_B200_TAIL_SEPARATE=1 forces them everywhere (A/B measurements).
+    static const int no_fuse = tc::env_int("SOM_B200_TAIL_SEPARATE");
+    const bool wide = d > 64 && K >= 512;
+    const bool fused = !no_fuse && !separable && !wide && (int64_t)K * d <= (int64_t)1 << 20;
+    if (!fused) {
+        float *scratch = has_scratch ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
+        if ((rc = launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support,
+                                     num_dev, den_dev, tables_dev, scratch, di.sm, st))) return rc;
+        if ((rc = som_b200_merge(w_dev, num_dev, den_dev, K, d, stream))) return rc;
+        if ((rc = som_b200_prepare_codebook(w_dev, K, d, dist_kind, p, ws_dev, ws_bytes, stream))) return rc;
+        SOM_CUDA(cudaMemsetAsync(s_dev, 0, (size_t)K * d * sizeof(float), st));
+        SOM_CUDA(cudaMemsetAsync(c_dev, 0, (size_t)K * sizeof(float), st));
+        return 0;
+    }
+    TailArgs A;
+    neigh_params(A.P, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support, tables_dev);
+    A.sigma = sigma; A.dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
+    A.S = s_dev; A.c = c_dev; A.num = num_dev; A.den = den_dev; A.W = w_dev;
+    A.k = K; A.d = d; A.dist_kind = dist_kind; A.k_pad = L.k_pad;
+    A.aux = reinterpret_cast<float *>(ws + L.aux_off); A.bias = reinterpret_cast<float *>(ws + L.bias_off);
+    A.amax = reinterpret_cast<float *>(ws + L.amax_off); A.gstat = reinterpret_cast<unsigned int *>(ws + L.gstat_off);
+    A.split = split_out(L, ws);
+    A.do_split = (dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE) ? 1 : 0;
+    A.bar = reinterpret_cast<unsigned int *>(ws + L.done_off + 256);
+    A.tiles_m = (int)ceil_div(K, 64); A.tiles_n = (int)ceil_div(d, 64);
+    static int blocks_per_sm = 0;
+    if (!blocks_per_sm) {
+        int nb = 0;
+        SOM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, epoch_tail_kernel<4, 4>, NB_THREADS, 0));
+        SOM_REQUIRE(nb >= 1, SOM_E_NODEVICE, "epoch_tail: kernel does not fit an SM");
+        blocks_per_sm = nb > 2 ? 2 : nb;
+    }
+    const int grid = di.sm * blocks_per_sm;
+    const int gxy = A.tiles_m * A.tiles_n;
+    int slices = grid / gxy;                                     // one wave of tiles over the persistent grid
+    const int max_slices = (int)ceil_div(K, 4 * NB_K);           // at least 64 BMUs per slice
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    A.b_per_slice = (int)round_up(ceil_div(K, slices), NB_K);
+    A.slices = (int)ceil_div(K, A.b_per_slice);
+    void *args[] = {&A};
+    // cooperative launch: all CTAs co-resident or the launch fails -- the grid barriers cannot deadlock
+    const cudaError_t e = cudaLaunchCooperativeKernel((const void *)epoch_tail_kernel<4, 4>, dim3(grid), dim3(NB_THREADS), args, 0, st);
+    return check_cuda(e, "epoch_tail_kernel launch");
 }
 
 __global__ void epoch_advance_kernel(int *epoch) { *epoch += 1; }

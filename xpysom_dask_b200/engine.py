@@ -131,6 +131,17 @@ class CudaEngine:
                        "som_b200_neigh_apply")
         self.launches += 2
 
+    def epoch_tail(self, s, c, w, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, dist_kind, p,
+                   num, den, tables, ws):
+        """neigh_apply + merge + prepare_codebook(new W) + clear S, c: one cooperative kernel on small maps."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_epoch_tail(self._p(s), self._p(c), self._p(w), gx, gy, d, topology, neigh_kind,
+                                                    float(sigma), float(eta), float(std_coeff), int(bool(compact)),
+                                                    dist_kind, float(p), self._p(num), self._p(den), self._p(tables),
+                                                    tables.numel(), self._p(ws), ws.numel(), self._stream()),
+                       "som_b200_epoch_tail")
+        self.launches += 1
+
     def neigh_apply_sched(self, s, c, gx, gy, d, topology, neigh_kind, sched, epoch, std_coeff, compact, num, den, tables):
         """neigh_apply with sigma / eta read on the device from sched[2e], sched[2e+1], e = epoch[0]."""
         with torch.cuda.device(self.device):

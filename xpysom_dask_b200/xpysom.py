@@ -341,10 +341,12 @@ class XPySom:
                 graph.replay()
             eng.launches = launches0 + per_epoch * n_ep    # kernels actually executed (capture launches none)
         else:
+            # epoch = BMU search + per-BMU sums (one fused kernel) -> all-reduce of the shards -> everything else
+            # (eng.epoch_tail: apply, merge, preparation of the new codebook for the next search, clean S / c)
+            if n_ep > 0:
+                eng.prepare_codebook(w, dist_kind, p, ws)        # sc is already zero (eng.zeros above)
             for t in range(iter_beg, iter_end):
                 sig, eta = schedule(t)
-                sc.zero_()
-                eng.prepare_codebook(w, dist_kind, p, ws)
                 if prof is not None:
                     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                     ev[0].record()
@@ -363,9 +365,8 @@ class XPySom:
                     ev[1].record()
                     prof.append(ev)
                 reduce_shards()
-                eng.neigh_apply(S, c, gx, gy, d, topo, neigh, sig, eta, self._std_coeff, self.compact_support,
-                                num, den, tables)
-                eng.merge(w, num, den)
+                eng.epoch_tail(S, c, w, gx, gy, d, topo, neigh, sig, eta, self._std_coeff, self.compact_support,
+                               dist_kind, p, num, den, tables, ws)
                 if verbose:
                     print('\r [ %d / %d ]' % (t + 1, num_epochs), end='')
 
