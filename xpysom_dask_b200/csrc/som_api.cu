@@ -460,16 +460,21 @@ int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_ho
         int rc = som_b200_prepare_samples(b.x, n, d, dld, b.xs, b.st);
         if (rc) return rc;
     }
+    // epoch = BMU search + per-BMU sums -> everything else (som_b200_epoch_tail leaves the workspace prepared for the
+    // next search and S, c cleared)
+    if (n_epochs > 0) {
+        SOM_CUDA(cudaMemsetAsync(b.sc, 0, ((size_t)K * d + K) * 4, b.st));
+        const int rc = som_b200_prepare_codebook(b.w, K, d, cfg->dist_kind, cfg->p, b.ws, ws_bytes, b.st);
+        if (rc) return rc;
+    }
     for (int e = 0; e < n_epochs; ++e) {
         int rc;
-        SOM_CUDA(cudaMemsetAsync(b.sc, 0, ((size_t)K * d + K) * 4, b.st));
-        if ((rc = som_b200_prepare_codebook(b.w, K, d, cfg->dist_kind, cfg->p, b.ws, ws_bytes, b.st))) return rc;
         if ((rc = som_b200_epoch_accumulate(b.x, n, d, dld, b.xs, b.w, K, cfg->dist_kind, cfg->p, cfg->algo, S, c, nullptr,
                                             b.ws, ws_bytes, b.st))) return rc;
-        if ((rc = som_b200_neigh_apply(S, c, cfg->gx, cfg->gy, d, cfg->topology, cfg->neigh_kind, sigma_per_epoch[e],
-                                       eta_per_epoch[e], cfg->std_coeff, cfg->compact_support, num, den, b.tab,
-                                       som_b200_neigh_scratch_floats(cfg->gx, cfg->gy, d), b.st))) return rc;
-        if ((rc = som_b200_merge(b.w, num, den, K, d, b.st))) return rc;
+        if ((rc = som_b200_epoch_tail(S, c, b.w, cfg->gx, cfg->gy, d, cfg->topology, cfg->neigh_kind, sigma_per_epoch[e],
+                                      eta_per_epoch[e], cfg->std_coeff, cfg->compact_support, cfg->dist_kind, cfg->p, num, den,
+                                      b.tab, som_b200_neigh_scratch_floats(cfg->gx, cfg->gy, d), b.ws, ws_bytes, b.st)))
+            return rc;
     }
     SOM_CUDA(cudaMemcpyAsync(w_host, b.w, (size_t)K * d * 4, cudaMemcpyDeviceToHost, b.st));
     SOM_CUDA(cudaStreamSynchronize(b.st));
