@@ -46,7 +46,8 @@ constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * BH_BYTES;   // 64 KB
 constexpr int NUM_THREADS = 576;
 constexpr int CONV_WARP0 = 2, EPI_WARP0 = 6, SCAT_WARP0 = 14;
 constexpr int EPI_THREADS = 256;
-constexpr int NUM_BARS = 4 * STAGES + 4 + 4;
+constexpr int MAXS = 4;                  // ring slots per barrier family (A ring: 3 or 2, B ring: 3 or 4)
+constexpr int NUM_BARS = 5 * MAXS + 8;
 // stages | per-warp bias slices | merge buffers [2][BM] (float + int) | bmu hand-off [2][BM] | barriers | tmem slot | slack
 constexpr int EPI_STAGE_BYTES = 8 * 128 * 4;
 constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
@@ -120,6 +121,9 @@ __device__ __forceinline__ void umma_commit_2sm(uint32_t bar) {
 // UMMA tile of the pair: M = 256 (two CTAs x 128 lanes), N = 256
 constexpr uint32_t kIdesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
 
+// RES (one 32-feature block, D <= 32): the converted X tile of a row tile stays RESIDENT across its neuron tiles
+// (two A buffers, loaded and converted once per row tile; four B slots) instead of travelling with every stage.
+template <bool RES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
                const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
@@ -138,13 +142,19 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint64_t *bars   = reinterpret_cast<uint64_t *>(tail + 2 * BM * 8 + 2 * BM * 4);
     const uint32_t bar0 = smem_u32(bars);
     auto xfull_bar  = [&](int s) { return bar0 + 8u * s; };                     // local: X chunk landed
-    auto bfull_bar  = [&](int s) { return bar0 + 8u * (STAGES + s); };          // leader: both W' halves landed
-    auto ready_bar  = [&](int s) { return bar0 + 8u * (2 * STAGES + s); };      // leader: both converters done
-    auto empty_bar  = [&](int s) { return bar0 + 8u * (3 * STAGES + s); };      // local: stage consumed (multicast commit)
-    auto tfull_bar  = [&](int a) { return bar0 + 8u * (4 * STAGES + a); };      // local: accumulator complete (multicast commit)
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (4 * STAGES + 2 + a); };  // leader: both epilogues drained it
-    auto bfullq_bar = [&](int b) { return bar0 + 8u * (4 * STAGES + 4 + b); };  // local: BMUs of a tile published
-    auto bemptyq_bar = [&](int b) { return bar0 + 8u * (4 * STAGES + 6 + b); }; // local: scatter warps done with them
+    auto bfull_bar  = [&](int s) { return bar0 + 8u * (MAXS + s); };            // leader: both W' halves landed
+    auto ready_bar  = [&](int s) { return bar0 + 8u * (2 * MAXS + s); };        // leader: both converters done
+    auto aempty_bar = [&](int s) { return bar0 + 8u * (3 * MAXS + s); };        // local: A slot consumed (multicast commit)
+    auto bempty_bar = [&](int s) { return bar0 + 8u * (4 * MAXS + s); };        // local: B slot consumed (multicast commit)
+    auto tfull_bar  = [&](int a) { return bar0 + 8u * (5 * MAXS + a); };        // local: accumulator complete (multicast commit)
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (5 * MAXS + 2 + a); };    // leader: both epilogues drained it
+    auto bfullq_bar = [&](int b) { return bar0 + 8u * (5 * MAXS + 4 + b); };    // local: BMUs of a tile published
+    auto bemptyq_bar = [&](int b) { return bar0 + 8u * (5 * MAXS + 6 + b); };   // local: scatter warps done with them
+    // operand rings.  streaming: three 64 KB stages [A hi | A lo | B hi | B lo], A and B advance together;
+    // resident: two A buffers [A hi | A lo] (one per row tile) followed by four B slots [B hi | B lo]
+    constexpr int NA = RES ? 2 : STAGES, NB = RES ? 4 : STAGES;
+    auto a_off = [&](int s) { return (uint32_t)(RES ? s * 2 * A_BYTES : s * STAGE_BYTES); };
+    auto b_off = [&](int s) { return (uint32_t)(RES ? 2 * 2 * A_BYTES + s * 2 * BH_BYTES : s * STAGE_BYTES + 2 * A_BYTES); };
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + NUM_BARS);
     __shared__ unsigned int last_cta;
 
@@ -159,10 +169,8 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     const int probe = (acc.dbg == 9 && blockIdx.x == 0) ? 1 : 0;     // timeline probe (tools/bmu_probe.py)
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) {
-            tc::mbar_init(xfull_bar(s), 1); tc::mbar_init(bfull_bar(s), 1);
-            tc::mbar_init(ready_bar(s), 2 * 4); tc::mbar_init(empty_bar(s), 1);
-        }
+        for (int s = 0; s < NA; ++s) { tc::mbar_init(xfull_bar(s), 1); tc::mbar_init(ready_bar(s), 2 * 4); tc::mbar_init(aempty_bar(s), 1); }
+        for (int s = 0; s < NB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) {
             tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * EPI_THREADS / 32);
             tc::mbar_init(bfullq_bar(a), 4); tc::mbar_init(bemptyq_bar(a), 4);
@@ -179,19 +187,23 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     if (warp == 0) {
         // ===================== TMA producer (each CTA loads its own rows and its half of W') ===========
         {
-            uint32_t it = 0;
-            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
+            uint32_t it = 0, tile_it = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it)
                 for (int nt = 0; nt < num_n_tiles; ++nt)
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-                        const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
-                        tc::mbar_wait(empty_bar(s), ph ^ 1);
-                        const uint32_t st = smem_base + s * STAGE_BYTES;
+                        const uint32_t ia = RES ? tile_it : it;                  // A ring position
+                        const bool a_step = !RES || nt == 0;                     // this iteration brings a new X chunk
+                        const int sa = ia % NA, sb = it % NB;
+                        if (a_step) tc::mbar_wait(aempty_bar(sa), ((ia / NA) & 1) ^ 1);
+                        tc::mbar_wait(bempty_bar(sb), ((it / NB) & 1) ^ 1);
                         if (tc::elect_one()) {
-                            if (leader) tc::mbar_expect_tx(bfull_bar(s), 4 * BH_BYTES);   // hi+lo halves of both CTAs
-                            tc::mbar_expect_tx(xfull_bar(s), A_BYTES);
-                            tc::tma_load_2d(st, &map_x, kb * BK, pt * (2 * BM) + (int)rank * BM, xfull_bar(s));
-                            tma_load_2d_2sm(st + 2 * A_BYTES,            &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
-                            tma_load_2d_2sm(st + 2 * A_BYTES + BH_BYTES, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(s));
+                            if (a_step) {
+                                tc::mbar_expect_tx(xfull_bar(sa), A_BYTES);
+                                tc::tma_load_2d(smem_base + a_off(sa), &map_x, kb * BK, pt * (2 * BM) + (int)rank * BM, xfull_bar(sa));
+                            }
+                            if (leader) tc::mbar_expect_tx(bfull_bar(sb), 4 * BH_BYTES);  // hi+lo halves of both CTAs
+                            tma_load_2d_2sm(smem_base + b_off(sb),            &map_whi, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(sb));
+                            tma_load_2d_2sm(smem_base + b_off(sb) + BH_BYTES, &map_wlo, kb * BK, nt * BN + (int)rank * BNH, bfull_bar(sb));
                         }
                         __syncwarp();
                     }
@@ -199,26 +211,27 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     } else if (warp == 1) {
         // ===================== MMA issuer: one thread of the LEADER CTA drives both tensor cores ========
         if (leader) {
-            uint32_t it = 0, acc_it = 0;
-            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
+            uint32_t it = 0, acc_it = 0, tile_it = 0;
+            for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it)
                 for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                     const int a = acc_it & 1; const uint32_t aph = (acc_it >> 1) & 1;
                     tc::dbg_stamp(probe, 0, acc_it);
                     const uint32_t tmem_d = tmem_base + (uint32_t)(a * BN);
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-                        const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
-                        mbar_wait_cluster(bfull_bar(s), ph);           // operands first: they are ready long before
-                        mbar_wait_cluster(ready_bar(s), ph);           // the accumulator is, so these return at once
+                        const uint32_t ia = RES ? tile_it : it;
+                        const bool a_step = !RES || nt == 0;
+                        const int sa = ia % NA, sb = it % NB;
+                        mbar_wait_cluster(bfull_bar(sb), (it / NB) & 1);          // operands first: they are ready long before
+                        if (a_step) mbar_wait_cluster(ready_bar(sa), (ia / NA) & 1);   // the accumulator is
                         if (kb == 0) {
                             mbar_wait_cluster(tempty_bar(a), aph ^ 1);  // both CTAs' epilogues drained this accumulator
                             tc::dbg_stamp(probe, 1, acc_it);
                         }
                         tc::tc_fence_after();
                         if (kb == 0) tc::dbg_stamp(probe, 2, acc_it);
-                        const uint32_t st = smem_base + s * STAGE_BYTES;
-                        const uint64_t a_hi = tc::make_smem_desc(st), a_lo = tc::make_smem_desc(st + A_BYTES);
-                        const uint64_t b_hi = tc::make_smem_desc(st + 2 * A_BYTES);
-                        const uint64_t b_lo = tc::make_smem_desc(st + 2 * A_BYTES + BH_BYTES);
+                        const uint32_t sta = smem_base + a_off(sa), stb = smem_base + b_off(sb);
+                        const uint64_t a_hi = tc::make_smem_desc(sta), a_lo = tc::make_smem_desc(sta + A_BYTES);
+                        const uint64_t b_hi = tc::make_smem_desc(stb), b_lo = tc::make_smem_desc(stb + BH_BYTES);
                         // only the 8-column steps that hold real features are issued (the rest of the block is the
                         // TMA zero fill); the folded bias columns d..d+2 live in the hi*hi term alone
                         const int dl = acc.d - kb * BK;
@@ -234,7 +247,8 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                             }
                             if (kk < kk_h) umma_tf32_2sm(tmem_d, a_hi + off, b_hi + off, kIdesc2, 1);
                         }
-                        umma_commit_2sm(empty_bar(s));
+                        umma_commit_2sm(bempty_bar(sb));
+                        if (!RES || nt == num_n_tiles - 1) umma_commit_2sm(aempty_bar(sa));
                         if (kb == num_k_blocks - 1) {
                             umma_commit_2sm(tfull_bar(a));
                             tc::dbg_stamp(probe, 3, acc_it);
@@ -252,15 +266,15 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const int o = acc.d - ((num_k_blocks - 1) * BK + ((((t & 7) ^ ((t >> 3) & 7))) << 2));
         const bool f0 = o <= 0 && o >= -2, f1 = o <= 1 && o >= -1, f2 = o <= 2 && o >= 0, f3 = o <= 3 && o >= 1;
         const bool any_f = fold && (f0 || f1 || f2 || f3);
-        uint32_t it = 0;
+        uint32_t it = 0;            // A ring position: one item per row tile (resident) or per (row tile, neuron tile, k block)
         for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
-            for (int nt = 0; nt < num_n_tiles; ++nt)
+            for (int nt = 0; nt < (RES ? 1 : num_n_tiles); ++nt)
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-                    const int s = it % STAGES; const uint32_t ph = (it / STAGES) & 1;
+                    const int s = it % NA; const uint32_t ph = (it / NA) & 1;
                     const bool ones = any_f && kb == num_k_blocks - 1;
                     tc::mbar_wait(xfull_bar(s), ph);
-                    float4 *ahi = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES);
-                    float4 *alo = reinterpret_cast<float4 *>(smem + s * STAGE_BYTES + A_BYTES);
+                    float4 *ahi = reinterpret_cast<float4 *>(smem + a_off(s));
+                    float4 *alo = reinterpret_cast<float4 *>(smem + a_off(s) + A_BYTES);
 #pragma unroll
                     for (int i = 0; i < A_BYTES / 16 / 128; ++i) {
                         const int e = t + 128 * i;
@@ -420,8 +434,10 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     if ((rc = tc::make_map_2d(&mhi, ws + L.whi_off, (uint64_t)L.d_pad, (uint64_t)L.k_pad, (uint64_t)L.d_pad * 4, BK, BNH))) return rc;
     if ((rc = tc::make_map_2d(&mlo, ws + L.wlo_off, (uint64_t)L.d_pad, (uint64_t)L.k_pad, (uint64_t)L.d_pad * 4, BK, BNH))) return rc;
     static bool attr_set[64] = {};
-    if (tc::first_launch_on_device(attr_set))
-        SOM_CUDA(cudaFuncSetAttribute(bmu_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    if (tc::first_launch_on_device(attr_set)) {
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc2_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc2_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    }
     const int num_pair_tiles = (int)ceil_div(n, 2 * BM);
     const int num_n_tiles = L.k_pad / BN;
     const int num_k_blocks = L.d_pad / BK;
@@ -435,10 +451,15 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
     static const int dbg = tc::env_int("SOM_B200_DBG");
     acc.dbg = dbg;
-    return check_cuda(launch_pdl(bmu_tc2_kernel, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, st, mx, mhi, mlo,
-                                 reinterpret_cast<const float *>(ws + L.bias_off),
-                                 reinterpret_cast<const unsigned int *>(ws + L.gstat_off), n, num_pair_tiles, num_n_tiles,
-                                 num_k_blocks, bmu, best, acc), "bmu_tc2_kernel launch");
+    static const int no_res = tc::env_int("SOM_B200_TC2_STREAM");     // A/B measurements: force the streaming variant
+    const float *bias_p = reinterpret_cast<const float *>(ws + L.bias_off);
+    const unsigned int *gstat_p = reinterpret_cast<const unsigned int *>(ws + L.gstat_off);
+    const cudaError_t e = (num_k_blocks == 1 && !no_res)
+        ? launch_pdl(bmu_tc2_kernel<true>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, st, mx, mhi, mlo, bias_p, gstat_p, n,
+                     num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc)
+        : launch_pdl(bmu_tc2_kernel<false>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, st, mx, mhi, mlo, bias_p, gstat_p, n,
+                     num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+    return check_cuda(e, "bmu_tc2_kernel launch");
 }
 
 }  // namespace tc2
