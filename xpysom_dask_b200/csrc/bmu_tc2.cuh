@@ -7,7 +7,9 @@
 //     K=8: each CTA owns 128 sample rows (its own TMEM accumulators, 2 x 256 columns) and stages
 //     only HALF of every W' tile (128 neurons), so the codebook traffic L2->SMEM and the SMEM reads
 //     of the B operand are halved with respect to the one-CTA kernel;
-//   * 3-stage ring of 64 KB stages (X chunk hi | lo, W'hi half, W'lo half), SWIZZLE_128B;
+//   * operand rings in 192 KB of shared memory, SWIZZLE_128B.  Streaming (D > 32): three 64 KB stages
+//     (X chunk hi | lo, W'hi half, W'lo half).  Resident (D <= 32, one feature block): two A buffers (the X
+//     tile of a row tile is loaded and converted ONCE and reused by all its neuron tiles) + four B slots;
 //   * W' tiles arrive by TMA with the .cta_group::2 form: both CTAs' loads complete on the
 //     leader CTA's mbarrier; X chunks complete on a local mbarrier that the converter waits on;
 //   * tcgen05.commit ... .multicast::cluster releases the stage / publishes the accumulator in

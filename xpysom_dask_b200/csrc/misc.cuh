@@ -76,6 +76,7 @@ struct SplitOut {
     __half *w16hi, *w16lo;       // (k_pad, d_pad64) fp16 hi / lo
     float *wsinv;                // (k_pad)
     int d_pad, d_pad64;
+    int allow_fold;              // 0: keep the bias in the epilogue (A/B measurements)
 };
 
 // one warp: the operand copies of neuron `row`.  (No __restrict__ here on purpose: epoch_tail_kernel writes W, aux,
@@ -92,7 +93,7 @@ __device__ __forceinline__ void codebook_split_row(const float *W, int row, bool
     // TF32 copies: when the last 32-feature block has three spare columns, the epilogue bias is FOLDED into the
     // contraction: columns d, d+1, d+2 of W'hi carry the three TF32 pieces of bias_k (33 mantissa bits, more than
     // the fp32 accumulator keeps) and the kernel sets the matching X columns to 1; gstat[3] = 1 tells it so.
-    const bool fold = O.d_pad - d >= 3;
+    const bool fold = O.allow_fold && O.d_pad - d >= 3;
     if (row == 0 && lane == 0) { gstat[2] = uniform ? 1u : 0u; gstat[3] = fold ? 1u : 0u; }
     const float bk = bias[row];                        // |w|^2, 0 (cosine) or +inf (padding neuron)
     float b0 = tf32_rna(bk), b1 = 0.f, b2 = 0.f;

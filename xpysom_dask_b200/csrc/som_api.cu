@@ -122,6 +122,8 @@ static SplitOut split_out(const WsLayout &L, uint8_t *ws) {
     O.w16hi = reinterpret_cast<__half *>(ws + L.w16hi_off); O.w16lo = reinterpret_cast<__half *>(ws + L.w16lo_off);
     O.wsinv = reinterpret_cast<float *>(ws + L.wsinv_off);
     O.d_pad = L.d_pad; O.d_pad64 = L.d_pad64;
+    static const int no_fold = tc::env_int("SOM_B200_NO_FOLD");
+    O.allow_fold = no_fold ? 0 : 1;
     return O;
 }
 
