@@ -320,16 +320,25 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 5, acc_it);
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + h * (BN / 2));
 #pragma unroll 1
-                for (int c = 0; c < BN / 2 / 32; ++c) {
+                for (int c = 0; c < BN / 2 / 32 - 1; ++c) {
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait_dep(v);
                     if (fold) rm.chunk_nobias(v, col0 + c * 32);
                     else      rm.chunk(v, bs + c * 32, col0 + c * 32);
                 }
-                tc::tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+                {   // last chunk: once it is in registers the accumulator is free -- release it BEFORE the compares,
+                    // so the MMAs of the tile after next start a chunk's worth of work earlier
+                    constexpr int c = BN / 2 / 32 - 1;
+                    uint32_t v[32];
+                    tc::tmem_ld32(taddr + c * 32, v);
+                    tc::tmem_ld_wait_dep(v);
+                    tc::tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty_bar(a), 0));
+                    if (fold) rm.chunk_nobias(v, col0 + c * 32);
+                    else      rm.chunk(v, bs + c * 32, col0 + c * 32);
+                }
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 6, acc_it);
             }
             float best; int bidx;
