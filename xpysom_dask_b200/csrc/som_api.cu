@@ -333,16 +333,18 @@ int som_b200_epoch_tail(float *s_dev, float *c_dev, float *w_dev, int gx, int gy
     static const int no_fuse = tc::env_int("SOM_B200_TAIL_SEPARATE");
     const bool wide = d > 64 && K >= 512;
     const bool fused = !no_fuse && !separable && !wide && (int64_t)K * d <= (int64_t)1 << 20;
-    if (!fused) {
+    auto separate_launches = [&]() -> int {
         float *scratch = has_scratch ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
-        if ((rc = launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support,
-                                     num_dev, den_dev, tables_dev, scratch, di.sm, st))) return rc;
-        if ((rc = som_b200_merge(w_dev, num_dev, den_dev, K, d, stream))) return rc;
-        if ((rc = som_b200_prepare_codebook(w_dev, K, d, dist_kind, p, ws_dev, ws_bytes, stream))) return rc;
+        int r;
+        if ((r = launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support,
+                                    num_dev, den_dev, tables_dev, scratch, di.sm, st))) return r;
+        if ((r = som_b200_merge(w_dev, num_dev, den_dev, K, d, stream))) return r;
+        if ((r = som_b200_prepare_codebook(w_dev, K, d, dist_kind, p, ws_dev, ws_bytes, stream))) return r;
         SOM_CUDA(cudaMemsetAsync(s_dev, 0, (size_t)K * d * sizeof(float), st));
         SOM_CUDA(cudaMemsetAsync(c_dev, 0, (size_t)K * sizeof(float), st));
         return 0;
-    }
+    };
+    if (!fused) return separate_launches();
     TailArgs A;
     neigh_params(A.P, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support, tables_dev);
     A.sigma = sigma; A.dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
@@ -372,6 +374,10 @@ int som_b200_epoch_tail(float *s_dev, float *c_dev, float *w_dev, int gx, int gy
     void *args[] = {&A};
     // cooperative launch: all CTAs co-resident or the launch fails -- the grid barriers cannot deadlock
     const cudaError_t e = cudaLaunchCooperativeKernel((const void *)epoch_tail_kernel<4, 4>, dim3(grid), dim3(NB_THREADS), args, 0, st);
+    if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
+        (void)cudaGetLastError();                   // the GPU is shared / partitioned: same work, separate launches
+        return separate_launches();
+    }
     return check_cuda(e, "epoch_tail_kernel launch");
 }
 
