@@ -13,7 +13,6 @@ NCCL 28 us (NVLS reduces inside the switch; this kernel reads seven remote mailb
 therefore stays the default and this path is opt-in (``SOM_B200_PEER=1``).
 """
 import ctypes
-import os
 import socket
 import zlib
 
