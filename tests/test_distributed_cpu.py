@@ -73,6 +73,32 @@ def test_two_rank_shards_equal_single_process(kw):
     assert U.codebook_rel_err(one._weights, w_ref) < 1e-4
 
 
+def test_empty_shard_on_one_rank():
+    """Fewer rows than ranks (or an unlucky split): the rank without samples contributes zeros to the all-reduce
+    and keeps its replica of the codebook identical (the reference's Dask graph accepts any chunking)."""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from oracle_engine import OracleEngine
+    from xpysom_dask_b200 import XPySom
+    kw = dict(x=5, y=4, input_len=6, random_seed=2)
+    data = U.blobs(300, 6, seed=1)
+    single = XPySom(engine=OracleEngine(), **kw)
+    single.train(data, 3)
+    shards = [data, np.zeros((0, 6), dtype=np.float32)]
+    mgr = mp.Manager()
+    out = mgr.dict()
+    port = _free_port()
+    ctx = mp.get_context("spawn")
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, kw, shards, 3, out)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    np.testing.assert_array_equal(out[0], out[1])
+    assert U.codebook_rel_err(out[0], single._weights) < 1e-6
+
+
 def test_process_group_requires_initialised_backend():
     from oracle_engine import OracleEngine
     from xpysom_dask_b200 import XPySom

@@ -278,7 +278,7 @@ class XPySom:
         ws = eng.workspace(0, K, d)
         bmu = eng.empty(n, dtype=torch.int32)
         # per-row power-of-two scales for the fp16-split contraction: once per upload, not per epoch
-        if not self._wants_xscale(dist_kind):
+        if not self._wants_xscale(dist_kind) or n == 0:
             xscale = None
         elif chunks is None:
             # a device tensor that has not been written since the last call keeps its scales (one pass over the
@@ -324,7 +324,8 @@ class XPySom:
             def epoch_body():
                 sc.zero_()
                 eng.prepare_codebook(w, dist_kind, p, ws)
-                eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
+                if n > 0:
+                    eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
                 reduce_shards()
                 eng.neigh_apply_sched(S, c, gx, gy, d, topo, neigh, sched, epoch_idx, self._std_coeff,
                                       self.compact_support, num, den, tables)
@@ -359,7 +360,7 @@ class XPySom:
                         if xscale is not None:
                             xs_c = eng.prepare_samples(x[r0:r1], out=xscale[r0:r1])
                         eng.epoch_accumulate(x[r0:r1], w, dist_kind, p, algo, S, c, ws, bmu_out=bmu[r0:r1], xscale=xs_c)
-                else:
+                elif n > 0:                 # a rank may hold an EMPTY shard: it still joins the all-reduce and the tail
                     eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
                 if prof is not None:
                     ev[1].record()
