@@ -457,6 +457,15 @@ def test_row_scales_cached_per_device_tensor_and_refreshed_on_in_place_change():
     assert len(calls) == 3
 
 
+def test_train_on_empty_shard_leaves_codebook_untouched():
+    """No rows: no BMU search, zero sums, den == 0 everywhere -> _merge_updates keeps W (xpysom.py:451-455)."""
+    from xpysom_dask_b200 import XPySom
+    som = XPySom(6, 5, 8, random_seed=3)
+    w0 = som._weights.astype(np.float32).copy()
+    som.train(np.zeros((0, 8), dtype=np.float32), 3)
+    np.testing.assert_array_equal(som._weights, w0)
+
+
 def test_activate_distance_from_weights_topographic_error():
     """tests.py:66-90 of the reference and its own outputs on seeded maps (golden api.npz)."""
     from xpysom_dask_b200 import XPySom
