@@ -143,6 +143,33 @@ def run_reference(args, wl, rank):
     print(json.dumps(line), flush=True)
 
 
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor throughput of this GPU (TFLOP/s): the roofline denominator of the TF32 kernel (SURVEY 8d asks
+    for it to be measured on the box; MEASURED_PEAKS.json has bf16 only).  cuBLAS, 8192^3, best of 5 after warm-up."""
+    import torch
+    try:
+        old = torch.backends.cuda.matmul.allow_tf32
+        torch.backends.cuda.matmul.allow_tf32 = True
+        m = 8192
+        a = torch.randn(m, m, device=dev)
+        b = torch.randn(m, m, device=dev)
+        for _ in range(3):
+            torch.matmul(a, b)
+        best = 0.0
+        for _ in range(5):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b)
+            e1.record()
+            torch.cuda.synchronize()
+            best = max(best, 2.0 * m ** 3 / (e0.elapsed_time(e1) * 1e-3) / 1e12)
+        torch.backends.cuda.matmul.allow_tf32 = old
+        del a, b
+        return best
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------ GPU arm
 def run_gpu(args, wl, rank, world, local_rank):
     import torch
@@ -230,7 +257,12 @@ def run_gpu(args, wl, rank, world, local_rank):
             peak, peak_note = pk["bf16"], "dense bf16/fp16 tensor rate bf16_tflops from %s" % pk["source"]
         else:
             kernel = "bmu_tc2_kernel (tcgen05 kind::tf32, 3-term TF32 split, cta_group::2, argmin + per-BMU accumulate fused)"
-            peak, peak_note = pk["bf16"] / 2.0, "dense TF32 rate taken as half of bf16_tflops from %s" % pk["source"]
+            tf32 = measure_tf32_peak(dev)
+            if tf32:
+                peak, peak_note = tf32, ("dense TF32 rate measured here with a cuBLAS 8192^3 TF32 GEMM (MEASURED_PEAKS.json "
+                                         "holds bf16 only: %.0f TFLOP/s)" % pk["bf16"])
+            else:
+                peak, peak_note = pk["bf16"] / 2.0, "dense TF32 rate taken as half of bf16_tflops from %s" % pk["source"]
         ach = flops / (bmu_ms * 1e-3) / 1e12
         traffic = None
         tp = os.path.join(ROOT, "profiles", "traffic.json")
