@@ -88,9 +88,14 @@ size_t som_b200_workspace_bytes(int k, int d);
 int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, void *stream);
 
 /* Q: per-epoch codebook preparation.  Replaces the |w|^2 cache of
- * xpysom.py:529-539 and, for the tensor-core kernel, writes the split
- * (hi/lo TF32) operand copies of W into the workspace.  Must be called after
- * every change of W and before _bmu / _epoch_accumulate with the same ws. */
+ * xpysom.py:529-539 and, for the tensor-core kernels, writes the operand
+ * copies of the scaled codebook W' (-2 W or -W/|W|) into the workspace: the
+ * TF32 hi/lo split (with the bias folded into three spare feature columns
+ * when the last 32-feature block has them) and the fp16 hi/lo split times an
+ * exact power-of-two scale (one for the codebook, or one per neuron when the
+ * neurons' magnitudes spread over more than 2^12).  Must be called after
+ * every change of W and before _bmu / _epoch_accumulate with the same ws
+ * (som_b200_epoch_tail does it for the codebook it has just merged). */
 int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, float p,
                               void *ws_dev, size_t ws_bytes, void *stream);
 
