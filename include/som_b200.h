@@ -114,10 +114,17 @@ int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float 
 /* Full distance matrix out_dev (n, K), for the callers that want it (activate xpysom.py:323-354,
  * distance_from_weights :647-671, topographic_error :709-746).  mode 0: the activation distance as the
  * reference defines it (euclidean = partial -2x.w+|w|^2, cosine = 1 - nan_to_num(sim), L1 / Linf / Lp sums);
- * mode 1: the Euclidean distance sqrt(|x-w|^2) with nan_to_num (distances.py:33-43) whatever dist_kind. */
+ * mode 1: the Euclidean distance sqrt(|x-w|^2) with nan_to_num (distances.py:33-43) whatever dist_kind;
+ * mode 2: the full squared Euclidean distance (-2x.w+|w|^2)+|x|^2 of 'euclidean_no_opt' (distances.py:25-31). */
 int som_b200_distances(const float *x_dev, int64_t n, int d, int64_t ldx,
                        const float *w_dev, int k, int dist_kind, float p, int mode,
                        float *out_dev, void *ws_dev, size_t ws_bytes, void *stream);
+
+/* Best and second-best matching unit of every row on the Euclidean distance (sqrt form, nan_to_num), fused: what
+ * topographic_error needs (xpysom.py:709-746 argsorts the whole (n, K) matrix and keeps two columns).
+ * top2_dev receives 2 n flat indices: [2r] = best, [2r+1] = second best. */
+int som_b200_top2(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k,
+                  int32_t *top2_dev, void *ws_dev, size_t ws_bytes, void *stream);
 
 /* U (first half): S[bmu[r], :] += X[r, :], c[bmu[r]] += 1 for the n rows.
  * Replaces the sample side of g^T X and sum(g) in XPySom._update

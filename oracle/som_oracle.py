@@ -329,13 +329,16 @@ def bmu_flat(spec: SomSpec, x, w, w_sq=None):
     return d.argmin(axis=1)
 
 
-def update_block(spec: SomSpec, x, w, eta, sig, w_sq=None):
-    """U: one block of samples -> (num (gx,gy,D), den (gx,gy,1))  (xpysom.py:420-443)."""
+def update_block(spec: SomSpec, x, w, eta, sig, w_sq=None, return_bmu=False):
+    """U: one block of samples -> (num (gx,gy,D), den (gx,gy,1))  (xpysom.py:420-443).
+    return_bmu: also hand back the flat BMU indices the block used (checker convenience)."""
     flat = bmu_flat(spec, x, w, w_sq)
     bi, bj = np.unravel_index(flat, (spec.gx, spec.gy))
     g = neighborhood(spec, bi, bj, sig) * eta
     den = np.sum(g, axis=0)[:, :, None]
     num = np.dot(g.reshape(g.shape[0], -1).T, x).reshape(w.shape)
+    if return_bmu:
+        return num, den, flat
     return num, den
 
 
@@ -360,9 +363,8 @@ def epoch(spec: SomSpec, data32, w32, t: int, T: int, return_bmu=False):
     bmus = []
     for s in range(0, len(data32), spec.n_parallel):
         blk = data32[s:s + spec.n_parallel]
-        if return_bmu:
-            bmus.append(bmu_flat(spec, blk, w32, w_sq))
-        a, b = update_block(spec, blk, w32, eta, sig, w_sq)
+        a, b, flat = update_block(spec, blk, w32, eta, sig, w_sq, return_bmu=True)
+        bmus.append(flat)
         num += a
         den += b
     w_new = merge(w32, num, den)

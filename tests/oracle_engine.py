@@ -1,6 +1,6 @@
 """CPU stand-in for CudaEngine, for tests of the HOST logic only (sharding, the per-epoch
 all-reduce, API plumbing).  Every method is answered by the oracle; it is never shipped and
-never selected by the product code (XPySom only takes it through the `engine=` test hook)."""
+never selected by the product code (the tests assign it to the private `_engine` attribute of an XPySom instance)."""
 import numpy as np
 import torch
 

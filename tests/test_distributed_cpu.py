@@ -1,7 +1,8 @@
 """The N>1 path on CPU: two `gloo` ranks, each holding one shard of the samples, one all-reduce
 of the per-BMU sums [S | c] per epoch, replicated codebook (replaces the Dask block
-graph of xpysom.py:545-558).  Device compute is answered by the oracle through the `engine=` test
-hook, so this covers the host logic only: sharding, the collective, replicated apply/merge."""
+graph of xpysom.py:545-558).  Device compute is answered by the oracle through the private `_engine`
+attribute,
+so this covers the host logic only: sharding, the collective, replicated apply/merge."""
 import os
 import socket
 
@@ -29,7 +30,8 @@ def _worker(rank, world, port, kw, shards, T, out):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     from oracle_engine import OracleEngine
     from xpysom_dask_b200 import XPySom
-    som = XPySom(engine=OracleEngine(), process_group=True, **kw)
+    som = XPySom(process_group=True, **kw)
+    som._engine = OracleEngine()
     som.train(shards[rank], T)
     out[rank] = som._weights.copy()
     dist.destroy_process_group()
@@ -47,7 +49,8 @@ def test_two_rank_shards_equal_single_process(kw):
     from xpysom_dask_b200 import XPySom
     data = U.blobs(1001, kw["input_len"], seed=8)              # ragged split: 501 + 500 rows
     T = 4
-    single = XPySom(engine=OracleEngine(), **kw)
+    single = XPySom(**kw)
+    single._engine = OracleEngine()
     single.train(data, T)
 
     shards = [data[:501], data[501:]]
@@ -68,7 +71,8 @@ def test_two_rank_shards_equal_single_process(kw):
     spec = so.SomSpec(gx=kw["x"], gy=kw["y"], dim=kw["input_len"], random_seed=kw["random_seed"], n_parallel=4000,
                       **{k: v for k, v in kw.items() if k not in ("x", "y", "input_len", "random_seed")})
     w_ref = so.epoch(spec, data, np.asarray(so.init_weights(spec), dtype=np.float32), 0, T)
-    one = XPySom(engine=OracleEngine(), **kw)
+    one = XPySom(**kw)
+    one._engine = OracleEngine()
     one.train(data, T, iter_beg=0, iter_end=1)
     assert U.codebook_rel_err(one._weights, w_ref) < 1e-4
 
@@ -82,7 +86,8 @@ def test_empty_shard_on_one_rank():
     from xpysom_dask_b200 import XPySom
     kw = dict(x=5, y=4, input_len=6, random_seed=2)
     data = U.blobs(300, 6, seed=1)
-    single = XPySom(engine=OracleEngine(), **kw)
+    single = XPySom(**kw)
+    single._engine = OracleEngine()
     single.train(data, 3)
     shards = [data, np.zeros((0, 6), dtype=np.float32)]
     mgr = mp.Manager()
@@ -102,6 +107,7 @@ def test_empty_shard_on_one_rank():
 def test_process_group_requires_initialised_backend():
     from oracle_engine import OracleEngine
     from xpysom_dask_b200 import XPySom
-    som = XPySom(5, 5, 3, engine=OracleEngine(), process_group=True)
+    som = XPySom(5, 5, 3, process_group=True)
+    som._engine = OracleEngine()
     with pytest.raises(RuntimeError):
         som.train(np.zeros((4, 3), np.float32), 1)

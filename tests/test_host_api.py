@@ -17,7 +17,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     from xpysom_dask_b200 import _lib
     lib = _lib.load()
     header = open(os.path.join(ROOT, "include", "som_b200.h")).read()
-    declared = set(re.findall(r"\b(som_b200_[a-z_]+)\s*\(", header))
+    declared = set(re.findall(r"\b(som_b200_[a-z0-9_]+)\s*\(", header))
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)

@@ -13,6 +13,7 @@ import numpy as np
 import pytest
 
 from oracle import som_oracle as so
+import som_testutil as U
 
 G = os.path.join(os.path.dirname(__file__), "golden")
 
@@ -248,3 +249,15 @@ def test_unknown_names_raise():
         so.activation_distance("ridethewave", np.zeros((1, 1)), np.zeros((1, 1)))
     with pytest.raises(ValueError):
         so.SomSpec(gx=5, gy=5, dim=1, topology="hexagonal", neighborhood_function="triangle")
+
+
+def test_separable_factors_reproduce_the_full_table():
+    """som_testutil.separable_factors (used by the config-scale GPU parity tests to avoid a K x K table at K = 10^4):
+    h((bi,bj),(i,j)) = A[bi,i] B[bj,j] / h00 for the product-form neighbourhoods of neighborhoods.py:33,112,130."""
+    for fn, compact in [("gaussian", False), ("gaussian", True), ("bubble", False), ("triangle", False), ("triangle", True)]:
+        for sig in (3.3, np.float64(1.7), 0.9):
+            spec = so.SomSpec(gx=9, gy=6, dim=3, neighborhood_function=fn, compact_support=compact)
+            H = so.neighborhood_table(spec, sig).astype(np.float64).reshape(9, 6, 9, 6)
+            A, B, h00 = U.separable_factors(spec, sig)
+            H2 = np.einsum("ai,bj->abij", A, B) / h00
+            assert np.abs(H - H2).max() <= 1e-7 * np.abs(H).max(), (fn, compact, sig)

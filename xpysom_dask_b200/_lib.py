@@ -33,6 +33,8 @@ SIGNATURES = {
     "som_b200_distances": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_float, ctypes.c_int, c_f32p, ctypes.c_void_p,
                                           ctypes.c_size_t, ctypes.c_void_p]),
+    "som_b200_top2": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int, c_i32p,
+                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "som_b200_accumulate": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_i32p, ctypes.c_int,
                                            c_f32p, c_f32p, ctypes.c_void_p]),
     "som_b200_epoch_accumulate": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, c_f32p,

@@ -170,7 +170,8 @@ bmu_simt_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx,
 // value written:  0 = the activation distance as the reference defines it (euclidean: partial
 // -2 x.w + |w|^2, distances.py:23; cosine: 1 - nan_to_num(x.w / sqrt(|x|^2 |w|^2)), distances.py:55-59;
 // manhattan / chebyshev / norm_p sums), 1 = Euclidean distance sqrt(max(0, |x|^2 - 2 x.w + |w|^2)) with
-// nan_to_num (distances.py:33-43), whatever DIST.
+// nan_to_num (distances.py:33-43), whatever DIST, 2 = the full squared Euclidean distance
+// (-2 x.w + |w|^2) + |x|^2 of 'euclidean_no_opt' (distances.py:25-31).
 template <int DIST>
 __global__ void __launch_bounds__(ST_THREADS, 2)
 dist_matrix_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, const float *__restrict__ W, int k,
@@ -211,7 +212,7 @@ dist_matrix_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, c
                 xs[i] = fmaf(a[i], a[i], xs[i]);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
-                    if (mode == 1) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    if (mode != 0) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
                     else simt_accum<DIST>(acc[i][j], a[i], b[j], p);
                 }
             }
@@ -230,6 +231,8 @@ dist_matrix_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, c
             if (mode == 1) {
                 v = sqrtf((fmaf(-2.f, acc[i][j], ws)) + xs[i]);             // (-2 x.w + |w|^2) + |x|^2, then sqrt
                 if (isnan(v)) v = 0.f;                                       // negative round-off -> NaN -> 0
+            } else if (mode == 2) {
+                v = fmaf(-2.f, acc[i][j], ws) + xs[i];
             } else if (DIST == SOM_DIST_EUCLIDEAN) {
                 v = fmaf(-2.f, acc[i][j], ws);
             } else if (DIST == SOM_DIST_COSINE) {
@@ -243,6 +246,105 @@ dist_matrix_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, c
             out[gr * (int64_t)k + col] = v;
         }
     }
+}
+
+
+// Best and second-best matching unit per row on the Euclidean distance sqrt(|x|^2 - 2 x.w + |w|^2) with nan_to_num
+// (distances.py:33-43), fused: what topographic_error needs (xpysom.py:709-746 argsorts the full (n, K) matrix and
+// keeps two columns).  Same tiling as bmu_simt_kernel; each thread keeps (d1, i1, d2, i2) for its 8 rows and the 16
+// threads of a row merge by shuffles.  Ties are ordered by index (numpy's argsort leaves them unspecified).
+__device__ __forceinline__ void top2_insert(float &d1, int &i1, float &d2, int &i2, float v, int idx) {
+    if (v < d1 || (v == d1 && idx < i1)) { d2 = d1; i2 = i1; d1 = v; i1 = idx; }
+    else if (v < d2 || (v == d2 && idx < i2)) { d2 = v; i2 = idx; }
+}
+
+__global__ void __launch_bounds__(ST_THREADS, 2)
+top2_simt_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, const float *__restrict__ W, int k,
+                 const float *__restrict__ wsq, int32_t *__restrict__ out2) {
+    __shared__ __align__(16) float Xs[ST_DK][ST_LD];
+    __shared__ __align__(16) float Ws[ST_DK][ST_LD];
+    const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+    const int lrow = tid >> 1, lcol = (tid & 1) * 8;
+    for (int64_t row0 = (int64_t)blockIdx.x * ST_TM; row0 < n; row0 += (int64_t)gridDim.x * ST_TM) {
+        float d1[8], d2[8];
+        int i1[8], i2[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { d1[i] = d2[i] = INFINITY; i1[i] = i2[i] = 0x7fffffff; }
+        for (int n0 = 0; n0 < k; n0 += ST_TN) {
+            float acc[8][8], xs[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { xs[i] = 0.f;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f; }
+            for (int d0 = 0; d0 < d; d0 += ST_DK) {
+                float xv[8], wv[8];
+                const int64_t gr = row0 + lrow;
+                const int gn = n0 + lrow, gc = d0 + lcol;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    xv[e] = (gr < n && gc + e < d) ? __ldg(X + gr * ldx + gc + e) : 0.f;
+                    wv[e] = (gn < k && gc + e < d) ? __ldg(W + (int64_t)gn * d + gc + e) : 0.f;
+                }
+                __syncthreads();
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { Xs[lcol + e][lrow] = xv[e]; Ws[lcol + e][lrow] = wv[e]; }
+                __syncthreads();
+#pragma unroll
+                for (int kk = 0; kk < ST_DK; ++kk) {
+                    float a[8], b[8];
+                    const float4 a0 = *reinterpret_cast<const float4 *>(&Xs[kk][ty * 8]);
+                    const float4 a1 = *reinterpret_cast<const float4 *>(&Xs[kk][ty * 8 + 4]);
+                    const float4 b0 = *reinterpret_cast<const float4 *>(&Ws[kk][tx * 4]);
+                    const float4 b1 = *reinterpret_cast<const float4 *>(&Ws[kk][64 + tx * 4]);
+                    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+                    b[0] = b0.x; b[1] = b0.y; b[2] = b0.z; b[3] = b0.w; b[4] = b1.x; b[5] = b1.y; b[6] = b1.z; b[7] = b1.w;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        xs[i] = fmaf(a[i], a[i], xs[i]);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int col = n0 + (j < 4 ? tx * 4 + j : 64 + tx * 4 + (j - 4));
+                if (col < k) {
+                    const float ws = __ldg(wsq + col);
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        float v = sqrtf(fmaf(-2.f, acc[i][j], ws) + xs[i]);
+                        if (isnan(v)) v = 0.f;
+                        top2_insert(d1[i], i1[i], d2[i], i2[i], v, col);
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) {
+                const float od1 = __shfl_xor_sync(0xffffffffu, d1[i], o), od2 = __shfl_xor_sync(0xffffffffu, d2[i], o);
+                const int oi1 = __shfl_xor_sync(0xffffffffu, i1[i], o), oi2 = __shfl_xor_sync(0xffffffffu, i2[i], o);
+                top2_insert(d1[i], i1[i], d2[i], i2[i], od1, oi1);
+                top2_insert(d1[i], i1[i], d2[i], i2[i], od2, oi2);
+            }
+            const int64_t gr = row0 + ty * 8 + i;
+            if (tx == 0 && gr < n) {
+                out2[2 * gr] = i1[i] == 0x7fffffff ? 0 : i1[i];
+                out2[2 * gr + 1] = i2[i] == 0x7fffffff ? (k > 1 ? 1 : 0) : i2[i];
+            }
+        }
+    }
+}
+
+inline int launch_top2_simt(const float *X, int64_t n, int d, int64_t ldx, const float *W, int k, const float *wsq,
+                            int32_t *out2, int sm_count, cudaStream_t st) {
+    int64_t tiles = ceil_div(n, ST_TM);
+    int grid = (int)(tiles < (int64_t)sm_count * 8 ? tiles : (int64_t)sm_count * 8);
+    if (grid < 1) grid = 1;
+    top2_simt_kernel<<<grid, ST_THREADS, 0, st>>>(X, n, d, ldx, W, k, wsq, out2);
+    return check_cuda(cudaGetLastError(), "top2_simt_kernel launch");
 }
 
 inline int launch_dist_matrix(const float *X, int64_t n, int d, int64_t ldx, const float *W, int k, int dist_kind,

@@ -194,7 +194,7 @@ int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float 
 int som_b200_distances(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int dist_kind,
                        float p, int mode, float *out_dev, void *ws_dev, size_t ws_bytes, void *stream) {
     SOM_REQUIRE(w_dev && ws_dev && out_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "distances: bad argument");
-    SOM_REQUIRE(known_dist(dist_kind) && (mode == 0 || mode == 1), SOM_E_BADARG, "distances: unknown kind / mode");
+    SOM_REQUIRE(known_dist(dist_kind) && mode >= 0 && mode <= 2, SOM_E_BADARG, "distances: unknown kind / mode");
     if (n == 0) return 0;
     SOM_REQUIRE(x_dev, SOM_E_BADARG, "distances: x is NULL");
     const WsLayout L = ws_layout(k, d);
@@ -207,6 +207,23 @@ int som_b200_distances(const float *x_dev, int64_t n, int d, int64_t ldx, const 
     int rc = check_cuda(cudaGetLastError(), "row_sq_kernel launch");
     if (rc) return rc;
     return launch_dist_matrix(x_dev, n, d, ldx, w_dev, k, dist_kind, p, mode, wsq, out_dev, (cudaStream_t)stream);
+}
+
+int som_b200_top2(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int32_t *top2_dev,
+                  void *ws_dev, size_t ws_bytes, void *stream) {
+    SOM_REQUIRE(w_dev && ws_dev && top2_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "top2: bad argument");
+    if (n == 0) return 0;
+    SOM_REQUIRE(x_dev, SOM_E_BADARG, "top2: x is NULL");
+    const WsLayout L = ws_layout(k, d);
+    SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "top2: workspace %zu < %zu bytes", ws_bytes, L.total);
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    uint8_t *ws = static_cast<uint8_t *>(ws_dev);
+    float *wsq = reinterpret_cast<float *>(ws + L.amax_off);        // as som_b200_distances: no BMU kernel reads this slot
+    row_sq_kernel<<<(unsigned)ceil_div(k, 8), 256, 0, (cudaStream_t)stream>>>(w_dev, k, d, wsq);
+    if ((rc = check_cuda(cudaGetLastError(), "row_sq_kernel launch"))) return rc;
+    return launch_top2_simt(x_dev, n, d, ldx, w_dev, k, wsq, top2_dev, di.sm, (cudaStream_t)stream);
 }
 
 int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const int32_t *bmu_dev, int k,

@@ -93,7 +93,7 @@ class CudaEngine:
         return bmu_out
 
     def distances(self, x, w, dist_kind, p, mode, ws):
-        """(n, K) distance matrix: mode 0 = activation distance, 1 = Euclidean distance (sqrt)."""
+        """(n, K) distance matrix: mode 0 = activation distance, 1 = Euclidean distance (sqrt), 2 = squared Euclidean."""
         n, d = x.shape
         k = w.shape[0]
         out = self.empty(n, k)
@@ -101,6 +101,16 @@ class CudaEngine:
             _lib.check(self.lib.som_b200_distances(self._p(x), n, d, x.stride(0), self._p(w), k, dist_kind, float(p),
                                                    int(mode), self._p(out), self._p(ws), ws.numel(), self._stream()),
                        "som_b200_distances")
+        self.launches += 2
+        return out
+
+    def top2(self, x, w, ws):
+        """(n, 2) int32: best and second-best unit of every row on the Euclidean distance (fused, no (n, K) matrix)."""
+        n, d = x.shape
+        out = self.empty(n, 2, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_top2(self._p(x), n, d, x.stride(0), self._p(w), w.shape[0], self._p(out),
+                                              self._p(ws), ws.numel(), self._stream()), "som_b200_top2")
         self.launches += 2
         return out
 

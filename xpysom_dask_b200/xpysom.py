@@ -64,14 +64,13 @@ class XPySom:
                  decay_function='exponential', neighborhood_function='gaussian', std_coeff=0.5,
                  topology='rectangular', activation_distance='euclidean', activation_distance_kwargs={},
                  random_seed=None, n_parallel=0, compact_support=False, xp=None, use_dask=False,
-                 dask_chunks='auto', *, device=None, algo='auto', process_group=None, engine=None,
-                 use_cuda_graph=False):
+                 dask_chunks='auto', *, device=None, algo='auto', process_group=None, use_cuda_graph=False):
         """Same arguments as the reference constructor (xpysom.py:73-82).
 
         Keyword-only additions: ``device`` (CUDA device of this process),
         ``algo`` ('auto' | 'tc' | 'simt': which BMU kernel), ``process_group``
         (a torch.distributed group, or True for the default group: this process
-        holds one shard of the samples), ``engine`` (test hook) and ``use_cuda_graph`` (replay one
+        holds one shard of the samples) and ``use_cuda_graph`` (replay one
         captured CUDA graph per epoch instead of launching the epoch's ~10 kernels one by one; capture
         costs a few milliseconds, so it only pays off for runs of several hundred epochs on small maps).
         """
@@ -128,7 +127,7 @@ class XPySom:
         self._algo = algo
         self._device = device
         self._process_group = process_group
-        self._engine = engine
+        self._engine = None                # the CudaEngine of this process, created on first use
         self._use_cuda_graph = bool(use_cuda_graph)
         self._profile = False              # bench.py: record CUDA events around the BMU / accumulate kernels
         self._profile_events = []
@@ -410,7 +409,9 @@ class XPySom:
 
     def activate(self, x):
         """Activation map of x: the (n, K) matrix of activation distances (xpysom.py:323-354)."""
-        return self._distance_matrix(x, 0).cpu().numpy()
+        # 'euclidean_no_opt' is the full squared distance (distances.py:25-31); 'euclidean' drops the row term |x|^2
+        mode = 2 if self._activation_distance_name == 'euclidean_no_opt' else 0
+        return self._distance_matrix(x, mode).cpu().numpy()
 
     def distance_from_weights(self, data, weights_gpu=None):
         """d[i, j] = Euclidean distance between data[i] and the j-th weight (xpysom.py:647-671; the second
@@ -424,15 +425,12 @@ class XPySom:
         if np.prod(self._weights.shape) == 1:
             warn('The topographic error is not defined for a 1-by-1 map.')
             return np.nan
-        gx, gy, _ = self._shape()
-        n = len(data)
-        b2 = []
-        step = max(1, (1 << 26) // (gx * gy))           # bound the (rows, K) matrix to 256 MB
-        t = _as_f32_matrix(data)
-        for s0 in range(0, n, step):
-            dmat = self._distance_matrix(t[s0:s0 + step], 1)
-            b2.append(torch.topk(dmat, 2, dim=1, largest=False, sorted=True).indices.cpu().numpy())
-        b2 = np.concatenate(b2)
+        eng = self._get_engine()
+        gx, gy, d = self._shape()
+        w = self._weights_to_device(eng)
+        x = self._data_to_device(eng, data)
+        # best and second-best unit per row from ONE fused kernel (the reference argsorts the (n, K) matrix)
+        b2 = eng.top2(x, w, eng.workspace(0, gx * gy, d)).cpu().numpy().astype(np.int64)
         bx, by = np.unravel_index(b2, (gx, gy))
         if self.topology == 'rectangular':
             return ((np.abs(np.diff(bx)) > 1) | (np.abs(np.diff(by)) > 1)).mean().item()
