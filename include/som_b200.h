@@ -25,6 +25,14 @@
  *     The reference's numerator/denominator (xpysom.py:436-441) are
  *     num = eta * H^T S, den = eta * H^T c with H[b,k] = h(bmu=b, neuron=k);
  *     the identity is checked in tests/test_oracle_golden.py.
+ *   - S and c are ACCUMULATED EXACTLY, as 64-bit fixed-point integers (one power-of-two scale per feature
+ *     column, from the column's largest magnitude and the total sample count): integer additions are
+ *     associative, so the sums do not depend on the order of the GPU's atomics, on tiling, or on how the
+ *     samples are sharded over GPUs (an integer all-reduce of the accumulator gives every rank the bits one
+ *     GPU would have computed).  The accumulator is `som_b200_accum_words(k, d)` uint64 words:
+ *     [S: k rows of (d rounded up to even) words | counts: k words], 16-byte aligned, zero before the first
+ *     accumulate of an epoch.  som_b200_accum_finalize / som_b200_epoch_tail round it ONCE to the fp32
+ *     S, c that the neighbourhood apply reads, and clear it.
  */
 #ifndef SOM_B200_H
 #define SOM_B200_H
@@ -36,7 +44,7 @@
 extern "C" {
 #endif
 
-#define SOM_B200_ABI_VERSION 1
+#define SOM_B200_ABI_VERSION 2
 
 /* activation distances: DistanceFunction table, distances.py:162-170 */
 enum som_dist {
@@ -82,10 +90,34 @@ int som_b200_device_info(int *sm_count, int *cc, size_t *smem_per_block_optin);
  * for a codebook of K neurons x D features (prepared operand copies, |w|^2). */
 size_t som_b200_workspace_bytes(int k, int d);
 
-/* Per-row power-of-two scales of the samples for SOM_ALGO_TC_3XF16: xscale_dev (n floats) receives
- * 2^a_r with max_c |x[r,c]| * 2^a_r in [2^14, 2^15).  One pass over X; valid as long as X is
- * unchanged (the host class computes it once per upload, not per epoch). */
-int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, void *stream);
+/* Which BMU kernel `algo` resolves to for this distance / feature count (SOM_ALGO_AUTO: a tensor-core kernel for
+ * the two contraction distances whenever TMA can address the rows and d >= 8: the fp16-split one when row scales
+ * are available, the TF32 one otherwise; SIMT for everything else). */
+int som_b200_pick_algo(int algo, int dist_kind, int d, int rows_tma_addressable, int has_row_scales);
+
+/* One-time statistics of an uploaded sample matrix (one pass each; valid as long as X is unchanged -- the host
+ * class computes them once per upload, not per epoch).  Either output may be NULL.
+ *   xscale_dev (n floats): per-row power-of-two scales for SOM_ALGO_TC_3XF16, 2^a_r with
+ *                          max_c |x[r,c]| * 2^a_r in [2^14, 2^15);
+ *   colmax_dev (d floats): per-column largest magnitude, MAX-ACCUMULATED into the buffer (zero it before the first
+ *                          part of an upload; sharded runs all-reduce it with MAX): the input of
+ *                          som_b200_accum_scales. */
+int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, float *colmax_dev,
+                             void *stream);
+
+/* Scales of the exact accumulation: qscale[c] = 2^q_c, qinv[c] = 2^-q_c (each d rounded up to a multiple of 4
+ * floats, 16-byte aligned), q_c = 62 - (exponent of colmax[c] + 1) - ceil(log2 n_total): n_total samples (over
+ * all shards) cannot overflow 63 bits.  Every shard of one job must use the same scales. */
+int    som_b200_accum_scales(const float *colmax_dev, int d, double n_total, float *qscale_dev, float *qinv_dev, void *stream);
+size_t som_b200_accum_words(int k, int d);
+
+/* Exact accumulator -> fp32 S (k, d) and c (k), one rounding per element; the accumulator is cleared. */
+int som_b200_accum_finalize(uint64_t *acc_dev, const float *qinv_dev, int k, int d, float *s_dev, float *c_dev, void *stream);
+/* Epochs whose samples arrive in several parts with different column scales (chunked uploads, blocks streamed from
+ * host memory): after each part, fold the accumulator into running fp64 sums sd_dev (k*d + k doubles, zero before
+ * the first part; the accumulator is cleared); after the last part round them once to fp32 (sd_dev is cleared). */
+int som_b200_accum_fold(uint64_t *acc_dev, const float *qinv_dev, int k, int d, double *sd_dev, void *stream);
+int som_b200_accum_finalize_f64(double *sd_dev, int k, int d, float *s_dev, float *c_dev, void *stream);
 
 /* Q: per-epoch codebook preparation.  Replaces the |w|^2 cache of
  * xpysom.py:529-539 and, for the tensor-core kernels, writes the operand
@@ -126,12 +158,11 @@ int som_b200_distances(const float *x_dev, int64_t n, int d, int64_t ldx,
 int som_b200_top2(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k,
                   int32_t *top2_dev, void *ws_dev, size_t ws_bytes, void *stream);
 
-/* U (first half): S[bmu[r], :] += X[r, :], c[bmu[r]] += 1 for the n rows.
- * Replaces the sample side of g^T X and sum(g) in XPySom._update
- * (xpysom.py:434-441).  S and c are accumulated into (zero them per epoch). */
+/* U (first half): S[bmu[r], :] += X[r, :], c[bmu[r]] += 1 for the n rows, exactly (see "accumulators" above).
+ * Replaces the sample side of g^T X and sum(g) in XPySom._update (xpysom.py:434-441). */
 int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
                         const int32_t *bmu_dev, int k,
-                        float *s_dev, float *c_dev, void *stream);
+                        const float *qscale_dev, uint64_t *acc_dev, void *stream);
 
 /* W+U fused: som_b200_bmu followed by som_b200_accumulate on one shard of rows
  * — the unit of distributed work (`_update` on one Dask block, xpysom.py:551).
@@ -139,7 +170,7 @@ int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
  * ws must also hold n int32 (see som_b200_shard_workspace_bytes). */
 int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const float *xscale_dev,
                               const float *w_dev, int k, int dist_kind, float p, int algo,
-                              float *s_dev, float *c_dev, int32_t *bmu_dev,
+                              const float *qscale_dev, uint64_t *acc_dev, int32_t *bmu_dev,
                               void *ws_dev, size_t ws_bytes, void *stream);
 size_t som_b200_shard_workspace_bytes(int64_t n, int k, int d);
 
@@ -154,10 +185,12 @@ int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy,
                          int topology, int neigh_kind, double sigma, double eta,
                          double std_coeff, int compact_support,
                          float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats, void *stream);
-/* minimum scratch (factor tables only: the direct K^2 D kernel is used) */
+/* minimum scratch (factor tables only: the direct K^2 D kernel, reduction over BMUs not sliced) */
 size_t som_b200_neigh_table_floats(int gx, int gy);
 /* scratch that also holds the intermediates of the two-pass separable path (rectangular gaussian / bubble /
- * triangle on maps of >= 4096 neurons: 2 K (gx+gy) D flops instead of 2 K^2 D) */
+ * triangle on maps of >= 4096 neurons: 2 K (gx+gy) D flops instead of 2 K^2 D) and the per-slice partial blocks
+ * of the direct kernel (small maps slice the reduction over BMUs to fill the GPU; the slices are summed in slice
+ * order, never with atomics, so num / den are bit-reproducible) */
 size_t som_b200_neigh_scratch_floats(int gx, int gy, int d);
 
 /* Graph-replay variant of som_b200_neigh_apply: sigma and the learning rate are read on the device,
@@ -174,15 +207,17 @@ int som_b200_epoch_advance(int *epoch_dev, void *stream);
 int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev,
                    int k, int d, void *stream);
 
-/* Everything between two BMU searches in one call: som_b200_neigh_apply (K4) + som_b200_merge (M) +
- * som_b200_prepare_codebook of the NEW codebook (Q, xpysom.py:529-539, for the next epoch) + S, c cleared
- * (xpysom.py:516-527).  On small maps (direct neighbourhood kernel with 64x64 tiles: at most 64 features or
+/* Everything between two BMU searches in one call: som_b200_accum_finalize (when acc_dev != NULL; with NULL, s_dev
+ * and c_dev must already hold the epoch's fp32 sums) + som_b200_neigh_apply (K4) + som_b200_merge (M) +
+ * som_b200_prepare_codebook of the NEW codebook (Q, xpysom.py:529-539, for the next epoch); the accumulator is
+ * left cleared (xpysom.py:516-527).  On small maps (direct neighbourhood kernel with 64x64 tiles: at most 64 features or
  * fewer than 512 neurons, K*D <= 2^20) this is ONE cooperative kernel with grid-wide barriers between the
  * phases instead of ten stream operations (csrc/epoch_tail.cuh); otherwise it issues the separate launches.
  * Same results either way.  The workspace must have been prepared before (som_b200_prepare_codebook), as it
  * is for the BMU search that precedes this call.  The caller's epoch becomes:
  * som_b200_epoch_accumulate -> (all-reduce of [S | c]) -> som_b200_epoch_tail. */
-int som_b200_epoch_tail(float *s_dev, float *c_dev, float *w_dev, int gx, int gy, int d,
+int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, float *c_dev, float *w_dev,
+                        int gx, int gy, int d,
                         int topology, int neigh_kind, double sigma, double eta, double std_coeff,
                         int compact_support, int dist_kind, float p,
                         float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats,
@@ -215,8 +250,8 @@ int som_b200_quantize(const float *x_dev, int64_t n, int d, int64_t ldx,
 int som_b200_distance_map(const float *w_dev, int gx, int gy, int d, int topology,
                           float *um_dev, void *stream);
 
-/* Experiments only: with SOM_B200_DBG=9 the fp16 kernel stamps clock64() at its pipeline hand-off
- * points; this copies the first n stamps (8 per tile) to host memory. */
+/* Experiments builds only (-DSOM_B200_EXPERIMENTS): with SOM_B200_DBG=9 the fp16 kernel stamps clock64() at its
+ * pipeline hand-off points; this copies the first n stamps (8 per tile) to host memory (zeros otherwise). */
 int som_b200_debug_timeline(long long *host_out, int n);
 
 /* Whole-job entry with HOST buffers: what a maintainer of the reference would

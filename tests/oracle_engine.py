@@ -36,8 +36,27 @@ class OracleEngine:
     def prepare_codebook(self, w, dist_kind, p, ws):
         pass
 
-    def prepare_samples(self, x):
-        return None
+    def prepare_samples(self, x, want_scale=True, out=None, colmax=None):
+        d = x.shape[1]
+        cm = torch.zeros((d + 3) // 4 * 4) if colmax is None else colmax
+        if x.shape[0]:
+            cm[:d] = torch.maximum(cm[:d], x.abs().amax(dim=0))
+        return None, cm
+
+    def accum_scales(self, colmax, d, n_total):
+        """The library's rule (csrc/accumulate.cuh): q_c = 62 - (exponent of the column maximum + 1) - ceil(log2 n_total)."""
+        dq = (d + 3) // 4 * 4
+        lg = int(np.ceil(np.log2(max(n_total, 1))))
+        q = np.zeros(dq)
+        cm = colmax.numpy()[:d].astype(np.float64)
+        ok = cm > 0
+        q[:d][ok] = 62 - (np.floor(np.log2(cm[ok])) + 1) - lg
+        qs, qi = np.zeros(dq), np.zeros(dq)
+        qs[:d], qi[:d] = 2.0 ** q[:d], 2.0 ** -q[:d]
+        return torch.from_numpy(qs), torch.from_numpy(qi)           # float64 here: exact powers of two either way
+
+    def accumulator(self, k, d):
+        return torch.zeros(k * ((d + 1) // 2 * 2) + k, dtype=torch.int64)
 
     def bmu(self, x, w, dist_kind, p, algo, ws, bmu_out=None, best_out=None, xscale=None):
         k, d = w.shape
@@ -50,14 +69,25 @@ class OracleEngine:
             return bmu_out
         return out
 
-    def accumulate(self, x, bmu, k, s, c):
-        S, cc = so.sums_by_bmu(bmu.numpy(), x.numpy(), k)
-        s.view(k, -1).add_(torch.from_numpy(S.astype(np.float32)))
-        c.add_(torch.from_numpy(cc.astype(np.float32)))
+    def accumulate(self, x, bmu, k, qscale, acc):
+        """Fixed-point sums, as the CUDA path: rint(x * 2^q_c) added as 64-bit integers (order-independent)."""
+        d = x.shape[1]
+        lds = (d + 1) // 2 * 2
+        xi = np.rint(x.numpy().astype(np.float64) * qscale.numpy()[:d]).astype(np.int64)
+        S = acc.numpy()[:k * lds].reshape(k, lds)
+        np.add.at(S[:, :d], bmu.numpy(), xi)
+        acc.numpy()[k * lds:] += np.bincount(bmu.numpy(), minlength=k)
 
-    def epoch_accumulate(self, x, w, dist_kind, p, algo, s, c, ws, bmu_out=None, xscale=None):
+    def epoch_accumulate(self, x, w, dist_kind, p, algo, qscale, acc, ws, bmu_out=None, xscale=None):
         bmu = self.bmu(x, w, dist_kind, p, algo, ws, bmu_out=bmu_out)
-        self.accumulate(x, bmu, w.shape[0], s, c)
+        self.accumulate(x, bmu, w.shape[0], qscale, acc)
+
+    def accum_finalize(self, acc, qinv, k, d, s, c):
+        lds = (d + 1) // 2 * 2
+        S = acc.numpy()[:k * lds].reshape(k, lds)[:, :d].astype(np.float64) * qinv.numpy()[:d]
+        s.copy_(torch.from_numpy(S.astype(np.float32).ravel()))
+        c.copy_(torch.from_numpy(acc.numpy()[k * lds:].astype(np.float32)))
+        acc.zero_()
 
     def neigh_apply(self, s, c, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, num, den, tables):
         spec = so.SomSpec(gx=gx, gy=gy, dim=d, sigma=1.0, neighborhood_function=_NEIGH[neigh_kind],
@@ -66,13 +96,13 @@ class OracleEngine:
         num.copy_(torch.from_numpy((H.T @ s.numpy().reshape(gx * gy, d).astype(np.float64)).astype(np.float32).ravel()))
         den.copy_(torch.from_numpy((H.T @ c.numpy().astype(np.float64)).astype(np.float32)))
 
-    def epoch_tail(self, s, c, w, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, dist_kind, p,
+    def epoch_tail(self, acc, qinv, s, c, w, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, dist_kind, p,
                    num, den, tables, ws):
+        if acc is not None:
+            self.accum_finalize(acc, qinv, gx * gy, d, s, c)
         self.neigh_apply(s, c, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, num, den, tables)
         self.merge(w, num, den)
         self.prepare_codebook(w, dist_kind, p, ws)
-        s.zero_()
-        c.zero_()
 
     def merge(self, w, num, den):
         k, d = w.shape

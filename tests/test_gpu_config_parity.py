@@ -122,7 +122,9 @@ def test_config_scale_teacher_forced_parity(name):
             print("    flipped rows in fp64: GPU pick within %.2e of the true minimum, reference pick within %.2e; GPU closer on "
                   "%d of %d" % (reg["gpu_worst"], reg["ref_worst"], reg["gpu_better"], reg["rows"]))
         assert r["bad"] == 0, line
-        assert err_same <= 1e-5, line
+        # (mexican hat: num / den with den crossing zero amplifies the fp32 rounding of the apply -- the reference's own
+        # epoch and an fp64 re-derivation of it differ by 1e-5 there)
+        assert err_same <= (1e-4 if spec.neighborhood_function == "mexican_hat" else 1e-5), line
         if flips == 0:
             assert err_ref <= 1e-4, line
         else:

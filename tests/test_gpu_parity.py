@@ -34,7 +34,7 @@ def _gpu_bmu(eng, x, w, dist, p, algo):
     wd = torch.from_numpy(np.ascontiguousarray(w.reshape(-1, w.shape[-1]), dtype=np.float32)).cuda()
     ws = eng.workspace(0, wd.shape[0], wd.shape[1])
     eng.prepare_codebook(wd, _lib.DIST[dist], p, ws)
-    xs = eng.prepare_samples(xd) if algo in ("tc16", "auto") else None
+    xs = eng.prepare_samples(xd)[0] if algo in ("tc16", "auto") else None
     bmu = eng.bmu(xd, wd, _lib.DIST[dist], p, _lib.ALGO[algo], ws, xscale=xs)
     torch.cuda.synchronize()
     return bmu.cpu().numpy()
@@ -138,19 +138,46 @@ def test_unaligned_rows_fall_back_to_simt(eng):
         eng.bmu(xd, wd, 0, 2.0, _lib.ALGO["tc"], ws)
 
 
+def _exact_sums(eng, xd, bd, K):
+    """S (K, D) and c (K) through the C ABI: column maxima -> scales -> exact accumulate -> finalize."""
+    n, d = xd.shape
+    _, colmax = eng.prepare_samples(xd, want_scale=False)
+    qscale, qinv = eng.accum_scales(colmax, d, n)
+    acc = eng.accumulator(K, d)
+    eng.accumulate(xd, bd, K, qscale, acc)
+    S, c = eng.empty(K, d), eng.empty(K)
+    raw = acc.clone()
+    eng.accum_finalize(acc, qinv, K, d, S, c)
+    torch.cuda.synchronize()
+    assert int(acc.abs().max()) == 0                       # finalize leaves the accumulator cleared
+    return S.cpu().numpy(), c.cpu().numpy(), raw.cpu().numpy()
+
+
 def test_accumulate_matches_oracle_sums(eng):
-    for n, d, K in [(5000, 16, 64), (3001, 30, 50), (20000, 64, 1024), (777, 5, 13000)]:
+    """Exact fixed-point accumulation (csrc/accumulate.cuh): equal to the fp64 segmented sums to fp32 rounding, exact
+    counts, bit-identical from launch to launch, vector and scalar paths, rows longer than one 128-column piece."""
+    for n, d, K in [(5000, 16, 64), (3001, 30, 50), (20000, 64, 1024), (777, 5, 13000), (1500, 300, 40), (900, 131, 7)]:
         x = U.blobs(n, d, seed=n)
+        x[:, ::3] *= 1e-3                                   # columns of different magnitudes: per-column scales
         bmu = np.random.RandomState(n).randint(K, size=n).astype(np.int32)
         S_ref, c_ref = so.sums_by_bmu(bmu, x, K)
-        xd, bd = torch.from_numpy(x).cuda(), torch.from_numpy(bmu).cuda()
-        S, c = eng.zeros(K, d), eng.zeros(K)
-        from xpysom_dask_b200 import _lib
-        _lib.check(eng.lib.som_b200_accumulate(eng._p(xd), n, d, d, eng._p(bd), K, eng._p(S), eng._p(c), eng._stream()),
-                   "accumulate")
-        torch.cuda.synchronize()
-        np.testing.assert_array_equal(c.cpu().numpy(), c_ref)
-        np.testing.assert_allclose(S.cpu().numpy(), S_ref, rtol=2e-5, atol=1e-5)
+        ld = (d + 3) // 4 * 4
+        buf = torch.zeros((n, ld), device="cuda")
+        buf[:, :d] = torch.from_numpy(x).cuda()
+        for xd in (buf[:, :d], torch.from_numpy(x).cuda()):          # 16-byte aligned rows / packed rows
+            bd = torch.from_numpy(bmu).cuda()
+            S, c, raw = _exact_sums(eng, xd, bd, K)
+            np.testing.assert_array_equal(c, c_ref)
+            assert np.abs(S - S_ref).max() <= 1e-7 * np.abs(S_ref).max() + 1e-30, (n, d, K)
+            col = np.abs(S_ref).max(axis=0)
+            assert (np.abs(S - S_ref).max(axis=0) <= 2e-7 * col + 1e-30).all(), (n, d, K)   # per column, not only overall
+            S2, c2, raw2 = _exact_sums(eng, xd, bd, K)
+            np.testing.assert_array_equal(raw, raw2)               # integers: the same bits every time
+            np.testing.assert_array_equal(S, S2)
+        # the order of the rows does not matter either
+        perm = np.random.RandomState(1).permutation(n)
+        S3, _, raw3 = _exact_sums(eng, torch.from_numpy(x[perm]).cuda(), torch.from_numpy(bmu[perm]).cuda(), K)
+        np.testing.assert_array_equal(raw, raw3)
 
 
 def _apply_neigh(eng, case, sigma, S, c, eta=0.37):
@@ -256,38 +283,50 @@ def test_neigh_apply_wide_tile_variant(eng, fn, compact, topology):
     (70, 60, 12, "gaussian", "rectangular", "euclidean"),       # separable path: the entry falls back to separate launches
 ])
 def test_epoch_tail_matches_separate_launches(eng, gx, gy, d, fn, topology, dist):
-    """som_b200_epoch_tail (one cooperative kernel on small maps) == neigh_apply + merge + prepare_codebook + clearing
-    S and c: same codebook, a workspace that finds the same BMUs, clean accumulators."""
+    """som_b200_epoch_tail (one cooperative kernel on small maps) == accum_finalize + neigh_apply + merge +
+    prepare_codebook: same codebook (bit for bit: no atomics anywhere), a workspace that finds the same BMUs, a
+    cleared accumulator."""
     from xpysom_dask_b200 import _lib
     K = gx * gy
     rng = np.random.RandomState(gx + d)
-    S = rng.randn(K, d).astype(np.float32)
-    c = rng.randint(0, 7, size=K).astype(np.float32)
-    S[c == 0] = 0
     W0 = rng.rand(K, d).astype(np.float32)
     X = torch.from_numpy(rng.rand(3000, (d + 3) // 4 * 4).astype(np.float32)).cuda()[:, :d]
+    b0 = torch.from_numpy(rng.randint(0, max(1, K // 2), size=3000).astype(np.int32)).cuda()   # half the units stay empty
     dk, tk, nk = _lib.DIST[dist], _lib.TOPO[topology], _lib.NEIGH[fn]
+    _, colmax = eng.prepare_samples(X, want_scale=False)
+    qscale, qinv = eng.accum_scales(colmax, d, 3000)
     res = []
     for fused in (False, True):
-        Sd, cd, w = torch.from_numpy(S).cuda(), torch.from_numpy(c).cuda(), torch.from_numpy(W0).cuda()
-        num, den = eng.empty(K, d), eng.empty(K)
+        w = torch.from_numpy(W0).cuda()
+        acc = eng.accumulator(K, d)
+        eng.accumulate(X, b0, K, qscale, acc)
+        Sd, cd, num, den = eng.empty(K, d), eng.empty(K), eng.empty(K, d), eng.empty(K)
         ws, tables = eng.workspace(0, K, d), eng.neigh_tables(gx, gy, d)
         eng.prepare_codebook(w, dk, 2.0, ws)          # as in training: the tail follows a BMU search on a prepared workspace
         if fused:
-            eng.epoch_tail(Sd, cd, w, gx, gy, d, tk, nk, 2.3, 0.4, 0.5, False, dk, 2.0, num, den, tables, ws)
+            eng.epoch_tail(acc, qinv, Sd, cd, w, gx, gy, d, tk, nk, 2.3, 0.4, 0.5, False, dk, 2.0, num, den, tables, ws)
         else:
+            eng.accum_finalize(acc, qinv, K, d, Sd, cd)
             eng.neigh_apply(Sd, cd, gx, gy, d, tk, nk, 2.3, 0.4, 0.5, False, num, den, tables)
             eng.merge(w, num, den)
             eng.prepare_codebook(w, dk, 2.0, ws)
-            Sd.zero_(); cd.zero_()
-        xs = eng.prepare_samples(X) if dist in ("euclidean", "cosine") else None
+        xs = eng.prepare_samples(X)[0] if dist in ("euclidean", "cosine") else None
         bmu = eng.bmu(X, w, dk, 2.0, _lib.ALGO["auto"], ws, xscale=xs)
         torch.cuda.synchronize()
-        res.append((w.cpu().numpy(), bmu.cpu().numpy(), float(Sd.abs().max()), float(cd.abs().max())))
-    (wa, ba, _, _), (wb, bb, smax, cmax) = res
+        res.append((w.cpu().numpy(), bmu.cpu().numpy(), int(acc.abs().max())))
+    (wa, ba, _), (wb, bb, amax) = res
+    assert amax == 0                         # the accumulator is handed back cleared
+    # the two routes slice the reduction over BMUs differently (fixed order each): last-bit differences only
     assert U.codebook_rel_err(wb, wa) < 2e-6
-    assert smax == 0.0 and cmax == 0.0
-    assert (ba != bb).mean() < 2e-3          # codebooks differ in the last bits (order of the sliced sums): near-ties only
+    assert (ba != bb).mean() < 2e-3
+    # and each route is bit-reproducible: the same call again lands on the same codebook
+    w = torch.from_numpy(W0).cuda()
+    acc = eng.accumulator(K, d)
+    eng.accumulate(X, b0, K, qscale, acc)
+    eng.prepare_codebook(w, dk, 2.0, ws)
+    eng.epoch_tail(acc, qinv, Sd, cd, w, gx, gy, d, tk, nk, 2.3, 0.4, 0.5, False, dk, 2.0, num, den, tables, ws)
+    torch.cuda.synchronize()
+    np.testing.assert_array_equal(w.cpu().numpy(), wb)
 
 
 def test_neigh_apply_skips_empty_bmus(eng):
@@ -413,8 +452,8 @@ def test_cuda_graph_replay_matches_eager_launches():
     """use_cuda_graph=True replays one captured graph per epoch with sigma / eta read from a device-side
     schedule; it must land where the kernel-by-kernel path lands.  The comparison is made fully
     deterministic: small-integer samples make the per-BMU sums exact in fp32 whatever the order of the
-    atomics, and a 64-neuron map keeps the neighbourhood apply in one un-sliced CTA row (no atomics), so
-    the two runs cannot drift apart chaotically the way free-running runs do."""
+    accumulation (they are exact anyway), so the two runs cannot drift apart chaotically the way free-running runs
+    do."""
     from xpysom_dask_b200 import XPySom
     rng = np.random.RandomState(21)
     centres = rng.randint(0, 8, size=(24, 32))

@@ -21,7 +21,7 @@ def test_library_loads_and_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.som_b200_abi_version() == 1
+    assert lib.som_b200_abi_version() == _lib.ABI_VERSION
     # pure host helpers may be called without a GPU
     assert lib.som_b200_workspace_bytes(1024, 64) >= 2 * 1024 * 64 * 4
     assert lib.som_b200_workspace_bytes(0, 64) == 0

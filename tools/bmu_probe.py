@@ -12,6 +12,8 @@ sys.path.insert(0, ROOT)
 from xpysom_dask_b200 import _lib                          # noqa: E402
 from xpysom_dask_b200.engine import CudaEngine             # noqa: E402
 
+if os.environ.get("SOM_TOOL_LIB"):          # tuning: time another build of the library (tools/variants/*.so)
+    _lib.LIB_PATH = os.environ["SOM_TOOL_LIB"]
 n, d, k = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3])
 fused = len(sys.argv) > 4 and sys.argv[4] == "fused"
 reps = int(sys.argv[5]) if len(sys.argv) > 5 else 5
@@ -23,14 +25,15 @@ w = torch.rand(k, d, generator=g, device="cuda")
 ws = eng.workspace(0, k, d)
 eng.prepare_codebook(w, 0, 2.0, ws)
 bmu = eng.empty(n, dtype=torch.int32)
-xs = eng.prepare_samples(x) if algo in ("tc16", "auto") else None
-S, c = eng.zeros(k, d), eng.zeros(k)
+xs, colmax = eng.prepare_samples(x, want_scale=algo in ("tc16", "auto"))
+qs, qi = eng.accum_scales(colmax, d, n)
+acc = eng.accumulator(k, d)
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for i in range(reps + 2):
     if i == 2:
         e0.record()
     if fused:
-        eng.epoch_accumulate(x, w, 0, 2.0, _lib.ALGO[algo], S, c, ws, bmu_out=bmu, xscale=xs)
+        eng.epoch_accumulate(x, w, 0, 2.0, _lib.ALGO[algo], qs, acc, ws, bmu_out=bmu, xscale=xs)
     else:
         eng.bmu(x, w, 0, 2.0, _lib.ALGO[algo], ws, bmu_out=bmu, xscale=xs)
 e1.record()
@@ -48,3 +51,13 @@ if os.environ.get("SOM_B200_DBG") == "9":
     print("tile |  MMA: wait_acc  acc_free  ops_ready  committed |  EPI: wait  tile_ready  drained   (cycles, leader CTA 0)")
     for i in range(8, 40):
         print("%4d | %9d %9d %9d %9d | %9d %9d %9d" % ((i,) + tuple(int(v - t0) for v in t[i, :7])))
+if os.environ.get("SOM_B200_DBG") == "8":
+    import ctypes
+    import numpy as np
+    buf = np.zeros(8 * 64, dtype=np.int64)
+    _lib.check(eng.lib.som_b200_debug_timeline(buf.ctypes.data_as(ctypes.c_void_p), buf.size), "timeline")
+    t = buf.reshape(64, 8)
+    t0 = t[8, 0]
+    print("batch | start  loads_issued  buffers_free  stored  fenced  sent   (cycles, scatter warp 0 of CTA 0)")
+    for i in range(8, 28):
+        print("%4d | %8d %8d %8d %8d %8d %8d" % ((i,) + tuple(int(v - t0) for v in t[i, :6])))

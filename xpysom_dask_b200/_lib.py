@@ -25,8 +25,17 @@ SIGNATURES = {
     "som_b200_neigh_scratch_floats": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "som_b200_prepare_codebook": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,
                                                  ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
-    "som_b200_prepare_samples": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p,
+    "som_b200_pick_algo": (ctypes.c_int, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
+    "som_b200_prepare_samples": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, c_f32p,
                                                 ctypes.c_void_p]),
+    "som_b200_accum_scales": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_double, c_f32p, c_f32p, ctypes.c_void_p]),
+    "som_b200_accum_words": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "som_b200_accum_finalize": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p,
+                                               ctypes.c_void_p]),
+    "som_b200_accum_fold": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                           ctypes.c_void_p]),
+    "som_b200_accum_finalize_f64": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p,
+                                                   ctypes.c_void_p]),
     "som_b200_bmu": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, c_f32p, ctypes.c_int,
                                     ctypes.c_int, ctypes.c_float, ctypes.c_int, c_i32p, c_f32p,
                                     ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -36,10 +45,10 @@ SIGNATURES = {
     "som_b200_top2": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int, c_i32p,
                                      ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "som_b200_accumulate": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_i32p, ctypes.c_int,
-                                           c_f32p, c_f32p, ctypes.c_void_p]),
+                                           c_f32p, ctypes.c_void_p, ctypes.c_void_p]),
     "som_b200_epoch_accumulate": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, c_f32p,
                                                  ctypes.c_int, ctypes.c_int, ctypes.c_float, ctypes.c_int,
-                                                 c_f32p, c_f32p, c_i32p, ctypes.c_void_p, ctypes.c_size_t,
+                                                 c_f32p, ctypes.c_void_p, c_i32p, ctypes.c_void_p, ctypes.c_size_t,
                                                  ctypes.c_void_p]),
     "som_b200_neigh_apply": (ctypes.c_int, [c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                             ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double,
@@ -50,7 +59,8 @@ SIGNATURES = {
                                                   ctypes.c_void_p]),
     "som_b200_epoch_advance": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
     "som_b200_merge": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
-    "som_b200_epoch_tail": (ctypes.c_int, [c_f32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+    "som_b200_epoch_tail": (ctypes.c_int, [ctypes.c_void_p, c_f32p, c_f32p, c_f32p, c_f32p, ctypes.c_int, ctypes.c_int,
+                                           ctypes.c_int, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_float, c_f32p, c_f32p, c_f32p, ctypes.c_size_t,
                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
@@ -85,6 +95,7 @@ NEIGH = {"gaussian": 0, "mexican_hat": 1, "bubble": 2, "triangle": 3}
 TOPO = {"rectangular": 0, "hexagonal": 1}
 ALGO = {"auto": 0, "simt": 1, "tc": 2, "tc16": 3}
 
+ABI_VERSION = 2
 _lib = None
 
 
@@ -106,8 +117,8 @@ def load():
         fn = getattr(lib, name)           # AttributeError if the ABI lost a symbol
         fn.restype = res
         fn.argtypes = args
-    if lib.som_b200_abi_version() != 1:
-        raise SomB200Error("libsom_b200.so ABI version %d, expected 1" % lib.som_b200_abi_version())
+    if lib.som_b200_abi_version() != ABI_VERSION:
+        raise SomB200Error("libsom_b200.so ABI version %d, expected %d" % (lib.som_b200_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

@@ -1,6 +1,9 @@
 """Build libsom_b200.so in-tree with nvcc for sm_100a.
 
-    python -m xpysom_dask_b200.build [--force]
+    python -m xpysom_dask_b200.build [--force] [--experiments]
+
+--experiments compiles the tuning knobs in (-DSOM_B200_EXPERIMENTS: SOM_B200_* environment variables, the
+in-kernel timeline probe); the production library never reads the environment.
 """
 import os
 import subprocess
@@ -26,10 +29,10 @@ def up_to_date():
     return all(os.path.getmtime(s) <= t for s in sources())
 
 
-def build(force=False, verbose=True):
-    if not force and up_to_date():
+def build(force=False, verbose=True, experiments=False):
+    if not force and not experiments and up_to_date():
         return OUT
-    cmd = [NVCC] + FLAGS + ["-o", OUT, os.path.join(CSRC, "som_api.cu")]
+    cmd = [NVCC] + FLAGS + (["-DSOM_B200_EXPERIMENTS"] if experiments else []) + ["-o", OUT, os.path.join(CSRC, "som_api.cu")]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.run(cmd, check=True)
@@ -37,5 +40,5 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    build(force="--force" in sys.argv, experiments="--experiments" in sys.argv)
     print("built", OUT)

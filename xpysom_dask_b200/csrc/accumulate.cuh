@@ -1,91 +1,132 @@
-// K3: per-BMU sample sums.  S[bmu[r], :] += X[r, :],  c[bmu[r]] += 1.
+// K3: per-BMU sample sums, exact and order-independent.  S[bmu[r], :] += X[r, :],  cnt[bmu[r]] += 1.
 //
-// This is the sample side of the reference's second GEMM g^T X and of sum(g)
-// (xpysom.py:436-440): because h(bmu, k) depends on the sample only through its
-// BMU, g^T X == H^T S.  HBM-bound streaming pass: 4*D bytes
-// per sample read once, one 16-byte vector reduction per 4 features into the
-// L2-resident (K, D) accumulator.  Counts go through a per-CTA shared-memory
-// integer histogram so that fp32 increments are never lost above 2^24.
+// This is the sample side of the reference's second GEMM g^T X and of sum(g) (xpysom.py:436-440): because
+// h(bmu, k) depends on the sample only through its BMU, g^T X == H^T S -- the "segmented
+// reduction" of north_star item (4).  The sums are 64-bit fixed-point integers (common.cuh: ExactAcc), so the
+// result does not depend on the order of the atomics, on the tiling or on the sharding; the fp32 values the
+// neighbourhood apply reads are produced once per epoch by accum_finalize_kernel (one rounding per element).
+//
+// Kernels here:
+//   column_absmax (inside row_scale_kernel, misc.cuh)   per-column largest magnitude of the samples, once per upload
+//   accum_scales_kernel       q_c from the column maxima and the total sample count: qscale = 2^q_c, qinv = 2^-q_c
+//   accumulate_kernel         the scatter for the SIMT BMU path (the tensor-core kernels scatter from their own warps)
+//   accum_finalize_kernel     int64 -> fp32 S, c (and clears the integers for the next epoch)
+//   accum_fold_kernel         int64 part -> running fp64 sums (several parts with different scales: chunked uploads,
+//                             streamed out-of-core blocks), accum_finalize_f64_kernel rounds those once
 #pragma once
 #include "common.cuh"
 
 namespace somb200 {
 
-constexpr int ACC_THREADS = 256;
-constexpr int ACC_HIST_MAX_K = 12288;   // 48 KB of int32 bins in shared memory
+constexpr int ACC_THREADS = 128;      // four scatter warps per CTA, as in the tensor-core kernels
+constexpr int ACC_NBUF = 4;
 
-template <bool VEC, bool HIST>
-__global__ void __launch_bounds__(ACC_THREADS)
-accumulate_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx,
-                  const int32_t *__restrict__ bmu, int k,
-                  float *__restrict__ S, float *__restrict__ c, int64_t rows_per_cta) {
-    extern __shared__ int hist[];
-    if (HIST) {
-        for (int i = threadIdx.x; i < k; i += blockDim.x) hist[i] = 0;
-        __syncthreads();
+// qscale[c] = 2^q_c, qinv[c] = 2^-q_c with q_c = 62 - (e_c + 1) - ceil(log2 n_total), e_c = ilogb(colmax[c]).
+// A zero / non-finite column gets q = 0.  q is clamped to what fp32 can hold as a power of two.
+__global__ void accum_scales_kernel(const float *__restrict__ colmax, int d, int d_pad, double n_total,
+                                    float *__restrict__ qscale, float *__restrict__ qinv) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= d_pad) return;
+    int q = 0;
+    if (c < d) {
+        const float m = colmax[c];
+        if (m > 0.f && isfinite(m)) {
+            int lg = 0;
+            while (ldexp(1.0, lg) < n_total) ++lg;
+            q = 62 - (ilogbf(m) + 1) - lg;
+            q = q > 120 ? 120 : (q < -120 ? -120 : q);
+        }
     }
+    qscale[c] = c < d ? ldexpf(1.f, q) : 0.f;
+    qinv[c] = c < d ? ldexpf(1.f, -q) : 0.f;
+}
+
+__global__ void __launch_bounds__(ACC_THREADS)
+accumulate_kernel(ExactAcc A, const int32_t *__restrict__ bmu, int64_t n, int64_t rows_per_cta) {
+    __shared__ __align__(128) long long stage[4][ACC_NBUF][ACC_PIECE];
+    __shared__ int bm[128];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t r0 = (int64_t)blockIdx.x * rows_per_cta;
     const int64_t r1 = r0 + rows_per_cta < n ? r0 + rows_per_cta : n;
-    if (VEC) {
-        const int d4 = d >> 2;
-        const int64_t items = (r1 - r0) * d4;
-        for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
-            const int64_t r = r0 + it / d4;
-            const int c4 = (int)(it % d4);
-            const int b = __ldg(bmu + r);
-            const float4 v = __ldcs(reinterpret_cast<const float4 *>(X + r * ldx) + c4);  // streaming: read once
-            red_add_v4(S + (int64_t)b * d + c4 * 4, v);
-            if (c4 == 0) {
-                if (HIST) atomicAdd(&hist[b], 1);
-                else      atomicAdd(c + b, 1.0f);
-            }
-        }
-    } else {
-        const int64_t items = (r1 - r0) * d;
-        for (int64_t it = threadIdx.x; it < items; it += blockDim.x) {
-            const int64_t r = r0 + it / d;
-            const int col = (int)(it % d);
-            const int b = __ldg(bmu + r);
-            atomicAdd(S + (int64_t)b * d + col, __ldcs(X + r * ldx + col));
-            if (col == 0) {
-                if (HIST) atomicAdd(&hist[b], 1);
-                else      atomicAdd(c + b, 1.0f);
-            }
-        }
-    }
-    if (HIST) {
+    uint32_t it = 0;
+    for (int64_t t0 = r0; t0 < r1; t0 += 128) {
+        const int rows = (int)(r1 - t0 < 128 ? r1 - t0 : 128);
         __syncthreads();
-        for (int i = threadIdx.x; i < k; i += blockDim.x) {
-            const int h = hist[i];
-            if (h) atomicAdd(c + i, (float)h);
-        }
+        if ((int)threadIdx.x < 128) bm[threadIdx.x] = (int)threadIdx.x < rows ? __ldg(bmu + t0 + threadIdx.x) : -1;
+        __syncthreads();
+        scatter_rows_exact<ACC_NBUF>(A, bm, t0, rows, warp, 4, lane, &stage[warp][0][0], it);
     }
+    bulk_wait_all();
 }
 
 inline int launch_accumulate(const float *X, int64_t n, int d, int64_t ldx, const int32_t *bmu, int k,
-                             float *S, float *c, int sm_count, cudaStream_t st) {
+                             const AccTarget &T, int sm_count, cudaStream_t st) {
     if (n <= 0) return 0;
-    const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
-    const bool hist = k <= ACC_HIST_MAX_K;
-    // a multiple of the SM count; each CTA takes a contiguous slab of rows so its loads are sequential
+    ExactAcc A;
+    A.X = X; A.ldx = ldx; A.d = d; A.k = k; A.qscale = T.qscale; A.S = T.S; A.cnt = T.cnt; A.lds = acc_ld(d); A.dbg = 0;
+    A.vec = ((d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0)) ? 1 : 0;
+    // a multiple of the SM count; each CTA takes a contiguous slab of whole 128-row tiles so its loads are sequential
     int64_t ctas = (int64_t)sm_count * 8;
-    int64_t rows_per_cta = ceil_div(n, ctas);
-    if (rows_per_cta < 32) rows_per_cta = 32;
+    int64_t rows_per_cta = round_up(ceil_div(n, ctas), 128);
     ctas = ceil_div(n, rows_per_cta);
-    const size_t smem = hist ? (size_t)k * sizeof(int) : 0;
-#define SOM_LAUNCH_ACC(V, H)                                                                  \
-    do {                                                                                      \
-        if (smem > 48 * 1024)                                                                 \
-            cudaFuncSetAttribute(accumulate_kernel<V, H>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
-        accumulate_kernel<V, H><<<(unsigned)ctas, ACC_THREADS, smem, st>>>(X, n, d, ldx, bmu, k, S, c, rows_per_cta); \
-    } while (0)
-    if (vec && hist) SOM_LAUNCH_ACC(true, true);
-    else if (vec)    SOM_LAUNCH_ACC(true, false);
-    else if (hist)   SOM_LAUNCH_ACC(false, true);
-    else             SOM_LAUNCH_ACC(false, false);
-#undef SOM_LAUNCH_ACC
+    accumulate_kernel<<<(unsigned)ctas, ACC_THREADS, 0, st>>>(A, bmu, n, rows_per_cta);
     return check_cuda(cudaGetLastError(), "accumulate_kernel launch");
+}
+
+// int64 sums -> the fp32 S (K, D) and c (K) the neighbourhood apply reads; the integers are cleared for the next
+// epoch when `clear` is set.  double(S_int) * 2^-q is exact up to 2^53, then rounded ONCE to fp32.
+__global__ void accum_finalize_kernel(unsigned long long *__restrict__ Si, unsigned long long *__restrict__ ci,
+                                      const float *__restrict__ qinv, int k, int d, int lds, float *__restrict__ S,
+                                      float *__restrict__ c, int clear) {
+    pdl_wait(); pdl_trigger();
+    const int64_t tot = (int64_t)k * lds;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / lds), col = (int)(e % lds);
+        const long long v = (long long)Si[e];
+        if (col < d) S[(int64_t)row * d + col] = (float)((double)v * (double)qinv[col]);
+        if (clear && v) Si[e] = 0ull;
+    }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k; e += gridDim.x * blockDim.x) {
+        const unsigned long long v = ci[e];
+        c[e] = (float)v;
+        if (clear && v) ci[e] = 0ull;
+    }
+}
+
+// one part of a multi-part epoch (its own column scales): Sd += double(S_int) * 2^-q, cd += count; integers cleared
+__global__ void accum_fold_kernel(unsigned long long *__restrict__ Si, unsigned long long *__restrict__ ci,
+                                  const float *__restrict__ qinv, int k, int d, int lds, double *__restrict__ Sd,
+                                  double *__restrict__ cd) {
+    const int64_t tot = (int64_t)k * lds;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        const int row = (int)(e / lds), col = (int)(e % lds);
+        const long long v = (long long)Si[e];
+        if (v) {
+            if (col < d) Sd[(int64_t)row * d + col] += (double)v * (double)qinv[col];
+            Si[e] = 0ull;
+        }
+    }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k; e += gridDim.x * blockDim.x) {
+        const unsigned long long v = ci[e];
+        if (v) { cd[e] += (double)v; ci[e] = 0ull; }
+    }
+}
+
+// running fp64 sums -> fp32 S, c; the doubles are cleared
+__global__ void accum_finalize_f64_kernel(double *__restrict__ Sd, double *__restrict__ cd, int k, int d,
+                                          float *__restrict__ S, float *__restrict__ c) {
+    const int64_t tot = (int64_t)k * d;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
+        S[e] = (float)Sd[e];
+        Sd[e] = 0.0;
+    }
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k; e += gridDim.x * blockDim.x) { c[e] = (float)cd[e]; cd[e] = 0.0; }
+}
+
+inline int grid_for(int64_t items, int sm_count) {
+    int64_t b = ceil_div(items, 256);
+    if (b > (int64_t)sm_count * 8) b = (int64_t)sm_count * 8;
+    return (int)(b < 1 ? 1 : b);
 }
 
 }  // namespace somb200

@@ -258,7 +258,7 @@ __device__ __forceinline__ void top2_insert(float &d1, int &i1, float &d2, int &
     else if (v < d2 || (v == d2 && idx < i2)) { d2 = v; i2 = idx; }
 }
 
-__global__ void __launch_bounds__(ST_THREADS, 2)
+__global__ void __launch_bounds__(ST_THREADS, 1)
 top2_simt_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, const float *__restrict__ W, int k,
                  const float *__restrict__ wsq, int32_t *__restrict__ out2) {
     __shared__ __align__(16) float Xs[ST_DK][ST_LD];

@@ -33,6 +33,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (prompt
 // wake-up) or the hint expires, instead of burning issue slots that the epilogue warps need
 constexpr uint32_t kSuspendHintNs = 20000;
+constexpr long long kTrapCycles = 8000000000LL;     // ~4 s at 2 GHz
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
     asm volatile("{\n\t.reg .pred p;\n\t"
@@ -54,7 +55,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if ((++polls & 255u) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            if (now - t0 > 40000000000LL) {   // ~20 s at 2 GHz (generous: profilers slow kernels down a lot)
+            if (now - t0 > kTrapCycles) {      // a protocol bug must trap quickly; profilers slow kernels down, hence seconds
                 printf("som_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
                        (int)blockIdx.x, (int)threadIdx.x, bar, parity);
                 __trap();
@@ -74,7 +75,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity,
         if ((++polls & 1023u) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            if (now - t0 > 40000000000LL) {
+            if (now - t0 > kTrapCycles) {
                 printf("som_b200: mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
                        (int)blockIdx.x, (int)threadIdx.x, bar, parity);
                 __trap();
@@ -95,22 +96,6 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
     asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
 }
 
-__device__ __forceinline__ void tmem_alloc(uint32_t slot_smem, uint32_t cols) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(slot_smem), "r"(cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(addr), "r"(cols) : "memory");
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n\t.reg .pred p;\n\t"
-                 "setp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(bar) : "memory");
-}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                  "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -205,11 +190,17 @@ struct RunMin {
     }
 };
 
-// Experiment knobs are read from the environment once per process (SOM_B200_DBG: timeline probe of
-// tools/bmu_probe.py; SOM_B200_TBN: neuron-tile width of the resident fp16 kernel).
+// Experiment knobs (SOM_B200_DBG: timeline probe of tools/bmu_probe.py; SOM_B200_TBN: neuron-tile width of the
+// resident fp16 kernel; ...) exist only in a library built with -DSOM_B200_EXPERIMENTS (python -m
+// xpysom_dask_b200.build --experiments); the production library never looks at the environment.
 inline int env_int(const char *name) {
+#ifdef SOM_B200_EXPERIMENTS
     const char *e = getenv(name);
     return e ? atoi(e) : 0;
+#else
+    (void)name;
+    return 0;
+#endif
 }
 // cudaFuncSetAttribute is per device: remember which devices have the large dynamic-shared-memory opt-in.
 inline bool first_launch_on_device(bool (&done)[64]) {
@@ -241,17 +232,10 @@ __device__ __forceinline__ void dbg_stamp(int on, int slot, uint32_t tile) {
     if (on && tile < 256) g_dbg[tile * 8 + slot] = clock64();
 }
 
-// arguments of the fused accumulate; S == nullptr turns it off
-struct FusedAcc {
-    const float *X;      // samples (row stride ldx), the same matrix map_x describes
-    int64_t ldx;
-    int d, k;
-    float *S, *c;        // (K, D) sums and (K) counts, accumulated into
-    int *cnt;            // k ints, zero on entry, zero again on exit
-    unsigned int *done;  // ticket counter, zero on entry and exit
-    int vec;             // rows are 16-byte aligned and d % 4 == 0: 128-bit path
-    int dbg;             // experiments only (SOM_B200_DBG); 0 in production
-};
+// arguments of the fused accumulate (common.cuh: ExactAcc; S == nullptr turns it off) plus the experiment probe
+typedef ExactAcc FusedAcc;
+constexpr int SCAT_NBUF = 4;                                        // staging buffers per scatter warp
+constexpr int SCAT_STAGE_BYTES = 4 * SCAT_NBUF * ACC_PIECE * 8;     // four scatter warps
 
 // ---- host side -----------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -271,7 +255,7 @@ inline EncodeTiledFn get_encode_fn() {
 }
 
 inline int make_map_2d(CUtensorMap *m, const void *base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
-                       uint32_t box_inner, uint32_t box_outer) {
+                       uint32_t box_inner, uint32_t box_outer, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
     EncodeTiledFn enc = get_encode_fn();
     SOM_REQUIRE(enc != nullptr, SOM_E_NODEVICE, "cuTensorMapEncodeTiled not available from the driver");
     cuuint64_t dims[2] = {inner, outer};
@@ -279,7 +263,7 @@ inline int make_map_2d(CUtensorMap *m, const void *base, uint64_t inner, uint64_
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SOM_REQUIRE(r == CUDA_SUCCESS, SOM_E_SHAPE, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
     return 0;

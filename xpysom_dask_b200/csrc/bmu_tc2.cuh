@@ -52,7 +52,7 @@ constexpr int MAXS = 4;                  // ring slots per barrier family (A rin
 constexpr int NUM_BARS = 5 * MAXS + 8;
 // stages | per-warp bias slices | merge buffers [2][BM] (float + int) | bmu hand-off [2][BM] | barriers | tmem slot | slack
 constexpr int EPI_STAGE_BYTES = 8 * 128 * 4;
-constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
+constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + EPI_STAGE_BYTES + tc::SCAT_STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
 
 // ---- cluster / 2-SM PTX wrappers -------------------------------------------------------
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
@@ -89,7 +89,7 @@ __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
         if ((++polls & 1023u) == 0) {
             const long long now = clock64();
             if (t0 == 0) t0 = now;
-            if (now - t0 > 40000000000LL) {
+            if (now - t0 > tc::kTrapCycles) {
                 printf("som_b200(tc2): mbarrier timeout (block %d thread %d bar 0x%x parity %u)\n",
                        (int)blockIdx.x, (int)threadIdx.x, bar, parity);
                 __trap();
@@ -137,7 +137,8 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
 
     float    *epi_stage = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);                    // [8 warps][128]
-    uint8_t  *tail   = smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES;
+    uint8_t  *scat_stage = smem + STAGES * STAGE_BYTES + EPI_STAGE_BYTES;            // [4 warps][SCAT_NBUF][128] int64
+    uint8_t  *tail   = scat_stage + tc::SCAT_STAGE_BYTES;
     float    *mrg_v  = reinterpret_cast<float *>(tail);                       // [2][BM]
     int      *mrg_i  = reinterpret_cast<int *>(tail + 2 * BM * 4);            // [2][BM]
     int      *bmu_s  = reinterpret_cast<int *>(tail + 2 * BM * 8);            // [2][BM]
@@ -158,7 +159,6 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     auto a_off = [&](int s) { return (uint32_t)(RES ? s * 2 * A_BYTES : s * STAGE_BYTES); };
     auto b_off = [&](int s) { return (uint32_t)(RES ? 2 * 2 * A_BYTES + s * 2 * BH_BYTES : s * STAGE_BYTES + 2 * A_BYTES); };
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + NUM_BARS);
-    __shared__ unsigned int last_cta;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -366,48 +366,18 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     } else {
         // ===================== scatter: S[bmu[r], :] += X[r, :], cnt[bmu[r]] += 1 =====================
         if (fused) {
-            const int t = threadIdx.x - SCAT_WARP0 * 32;
             const int wq = warp - SCAT_WARP0;
-            const int d4 = acc.d >> 2;
-            uint32_t tile_it = 0;
+            long long *stage = reinterpret_cast<long long *>(scat_stage) + wq * (tc::SCAT_NBUF * ACC_PIECE);
+            uint32_t tile_it = 0, bulk_it = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
                 const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                 tc::mbar_wait_relaxed(bfullq_bar(b), bph, 400);
-                const int *bm = bmu_s + b * BM;
                 const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
-                { const int mine = bm[t]; if (mine >= 0) atomicAdd(acc.cnt + mine, 1); }
-                if (acc.vec) {
-                    if (d4 <= 32) {
-                        const int lanes_per_row = d4 <= 1 ? 1 : d4 <= 2 ? 2 : d4 <= 4 ? 4 : d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
-                        const int rows_per_pass = 32 / lanes_per_row;
-                        const int sub = lane / lanes_per_row, c4 = lane % lanes_per_row;
-                        for (int r = wq * rows_per_pass + sub; r < BM; r += 4 * rows_per_pass) {
-                            const int bb = bm[r];
-                            if (bb >= 0 && c4 < d4) {
-                                const float4 v = __ldg(reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx) + c4);
-                                red_add_v4(acc.S + (int64_t)bb * acc.d + c4 * 4, v);
-                            }
-                        }
-                    } else {
-                        for (int r = wq; r < BM; r += 4) {
-                            const int bb = bm[r];
-                            if (bb < 0) continue;
-                            const float4 *xr = reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx);
-                            float *sr = acc.S + (int64_t)bb * acc.d;
-                            for (int c4 = lane; c4 < d4; c4 += 32) red_add_v4(sr + c4 * 4, __ldg(xr + c4));
-                        }
-                    }
-                } else {
-                    for (int r = wq; r < BM; r += 4) {
-                        const int bb = bm[r];
-                        if (bb < 0) continue;
-                        for (int cc = lane; cc < acc.d; cc += 32)
-                            atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
-                    }
-                }
+                scatter_rows_exact<tc::SCAT_NBUF>(acc, bmu_s + b * BM, row0, BM, wq, 4, lane, stage, bulk_it);
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
             }
+            bulk_wait_all();          // every bulk reduction of this thread has been performed
         }
     }
 
@@ -416,25 +386,10 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     cluster_sync();                      // the peer may still be signalling this CTA's barriers / reading its SMEM
     if (warp == 1) { tc::tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
 
-    if (fused) {
-        if (threadIdx.x == 0) {
-            __threadfence();
-            last_cta = (atomicAdd(acc.done, 1u) == gridDim.x - 1) ? 1u : 0u;
-        }
-        __syncthreads();
-        if (last_cta) {
-            __threadfence();
-            for (int i = threadIdx.x; i < acc.k; i += blockDim.x) {
-                const int v = atomicExch(acc.cnt + i, 0);
-                if (v) atomicAdd(acc.c + i, (float)v);
-            }
-            if (threadIdx.x == 0) *acc.done = 0u;
-        }
-    }
 }
 
 inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, const WsLayout &L, uint8_t *ws,
-                          int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
+                          int32_t *bmu, float *best, const AccTarget &T, int sm_count, cudaStream_t st) {
     SOM_REQUIRE(L.k_pad < (1 << 24), SOM_E_SHAPE,
                 "tensor-core BMU kernels track the winning neuron as an exact fp32 integer: at most 2^24 neurons (k=%d)", k);
     SOM_REQUIRE(tc::shape_ok(X, n, d, ldx), SOM_E_SHAPE,
@@ -456,10 +411,9 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     if (pairs > num_pair_tiles) pairs = num_pair_tiles;
     if (pairs < 1) pairs = 1;
     FusedAcc acc;
-    acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = S; acc.c = c;
-    acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
-    acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
-    acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+    acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = T.S; acc.cnt = T.cnt; acc.qscale = T.qscale;
+    acc.lds = acc_ld(d);
+    acc.vec = (d % 4 == 0) ? 1 : 0;              // X rows are 16-byte aligned here (tc::shape_ok)
     static const int dbg = tc::env_int("SOM_B200_DBG");
     acc.dbg = dbg;
     static const int no_res = tc::env_int("SOM_B200_TC2_STREAM");     // A/B measurements: force the streaming variant

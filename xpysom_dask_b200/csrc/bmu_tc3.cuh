@@ -21,6 +21,21 @@
 //   B ring (3 slots): this CTA's half (128 neurons) of the W'hi and W'lo fp16 tiles.
 // 12 MMAs (M=256 N=256 K=16 over the CTA pair) per 64-feature block.
 //
+// Three instantiations of the pipeline (MODE):
+//   0  resident   D <= 128: the converted X tiles of a row tile stay in shared memory across its neuron tiles
+//   1  streaming  larger D: X chunks stream once per neuron tile
+//   2  packed     D <= 16 (resident): ONE 64-column tile carries the three products of the split as three 16-column
+//                 K steps -- x^ = [hi | lo | hi | 0] against w^ = [hi | hi | lo | 0] (prepared by codebook_split_kernel):
+//                 3 MMAs per neuron tile instead of 7 on the TF32 kernel, half the W' traffic.
+// FOLD (resident, one feature block: D <= 64): the bias joins the contraction through ONE extra kind::tf32 MMA per
+// neuron tile, acc += u_r * B_k with u_r = 2^a_r (the row scale, exact in TF32) and B_k = bias_k 2^b_k split into three
+// TF32 pieces (33 bits; TF32's 8-bit exponent has no range problem where an fp16 fold column would overflow).  The
+// epilogue then only compares raw accumulators: 3 instructions per score instead of 4.25 (the epilogue is bound by
+// instruction issue: 128 x 256 scores / 32 lanes / 4 schedulers).  The fold operands are 32 bytes per row in the
+// no-swizzle K-major core-matrix layout: A_f is written by the converter (one 16-byte store per row and row tile),
+// B_f arrives as a 4 KB image per 128 neurons (TMA, prepared by codebook_split_kernel).  With one feature block per
+// row tile the A ring needs two slots, the third one's shared memory hosts the fold operands.
+//
 // Warp roles per CTA (640 threads): 0 B producer | 1 MMA issuer (leader) + TMEM alloc | 2 A producer |
 // 3 spare | 4-7 converter | 8-15 epilogue (two warps per TMEM lane quarter) | 16-19 scatter.
 #pragma once
@@ -37,21 +52,40 @@ using tc::FusedAcc;
 using tc::smem_u32;
 using namespace tc2;   // cluster / 2-SM wrappers
 
-constexpr int BM = 128;                  // sample rows per CTA (TMEM lanes); the neuron-tile width is the TBN template argument
+constexpr int BM = 128;                  // sample rows per CTA (TMEM lanes)
+constexpr int TBN = 256;                 // neurons per accumulator tile (UMMA N over the pair); two stages in TMEM
+constexpr int TBNH = TBN / 2;            // this CTA's share of a neuron tile (B rows)
+constexpr int NACC = 2;
 constexpr int BK = 64;                   // features per block: 128 bytes of fp16
 constexpr int UMMA_K = 16;
 constexpr int NA = 3, NB = 3;
 constexpr int SLOT_BYTES = 32 * 1024;    // A: raw fp32 [128 x 64] -> hi | lo ;  B: W'hi half | W'lo half
 constexpr int HALF_SLOT = 16 * 1024;
+constexpr int FOLD_TILE_BYTES = 128 * 32;          // fold operand tile: 128 rows x 8 tf32
+constexpr int NAF = 2;                             // A ring slots when the bias is folded (one feature block per row tile):
+                                                   // the third slot's shared memory hosts the fold operands
+constexpr int NB_PACKED = 6;                       // W' ring of the packed mode: 16 KB slots
 constexpr int NUM_THREADS = 640;
 constexpr int APROD_WARP = 2, CONV_WARP0 = 4, EPI_WARP0 = 8, SCAT_WARP0 = 16;
 constexpr int EPI_THREADS = 256;
 constexpr int RESIDENT_MAX_KB = 2;       // D <= 128: X tiles resident across neuron tiles
-constexpr int MAX_ACC = 4;                 // accumulator stages in TMEM: 512 columns / neuron-tile width
-constexpr int NUM_BARS = 3 * NA + 2 * NB + 2 * MAX_ACC + 4;
+constexpr int MAXB = NB_PACKED;                    // barrier slots of the W' ring
+constexpr int NUM_BARS = 3 * NA + 2 * MAXB + 2 * NACC + 4;
 constexpr int EPI_STAGE_BYTES = 8 * 2 * 128 * 4;   // per epilogue warp: 128 bias + 128 inverse-scale floats
-constexpr int SMEM_BYTES = (NA + NB) * SLOT_BYTES + EPI_STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
+constexpr int SMEM_BYTES = (NA + NB) * SLOT_BYTES + EPI_STAGE_BYTES + tc::SCAT_STAGE_BYTES + 2 * BM * 8 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
+static_assert(SMEM_BYTES <= 227 * 1024, "shared memory of the fp16 kernel");
+static_assert(NAF * FOLD_TILE_BYTES + NB_PACKED * FOLD_TILE_BYTES <= SLOT_BYTES, "fold operands live in the third A slot");
 
+// no-swizzle ("interleave") K-major shared-memory matrix descriptor: 8-row x 16-byte core matrices; the two K chunks of
+// a 32-byte row are LBO bytes apart, consecutive 8-row groups SBO bytes apart (cute: ((8,n),2):((1,SBO),LBO) in 16-byte units)
+__device__ __forceinline__ uint64_t make_smem_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
 __device__ __forceinline__ void umma_f16_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n\t.reg .pred p;\n\t"
                  "setp.ne.b32 p, %4, 0;\n\t"
@@ -94,6 +128,21 @@ struct RunMinScaled : tc::RunMin {
             for (int e = 0; e < 4; ++e) {
                 const int j = j4 * 4 + e;
                 upd(j % tc::EPI_ACC, fmaf(bb[e], rsg, __uint_as_float(acc[j])), basef, (float)j);
+            }
+        }
+    }
+    // folded bias, per-neuron codebook scales: sc = acc * 2^-b_k
+    __device__ __forceinline__ void chunk_scaled_nobias(const uint32_t (&acc)[32], const float *winv32, int colbase) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(winv32);
+        const float basef = (float)colbase;
+#pragma unroll
+        for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 s = s4[j4];
+            const float ss[4] = {s.x, s.y, s.z, s.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int j = j4 * 4 + e;
+                upd(j % tc::EPI_ACC, __uint_as_float(acc[j]) * ss[e], basef, (float)j);
             }
         }
     }
@@ -151,26 +200,64 @@ __device__ __forceinline__ void convert_item(uint8_t *slot, int t, int64_t row0,
     }
 }
 
-// STREAM = false: D <= 128, X tiles resident across neuron tiles, 4 converter + 8 epilogue warps.
-// STREAM = true : larger D, X tiles stream once per neuron tile, 8 converter + 4 epilogue warps.
-// TBN = neuron-tile width: 256 (two accumulator stages in TMEM, the default) or 128 (four stages, so the MMAs of up
-// to three tiles queue while the epilogue drains one).  Measured on B200: the four-stage variant is 20-30 % SLOWER
-// (config 2: 0.44 vs 0.36 ms) -- the per-tile hand-off cost, not its latency, is what the short tiles pay for --
-// so it is kept only as the SOM_B200_TBN=128 experiment.
-template <bool STREAM, int TBN>
+// Packed A item (D <= 16): thread t owns row t of the raw box [128 rows x 32 floats] (only the first 16 floats are
+// features, the rest is the TMA zero fill) and rewrites the row, in place, as 64 halves [hi | lo | hi | 0] x 16.
+__device__ __forceinline__ void convert_item_packed(uint8_t *slot, int t, float rs) {
+    const int sw = t & 7;
+    float4 v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = *reinterpret_cast<const float4 *>(slot + t * 128 + ((j ^ sw) << 4));
+    asm volatile("bar.sync 2, 128;" ::: "memory");                          // everyone has read the box
+    uint32_t hi[8], lo[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float x0 = v[j].x * rs, x1 = v[j].y * rs, x2 = v[j].z * rs, x3 = v[j].w * rs;
+        const __half2 h01 = __floats2half2_rn(x0, x1), h23 = __floats2half2_rn(x2, x3);
+        const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+        const __half2 l01 = __floats2half2_rn(x0 - f01.x, x1 - f01.y);
+        const __half2 l23 = __floats2half2_rn(x2 - f23.x, x3 - f23.y);
+        hi[2 * j] = *reinterpret_cast<const uint32_t *>(&h01); hi[2 * j + 1] = *reinterpret_cast<const uint32_t *>(&h23);
+        lo[2 * j] = *reinterpret_cast<const uint32_t *>(&l01); lo[2 * j + 1] = *reinterpret_cast<const uint32_t *>(&l23);
+    }
+    // logical 16-byte chunks of the 128-byte row: 0,1 = hi | 2,3 = lo | 4,5 = hi | 6,7 = zero
+    uint8_t *row = slot + t * 128;
+    const uint4 h0 = make_uint4(hi[0], hi[1], hi[2], hi[3]), h1 = make_uint4(hi[4], hi[5], hi[6], hi[7]);
+    const uint4 l0 = make_uint4(lo[0], lo[1], lo[2], lo[3]), l1 = make_uint4(lo[4], lo[5], lo[6], lo[7]);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    *reinterpret_cast<uint4 *>(row + ((0 ^ sw) << 4)) = h0;
+    *reinterpret_cast<uint4 *>(row + ((1 ^ sw) << 4)) = h1;
+    *reinterpret_cast<uint4 *>(row + ((2 ^ sw) << 4)) = l0;
+    *reinterpret_cast<uint4 *>(row + ((3 ^ sw) << 4)) = l1;
+    *reinterpret_cast<uint4 *>(row + ((4 ^ sw) << 4)) = h0;
+    *reinterpret_cast<uint4 *>(row + ((5 ^ sw) << 4)) = h1;
+    *reinterpret_cast<uint4 *>(row + ((6 ^ sw) << 4)) = z;
+    *reinterpret_cast<uint4 *>(row + ((7 ^ sw) << 4)) = z;
+}
+
+constexpr int MODE_RESIDENT = 0, MODE_STREAM = 1, MODE_PACKED = 2;
+
+template <int MODE, bool FOLD>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NUM_THREADS, 1)
 bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_whi,
-               const __grid_constant__ CUtensorMap map_wlo, const float *__restrict__ bias,
-               const float *__restrict__ wsinv, const unsigned int *__restrict__ gstat,
+               const __grid_constant__ CUtensorMap map_wlo, const __grid_constant__ CUtensorMap map_fold,
+               const float *__restrict__ bias, const float *__restrict__ wsinv, const unsigned int *__restrict__ gstat,
                const float *__restrict__ xscale, int64_t n, int num_pair_tiles, int num_n_tiles, int num_k_blocks,
                int32_t *__restrict__ bmu_out, float *__restrict__ best_out, const FusedAcc acc) {
+    static_assert(!(FOLD && MODE == MODE_STREAM), "the bias is folded only with resident X tiles");
+    static_assert(!(MODE == MODE_PACKED && !FOLD), "the packed mode always folds");
     pdl_wait(); pdl_trigger();        // programmatic dependent launch (common.cuh)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     uint8_t *smem = smem_raw + (smem_base - smem_u32(smem_raw));
+    constexpr int NAR = FOLD ? NAF : NA;                      // A ring slots in use
+    constexpr int NBR = MODE == MODE_PACKED ? NB_PACKED : NB; // W' ring slots (packed: one 16 KB tile per slot)
+    constexpr int BSLOT = MODE == MODE_PACKED ? HALF_SLOT : SLOT_BYTES;
     const uint32_t a_base = smem_base, b_base = smem_base + NA * SLOT_BYTES;
+    // fold operands in the third A slot: A_f ring (one tile per A slot in use), then the B_f ring (one tile per W' slot)
+    const uint32_t af_base = a_base + NAF * SLOT_BYTES, bf_base = af_base + NAF * FOLD_TILE_BYTES;
     float *epi_stage = reinterpret_cast<float *>(smem + (NA + NB) * SLOT_BYTES);
-    uint8_t *tail = smem + (NA + NB) * SLOT_BYTES + EPI_STAGE_BYTES;
+    uint8_t *scat_stage = smem + (NA + NB) * SLOT_BYTES + EPI_STAGE_BYTES;                 // [4 warps][SCAT_NBUF][128] int64
+    uint8_t *tail = scat_stage + tc::SCAT_STAGE_BYTES;
 
     float    *mrg_v = reinterpret_cast<float *>(tail);                   // [2][BM]
     int      *mrg_i = reinterpret_cast<int *>(tail + 2 * BM * 4);        // [2][BM]
@@ -181,39 +268,38 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     auto aready_bar = [&](int s) { return bar0 + 8u * (NA + s); };                // leader: both converters done
     auto aempty_bar = [&](int s) { return bar0 + 8u * (2 * NA + s); };            // local: A slot consumed
     auto bfull_bar  = [&](int s) { return bar0 + 8u * (3 * NA + s); };            // leader: both W' halves landed
-    auto bempty_bar = [&](int s) { return bar0 + 8u * (3 * NA + NB + s); };       // local: B slot consumed
-    auto tfull_bar  = [&](int a) { return bar0 + 8u * (3 * NA + 2 * NB + a); };
-    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * NA + 2 * NB + MAX_ACC + a); };
-    auto bfullq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * NB + 2 * MAX_ACC + b); };
-    auto bemptyq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * NB + 2 * MAX_ACC + 2 + b); };
-    constexpr int TBNH = TBN / 2;                            // this CTA's share of a neuron tile (B rows)
-    constexpr int NACC = 512 / TBN;                          // accumulator stages
+    auto bempty_bar = [&](int s) { return bar0 + 8u * (3 * NA + MAXB + s); };     // local: B slot consumed
+    auto tfull_bar  = [&](int a) { return bar0 + 8u * (3 * NA + 2 * MAXB + a); };
+    auto tempty_bar = [&](int a) { return bar0 + 8u * (3 * NA + 2 * MAXB + NACC + a); };
+    auto bfullq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * MAXB + 2 * NACC + b); };
+    auto bemptyq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * MAXB + 2 * NACC + 2 + b); };
     constexpr uint32_t kIdescF16 = idesc_f16(TBN);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + NUM_BARS);
-    __shared__ unsigned int last_cta;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const bool fused = acc.S != nullptr;
-    constexpr bool resident = !STREAM;                       // A tiles live across the neuron tiles
+    constexpr bool resident = MODE != MODE_STREAM;           // A tiles live across the neuron tiles
+    constexpr bool packed = MODE == MODE_PACKED;
     const bool uniform = gstat[2] != 0u;                     // one power-of-two scale for the whole codebook
     // Streaming mode (large D) converts one X chunk per MMA block, which 4 warps cannot sustain, while the
     // epilogue has a whole row of k blocks per tile to drain one accumulator: epilogue warps 12-15 join the
     // converter and warps 8-11 drain all 256 columns.
-    constexpr bool conv_extra = STREAM;
+    constexpr bool conv_extra = MODE == MODE_STREAM;
     constexpr int nconv = conv_extra ? 256 : 128;            // converter threads per CTA
     constexpr int nepi = conv_extra ? 128 : 256;             // epilogue threads per CTA
     const int probe = (acc.dbg == 9 && blockIdx.x == 0) ? 1 : 0;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NA; ++s) { tc::mbar_init(afull_bar(s), 1); tc::mbar_init(aready_bar(s), 2 * nconv / 32); tc::mbar_init(aempty_bar(s), 1); }
-        for (int s = 0; s < NB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
+        for (int s = 0; s < MAXB; ++s) { tc::mbar_init(bfull_bar(s), 1); tc::mbar_init(bempty_bar(s), 1); }
         for (int a = 0; a < NACC; ++a) { tc::mbar_init(tfull_bar(a), 1); tc::mbar_init(tempty_bar(a), 2 * nepi / 32); }
         for (int b = 0; b < 2; ++b) { tc::mbar_init(bfullq_bar(b), 4); tc::mbar_init(bemptyq_bar(b), 4); }
         tc::fence_barrier_init();
         tc::tma_prefetch_desc(&map_x); tc::tma_prefetch_desc(&map_whi); tc::tma_prefetch_desc(&map_wlo);
+        if (FOLD) tc::tma_prefetch_desc(&map_fold);
     }
     if (warp == 1) tmem_alloc_2sm(smem_u32((const void *)tmem_slot), 512);
     tc::tc_fence_before();
@@ -229,13 +315,16 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs)
                 for (int nt = 0; nt < num_n_tiles; ++nt)
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
-                        const int s = it % NB; const uint32_t ph = (it / NB) & 1;
+                        const int s = it % NBR; const uint32_t ph = (it / NBR) & 1;
                         tc::mbar_wait(bempty_bar(s), ph ^ 1);
-                        const uint32_t st = b_base + s * SLOT_BYTES;
+                        const uint32_t st = b_base + s * BSLOT;
                         if (tc::elect_one()) {
-                            if (leader) tc::mbar_expect_tx(bfull_bar(s), 4 * TBNH * 128);   // hi + lo of both CTAs
-                            tma_load_2d_2sm(st,             &map_whi, kb * BK, nt * TBN + (int)rank * TBNH, bfull_bar(s));
-                            tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nt * TBN + (int)rank * TBNH, bfull_bar(s));
+                            // bytes of both CTAs: hi (+ lo unless packed) halves (+ the fold images)
+                            if (leader) tc::mbar_expect_tx(bfull_bar(s), (packed ? 2 : 4) * TBNH * 128 + (FOLD ? 2 * FOLD_TILE_BYTES : 0));
+                            tma_load_2d_2sm(st, &map_whi, kb * BK, nt * TBN + (int)rank * TBNH, bfull_bar(s));
+                            if (!packed) tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nt * TBN + (int)rank * TBNH, bfull_bar(s));
+                            if (FOLD)      // this CTA's 4 KB fold image: 16 rows of 64 floats of the (k_pad / 8, 64) view, no swizzle
+                                tma_load_2d_2sm(bf_base + s * FOLD_TILE_BYTES, &map_fold, 0, (nt * 2 + (int)rank) * 16, bfull_bar(s));
                         }
                         __syncwarp();
                     }
@@ -248,14 +337,14 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 const int reps = resident ? 1 : num_n_tiles;
                 for (int rep = 0; rep < reps; ++rep)
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++ia) {
-                        const int s = ia % NA; const uint32_t ph = (ia / NA) & 1;
+                        const int s = ia % NAR; const uint32_t ph = (ia / NAR) & 1;
                         tc::mbar_wait(aempty_bar(s), ph ^ 1);
                         const uint32_t st = a_base + s * SLOT_BYTES;
                         const int row0 = pt * (2 * BM) + (int)rank * BM;
                         if (tc::elect_one()) {
-                            tc::mbar_expect_tx(afull_bar(s), SLOT_BYTES);
-                            tc::tma_load_2d(st,             &map_x, kb * BK,      row0, afull_bar(s));
-                            tc::tma_load_2d(st + HALF_SLOT, &map_x, kb * BK + 32, row0, afull_bar(s));
+                            tc::mbar_expect_tx(afull_bar(s), packed ? HALF_SLOT : SLOT_BYTES);
+                            tc::tma_load_2d(st, &map_x, kb * BK, row0, afull_bar(s));
+                            if (!packed) tc::tma_load_2d(st + HALF_SLOT, &map_x, kb * BK + 32, row0, afull_bar(s));
                         }
                         __syncwarp();
                     }
@@ -272,8 +361,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const uint32_t tmem_d = tmem_base + (uint32_t)(a * TBN);
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                         const uint32_t ia = resident ? (tile_it * (uint32_t)num_k_blocks + kb) : it;
-                        const int sa = ia % NA; const uint32_t pha = (ia / NA) & 1;
-                        const int sb = it % NB; const uint32_t phb = (it / NB) & 1;
+                        const int sa = ia % NAR; const uint32_t pha = (ia / NAR) & 1;
+                        const int sb = it % NBR; const uint32_t phb = (it / NBR) & 1;
                         mbar_wait_cluster(aready_bar(sa), pha);       // hi/lo tiles of both CTAs written
                         mbar_wait_cluster(bfull_bar(sb), phb);        // W' halves of both CTAs landed
                         if (kb == 0) {                                // operands first, then the accumulator
@@ -282,20 +371,32 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         }
                         tc::tc_fence_after();
                         if (kb == 0) tc::dbg_stamp(probe, 2, acc_it);    // MMA: operands of the first k block ready
-                        const uint32_t sta = a_base + sa * SLOT_BYTES, stb = b_base + sb * SLOT_BYTES;
+                        const uint32_t sta = a_base + sa * SLOT_BYTES, stb = b_base + sb * BSLOT;
                         const uint64_t a_hi = tc::make_smem_desc(sta), a_lo = tc::make_smem_desc(sta + HALF_SLOT);
                         const uint64_t b_hi = tc::make_smem_desc(stb), b_lo = tc::make_smem_desc(stb + HALF_SLOT);
                         const int dl = acc.d - kb * BK;          // real features in this block; the rest is zero fill
                         const int kk_n = dl >= BK ? BK / UMMA_K : (dl + UMMA_K - 1) / UMMA_K;
                         if (tc::elect_one()) {
+                            if (packed) {
+                                // one tile, three K steps: hi*hi, lo*hi, hi*lo (operands packed along K)
 #pragma unroll
-                            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                                if (kk >= kk_n) break;
-                                const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);    // +32 B along K
-                                umma_f16_2sm(tmem_d, a_lo + off, b_hi + off, kIdescF16, (kb | kk) != 0);
-                                umma_f16_2sm(tmem_d, a_hi + off, b_lo + off, kIdescF16, 1);
-                                umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, kIdescF16, 1);
+                                for (int kk = 0; kk < 3; ++kk) {
+                                    const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);
+                                    umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, kIdescF16, kk != 0);
+                                }
+                            } else {
+#pragma unroll
+                                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                                    if (kk >= kk_n) break;
+                                    const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);    // +32 B along K
+                                    umma_f16_2sm(tmem_d, a_lo + off, b_hi + off, kIdescF16, (kb | kk) != 0);
+                                    umma_f16_2sm(tmem_d, a_hi + off, b_lo + off, kIdescF16, 1);
+                                    umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, kIdescF16, 1);
+                                }
                             }
+                            if (FOLD)      // acc += 2^a_r * (bias_k 2^b_k): one kind::tf32 step, K = 8 (three pieces + zeros)
+                                umma_tf32_2sm(tmem_d, make_smem_desc_nosw(af_base + sa * FOLD_TILE_BYTES, 128, 256),
+                                              make_smem_desc_nosw(bf_base + sb * FOLD_TILE_BYTES, 128, 256), kIdesc2, 1);
                             umma_commit_2sm(bempty_bar(sb));
                             if (!resident || nt == num_n_tiles - 1) umma_commit_2sm(aempty_bar(sa));
                             if (kb == num_k_blocks - 1) {
@@ -317,11 +418,20 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
             for (int rep = 0; rep < reps; ++rep)
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++ia) {
-                    const int s = ia % NA; const uint32_t ph = (ia / NA) & 1;
+                    const int s = ia % NAR; const uint32_t ph = (ia / NAR) & 1;
+                    float rs_t = 1.f;                         // scale of THIS thread's row (fold operand, packed tile)
+                    if ((FOLD || packed) && row0 + t < n) rs_t = __ldg(xscale + row0 + t);
                     tc::mbar_wait(afull_bar(s), ph);
                     uint8_t *slot = smem + s * SLOT_BYTES;
-                    if (conv_extra) convert_item<256>(slot, t, row0, n, xscale);
-                    else            convert_item<128>(slot, t, row0, n, xscale);
+                    if (packed)          convert_item_packed(slot, t, rs_t);
+                    else if (conv_extra) convert_item<256>(slot, t, row0, n, xscale);
+                    else                 convert_item<128>(slot, t, row0, n, xscale);
+                    if (FOLD) {
+                        // A_f row t: K chunk 0 = (u, u, u, 0) with u = 2^a_r, K chunk 1 = 0 (no-swizzle K-major core matrices)
+                        uint8_t *af = smem + (af_base - smem_base) + s * FOLD_TILE_BYTES + (t >> 3) * 256 + (t & 7) * 16;
+                        *reinterpret_cast<float4 *>(af) = make_float4(rs_t, rs_t, rs_t, 0.f);
+                        *reinterpret_cast<float4 *>(af + 128) = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
                     tc::fence_proxy_async();
                     __syncwarp();                                           // one arrival per warp (see bmu_tc2.cuh)
                     if (lane == 0) mbar_arrive_cluster(map_to_cta(aready_bar(s), 0));
@@ -337,7 +447,10 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
         const bool ld_lane = lane < ncols / 4 || conv_extra;       // lanes that stage this warp's bias slice
         const int row_in_tile = q * 32 + lane;
         const float winv0 = __ldg(wsinv);                    // 2^-b of the uniform codebook scale
-        // this warp's private shared-memory slice: ncols bias values, then ncols inverse scales
+        // folded bias + uniform codebook scale: the raw accumulator is already a row-constant multiple of the score,
+        // nothing is staged; otherwise this warp's private shared-memory slice holds ncols bias values, then ncols
+        // inverse scales
+        const bool staged = !(FOLD && uniform);
         float *wb = epi_stage + (warp - EPI_WARP0) * (conv_extra ? 512 : 256);
         float *wsv = wb + ncols;
         uint32_t acc_it = 0, tile_it = 0;
@@ -348,7 +461,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             if (pair < num_pair_tiles && row < n) rs_next = __ldg(xscale + row);
         }
         float4 nb = make_float4(0.f, 0.f, 0.f, 0.f), ns = nb;
-        if (ld_lane) {
+        if (staged && ld_lane) {
             nb = __ldg(reinterpret_cast<const float4 *>(bias + h * (TBN / 2)) + lane);
             ns = __ldg(reinterpret_cast<const float4 *>(wsinv + h * (TBN / 2)) + lane);
         }
@@ -370,25 +483,27 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             for (int nt = 0; nt < num_n_tiles; ++nt, ++acc_it) {
                 const int a = acc_it % NACC; const uint32_t aph = (acc_it / NACC) & 1;
                 const int col0 = nt * TBN + h * (TBN / 2);
-                __syncwarp();
-                if (ld_lane) {
-                    reinterpret_cast<float4 *>(wb)[lane] = nb;
-                    reinterpret_cast<float4 *>(wsv)[lane] = ns;
-                }
-                if (conv_extra) {
-                    reinterpret_cast<float4 *>(wb + 128)[lane] = nb2;
-                    reinterpret_cast<float4 *>(wsv + 128)[lane] = ns2;
-                }
-                __syncwarp();
-                {   // prefetch the next neuron tile's slice (wraps to tile 0 for the next row tile)
-                    const int nn = (nt + 1 < num_n_tiles ? nt + 1 : 0) * TBN + h * (TBN / 2);
+                if (staged) {
+                    __syncwarp();
                     if (ld_lane) {
-                        nb = __ldg(reinterpret_cast<const float4 *>(bias + nn) + lane);
-                        ns = __ldg(reinterpret_cast<const float4 *>(wsinv + nn) + lane);
+                        reinterpret_cast<float4 *>(wb)[lane] = nb;
+                        reinterpret_cast<float4 *>(wsv)[lane] = ns;
                     }
                     if (conv_extra) {
-                        nb2 = __ldg(reinterpret_cast<const float4 *>(bias + nn + 128) + lane);
-                        ns2 = __ldg(reinterpret_cast<const float4 *>(wsinv + nn + 128) + lane);
+                        reinterpret_cast<float4 *>(wb + 128)[lane] = nb2;
+                        reinterpret_cast<float4 *>(wsv + 128)[lane] = ns2;
+                    }
+                    __syncwarp();
+                    {   // prefetch the next neuron tile's slice (wraps to tile 0 for the next row tile)
+                        const int nn = (nt + 1 < num_n_tiles ? nt + 1 : 0) * TBN + h * (TBN / 2);
+                        if (ld_lane) {
+                            nb = __ldg(reinterpret_cast<const float4 *>(bias + nn) + lane);
+                            ns = __ldg(reinterpret_cast<const float4 *>(wsinv + nn) + lane);
+                        }
+                        if (conv_extra) {
+                            nb2 = __ldg(reinterpret_cast<const float4 *>(bias + nn + 128) + lane);
+                            ns2 = __ldg(reinterpret_cast<const float4 *>(wsinv + nn + 128) + lane);
+                        }
                     }
                 }
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 4, acc_it);   // EPI: starts waiting for the tile
@@ -396,13 +511,24 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 tc::tc_fence_after();
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 5, acc_it);   // EPI: tile complete in TMEM
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * TBN + h * (TBN / 2));
+                auto drain = [&](const uint32_t (&v)[32], int c) {
+                    if (FOLD) {
+                        if (uniform) rm.chunk_nobias(v, col0 + c * 32);
+                        else         rm.chunk_scaled_nobias(v, wsv + c * 32, col0 + c * 32);
+                    } else {
+                        if (uniform) rm.chunk_uniform(v, wb + c * 32, rsg, col0 + c * 32);
+                        else         rm.chunk(v, wb + c * 32, wsv + c * 32, rs, col0 + c * 32);
+                    }
+                };
+                // (measured in round 2: a second tcgen05.ld buffer in flight, 64-column loads and 8 instead of 4 running
+                // minima all made this loop SLOWER or no faster -- the drain of a 128 x 256 tile takes ~1400 cycles, which
+                // is the TMEM read rate (~90 bytes per clock and SM), not instruction issue or dependency latency)
 #pragma unroll 1
                 for (int c = 0; c < ncols / 32; ++c) {
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait_dep(v);
-                    if (uniform) rm.chunk_uniform(v, wb + c * 32, rsg, col0 + c * 32);
-                    else         rm.chunk(v, wb + c * 32, wsv + c * 32, rs, col0 + c * 32);
+                    drain(v, c);
                 }
                 tc::tc_fence_before();
                 if (warp == EPI_WARP0 && lane == 0) tc::dbg_stamp(probe, 6, acc_it);   // EPI: this warp drained its half
@@ -420,7 +546,8 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                 if (!conv_extra) argmin_merge(best, bidx, mrg_v[mb + row_in_tile], mrg_i[mb + row_in_tile]);
                 if (row < n) {
                     if (bmu_out) bmu_out[row] = bidx;
-                    if (best_out) best_out[row] = uniform ? best / rsg : best / rs;   // undo the scaling (exact)
+                    // undo the scaling (exact powers of two): the score x . w' + bias
+                    if (best_out) best_out[row] = FOLD ? (uniform ? best * winv0 / rs : best / rs) : (uniform ? best / rsg : best / rs);
                 }
                 if (fused) {
                     const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
@@ -432,50 +559,20 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             }
         }
     } else if (warp >= SCAT_WARP0) {
-        // ===================== scatter: S[bmu[r], :] += X[r, :], cnt[bmu[r]] += 1 ================================
+        // ===================== scatter: exact per-BMU sums (common.cuh: scatter_rows_exact) =====================
         if (fused) {
-            const int t = threadIdx.x - SCAT_WARP0 * 32;
             const int wq = warp - SCAT_WARP0;
-            const int d4 = acc.d >> 2;
-            uint32_t tile_it = 0;
+            long long *stage = reinterpret_cast<long long *>(scat_stage) + wq * (tc::SCAT_NBUF * ACC_PIECE);
+            uint32_t tile_it = 0, bulk_it = 0;
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
                 const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                 tc::mbar_wait_relaxed(bfullq_bar(b), bph, 400);
-                const int *bm = bmu_s + b * BM;
                 const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
-                { const int mine = bm[t]; if (mine >= 0) atomicAdd(acc.cnt + mine, 1); }
-                if (acc.vec) {
-                    if (d4 <= 32) {
-                        const int lanes_per_row = d4 <= 1 ? 1 : d4 <= 2 ? 2 : d4 <= 4 ? 4 : d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
-                        const int rows_per_pass = 32 / lanes_per_row;
-                        const int sub = lane / lanes_per_row, c4 = lane % lanes_per_row;
-                        for (int r = wq * rows_per_pass + sub; r < BM; r += 4 * rows_per_pass) {
-                            const int bb = bm[r];
-                            if (bb >= 0 && c4 < d4) {
-                                const float4 v = __ldg(reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx) + c4);
-                                red_add_v4(acc.S + (int64_t)bb * acc.d + c4 * 4, v);
-                            }
-                        }
-                    } else {
-                        for (int r = wq; r < BM; r += 4) {
-                            const int bb = bm[r];
-                            if (bb < 0) continue;
-                            const float4 *xr = reinterpret_cast<const float4 *>(acc.X + (row0 + r) * acc.ldx);
-                            float *sr = acc.S + (int64_t)bb * acc.d;
-                            for (int c4 = lane; c4 < d4; c4 += 32) red_add_v4(sr + c4 * 4, __ldg(xr + c4));
-                        }
-                    }
-                } else {
-                    for (int r = wq; r < BM; r += 4) {
-                        const int bb = bm[r];
-                        if (bb < 0) continue;
-                        for (int cc = lane; cc < acc.d; cc += 32)
-                            atomicAdd(acc.S + (int64_t)bb * acc.d + cc, __ldg(acc.X + (row0 + r) * acc.ldx + cc));
-                    }
-                }
+                scatter_rows_exact<tc::SCAT_NBUF>(acc, bmu_s + b * BM, row0, BM, wq, 4, lane, stage, bulk_it);
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
             }
+            bulk_wait_all();          // every bulk reduction of this thread has been performed
         }
     }
 
@@ -483,22 +580,6 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     tc::tc_fence_before();
     cluster_sync();
     if (warp == 1) { tc::tc_fence_after(); tmem_dealloc_2sm(tmem_base, 512); }
-
-    if (fused) {
-        if (threadIdx.x == 0) {
-            __threadfence();
-            last_cta = (atomicAdd(acc.done, 1u) == gridDim.x - 1) ? 1u : 0u;
-        }
-        __syncthreads();
-        if (last_cta) {
-            __threadfence();
-            for (int i = threadIdx.x; i < acc.k; i += blockDim.x) {
-                const int v = atomicExch(acc.cnt + i, 0);
-                if (v) atomicAdd(acc.c + i, (float)v);
-            }
-            if (threadIdx.x == 0) *acc.done = 0u;
-        }
-    }
 }
 
 inline int make_map_2d_f16(CUtensorMap *m, const void *base, uint64_t inner, uint64_t outer, uint64_t row_stride_bytes,
@@ -517,38 +598,40 @@ inline int make_map_2d_f16(CUtensorMap *m, const void *base, uint64_t inner, uin
 }
 
 inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const float *xscale, int k, const WsLayout &L,
-                          uint8_t *ws, int32_t *bmu, float *best, float *S, float *c, int sm_count, cudaStream_t st) {
+                          uint8_t *ws, int32_t *bmu, float *best, const AccTarget &T, int sm_count, cudaStream_t st) {
     SOM_REQUIRE(L.k_pad < (1 << 24), SOM_E_SHAPE,
                 "tensor-core BMU kernels track the winning neuron as an exact fp32 integer: at most 2^24 neurons (k=%d)", k);
     SOM_REQUIRE(tc::shape_ok(X, n, d, ldx), SOM_E_SHAPE,
                 "tensor-core BMU kernel needs ldx %% 4 == 0 and a 16-byte aligned X for TMA (d=%d ldx=%lld)", d, (long long)ldx);
     SOM_REQUIRE(xscale != nullptr, SOM_E_BADARG, "the fp16-split kernel needs the per-row scales (som_b200_prepare_samples)");
     const int num_k_blocks = L.d_pad64 / BK;
+    const bool packed = d <= 16;
     const bool resident = num_k_blocks <= RESIDENT_MAX_KB;
-    int tbn = 256;      // SOM_B200_TBN=128: four-accumulator-stage experiment (resident mode only; slower, see above)
-    static const int tbn_env = tc::env_int("SOM_B200_TBN");
-    if (resident && tbn_env == 128) tbn = 128;
-    CUtensorMap mx, mhi, mlo;
+    static const int no_fold = tc::env_int("SOM_B200_NO_FOLD");        // experiments builds: bias in the epilogue
+    const bool fold = packed || (resident && num_k_blocks == 1 && !no_fold);
+    CUtensorMap mx, mhi, mlo, mfold;
     int rc;
     if ((rc = tc::make_map_2d(&mx, X, (uint64_t)d, (uint64_t)n, (uint64_t)ldx * 4, 32, BM))) return rc;
-    if ((rc = make_map_2d_f16(&mhi, ws + L.w16hi_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, tbn / 2))) return rc;
-    if ((rc = make_map_2d_f16(&mlo, ws + L.w16lo_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, tbn / 2))) return rc;
+    // fold operand image: 4 KB per 128 neurons, viewed as rows of 64 floats; one box = 16 rows = one image, no swizzle
+    if ((rc = tc::make_map_2d(&mfold, ws + L.wfold_off, 64, (uint64_t)L.k_pad / 8, 256, 64, 16, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    if ((rc = make_map_2d_f16(&mhi, ws + L.w16hi_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, TBNH))) return rc;
+    if ((rc = make_map_2d_f16(&mlo, ws + L.w16lo_off, (uint64_t)L.d_pad64, (uint64_t)L.k_pad, (uint64_t)L.d_pad64 * 2, BK, TBNH))) return rc;
     static bool attr_set[64] = {};
     if (tc::first_launch_on_device(attr_set)) {
-        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<false, 128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<MODE_RESIDENT, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<MODE_RESIDENT, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<MODE_STREAM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        SOM_CUDA(cudaFuncSetAttribute(bmu_tc3_kernel<MODE_PACKED, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     }
     const int num_pair_tiles = (int)ceil_div(n, 2 * BM);
-    const int num_n_tiles = L.k_pad / tbn;
+    const int num_n_tiles = L.k_pad / TBN;
     int pairs = sm_count / 2;
     if (pairs > num_pair_tiles) pairs = num_pair_tiles;
     if (pairs < 1) pairs = 1;
     FusedAcc acc;
-    acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = S; acc.c = c;
-    acc.cnt = reinterpret_cast<int *>(ws + L.cnt_off);
-    acc.done = reinterpret_cast<unsigned int *>(ws + L.done_off);
-    acc.vec = (d % 4 == 0) && S != nullptr && ((reinterpret_cast<uintptr_t>(S) & 15) == 0);
+    acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = T.S; acc.cnt = T.cnt; acc.qscale = T.qscale;
+    acc.lds = acc_ld(d);
+    acc.vec = (d % 4 == 0) ? 1 : 0;              // X rows are 16-byte aligned here (tc::shape_ok)
     static const int dbg = tc::env_int("SOM_B200_DBG");
     acc.dbg = dbg;
     const float *bias_p = reinterpret_cast<const float *>(ws + L.bias_off);
@@ -556,15 +639,14 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     const unsigned int *gstat_p = reinterpret_cast<const unsigned int *>(ws + L.gstat_off);
     const dim3 grid(2 * pairs), block(NUM_THREADS);
     cudaError_t e;
-    if (resident && tbn == 128)
-        e = launch_pdl(bmu_tc3_kernel<false, 128>, grid, block, SMEM_BYTES, st, mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n,
-                       num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
-    else if (resident)
-        e = launch_pdl(bmu_tc3_kernel<false, 256>, grid, block, SMEM_BYTES, st, mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n,
-                       num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
-    else
-        e = launch_pdl(bmu_tc3_kernel<true, 256>, grid, block, SMEM_BYTES, st, mx, mhi, mlo, bias_p, wsinv_p, gstat_p, xscale, n,
-                       num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc);
+#define SOM_LAUNCH_TC3(M, F)                                                                                              \
+    e = launch_pdl(bmu_tc3_kernel<M, F>, grid, block, SMEM_BYTES, st, mx, mhi, mlo, mfold, bias_p, wsinv_p, gstat_p, xscale, n, \
+                   num_pair_tiles, num_n_tiles, num_k_blocks, bmu, best, acc)
+    if (packed)                SOM_LAUNCH_TC3(MODE_PACKED, true);
+    else if (resident && fold) SOM_LAUNCH_TC3(MODE_RESIDENT, true);
+    else if (resident)         SOM_LAUNCH_TC3(MODE_RESIDENT, false);
+    else                       SOM_LAUNCH_TC3(MODE_STREAM, false);
+#undef SOM_LAUNCH_TC3
     return check_cuda(e, "bmu_tc3_kernel launch");
 }
 

@@ -7,9 +7,11 @@
 // each with a launch gap between every pair -- 70 us of a 420 us epoch at config 2.  Here the phases run back
 // to back in one persistent grid, separated by grid-wide barriers:
 //
-//   phase 0  factor tables (fp64), num/den cleared when the apply is sliced, statistics cleared
-//   phase 1  apply, the same 64x64 tiles as neigh_apply_kernel<4, 4>, a linear tile index per CTA
-//   phase 2  one warp per neuron: merge, statistics of the new row, S row and c cleared
+//   phase 0  factor tables (fp64); the exact int64 per-BMU sums rounded once to the fp32 S, c the apply reads, and
+//            cleared for the next epoch (accumulate.cuh); statistics cleared
+//   phase 1  apply, the same 64x64 tiles as neigh_apply_kernel<4, 4>, a linear tile index per CTA; when the
+//            reduction over BMUs is sliced every slice writes its own partial block (no atomics)
+//   phase 2  one warp per neuron: partial blocks summed in slice order, merge, statistics of the new row
 //   phase 3  one warp per neuron: TF32 and fp16 operand copies (needs the codebook-wide statistics)
 //
 // Measured (B200, bench.py --steps 10, same box): 0.426 vs 0.438 ms per epoch at config 2; maps that take the 128x128
@@ -27,6 +29,10 @@ struct TailArgs {
     NeighParams P;
     double sigma, dd;
     float *S, *c, *num, *den, *W;
+    unsigned long long *Si, *ci;        // exact sums / counts (nullptr: S and c already hold this epoch's fp32 values)
+    const float *qinv;
+    int lds;
+    float *partials;                    // [slices][K*D + K] when slices > 1
     int k, d, dist_kind, k_pad;
     int slices, b_per_slice, tiles_m, tiles_n;
     float *aux, *bias, *amax;
@@ -68,9 +74,19 @@ epoch_tail_kernel(TailArgs A) {
     // ---- phase 0 ----
     neigh_tables_fill(A.P.gx, A.P.gy, A.P.kind, A.P.compact, A.P.shifted, A.sigma, A.dd, const_cast<float *>(A.P.tx),
                       const_cast<float *>(A.P.ty), const_cast<float *>(A.P.mx), const_cast<float *>(A.P.my), tid, nthr);
-    if (A.slices > 1) {
-        for (int64_t e = tid; e < (int64_t)K * D; e += nthr) A.num[e] = 0.f;
-        for (int e = tid; e < K; e += nthr) A.den[e] = 0.f;
+    if (A.Si != nullptr) {
+        const int64_t tot = (int64_t)K * A.lds;
+        for (int64_t e = tid; e < tot; e += nthr) {
+            const int row = (int)(e / A.lds), col = (int)(e % A.lds);
+            const long long v = (long long)A.Si[e];
+            if (col < D) A.S[(int64_t)row * D + col] = (float)((double)v * (double)A.qinv[col]);
+            if (v) A.Si[e] = 0ull;
+        }
+        for (int e = tid; e < K; e += nthr) {
+            const unsigned long long v = A.ci[e];
+            A.c[e] = (float)v;
+            if (v) A.ci[e] = 0ull;
+        }
     }
     if (tid < 4) A.gstat[tid] = 0u;
     grid_barrier(A.bar);
@@ -82,8 +98,10 @@ epoch_tail_kernel(TailArgs A) {
             const int by = r / A.tiles_m, bx = r % A.tiles_m;
             const int b_begin = bz * A.b_per_slice;
             const int b_end = min(K, b_begin + A.b_per_slice);
-            neigh_apply_tile<RM, RN>(A.P, A.P.inv_d, A.P.two_over_d, A.P.eta, A.S, A.c, A.num, A.den, bx * 16 * RM, by * 16 * RN,
-                                     b_begin, b_end, A.slices > 1, by == 0);
+            float *num = A.num, *den = A.den;
+            if (A.slices > 1) { num = A.partials + (size_t)bz * ((size_t)K * D + K); den = num + (size_t)K * D; }
+            neigh_apply_tile<RM, RN>(A.P, A.P.inv_d, A.P.two_over_d, A.P.eta, A.S, A.c, num, den, bx * 16 * RM, by * 16 * RN,
+                                     b_begin, b_end, by == 0);
         }
     }
     grid_barrier(A.bar);
@@ -94,15 +112,29 @@ epoch_tail_kernel(TailArgs A) {
         double s = 0.0;
         float m = 0.f;
         if (real) {
-            const float dn = A.den[row];
+            const size_t block = (size_t)K * D + K;
+            float dn;
+            if (A.slices > 1) {
+                dn = 0.f;
+                for (int z = 0; z < A.slices; ++z) dn += A.partials[(size_t)z * block + (size_t)K * D + row];
+            } else {
+                dn = A.den[row];
+            }
             for (int cc = lane; cc < D; cc += 32) {
                 const int64_t e = (int64_t)row * D + cc;
                 float v = A.W[e];
-                if (dn != 0.f) { v = __fdiv_rn(A.num[e], dn); A.W[e] = v; }        // xpysom.py:451-455
+                if (dn != 0.f) {
+                    float nm;
+                    if (A.slices > 1) {
+                        nm = 0.f;
+                        for (int z = 0; z < A.slices; ++z) nm += A.partials[(size_t)z * block + e];     // slice order
+                    } else {
+                        nm = A.num[e];
+                    }
+                    v = __fdiv_rn(nm, dn); A.W[e] = v;                              // xpysom.py:451-455
+                }
                 s += (double)v * v; m = fmaxf(m, fabsf(v));
-                A.S[e] = 0.f;
             }
-            if (lane == 0) A.c[row] = 0.f;
         }
         codebook_stats_row(row, real, s, m, lane, A.dist_kind, A.aux, A.bias, A.amax, A.gstat);
     }

@@ -73,8 +73,9 @@ __global__ void codebook_stats_kernel(const float *__restrict__ W, int k, int d,
 //                b_k (exact, undone per column in the epilogue) so that tiny neurons keep their 22 bits.
 struct SplitOut {
     float *whi, *wlo;            // (k_pad, d_pad) TF32 hi / lo
-    __half *w16hi, *w16lo;       // (k_pad, d_pad64) fp16 hi / lo
+    __half *w16hi, *w16lo;       // (k_pad, d_pad64) fp16 hi / lo; d <= 16: w16hi rows are PACKED [hi | hi | lo | 0] x 16
     float *wsinv;                // (k_pad)
+    float *wfold;                // fold operand image of the fp16 kernel: (bias_k 2^b_k) as three TF32 pieces per neuron
     int d_pad, d_pad64;
     int allow_fold;              // 0: keep the bias in the epilogue (A/B measurements)
 };
@@ -107,13 +108,36 @@ __device__ __forceinline__ void codebook_split_row(const float *W, int row, bool
         O.wlo[(int64_t)row * O.d_pad + c] = lo;
     }
     const float ps = pow2_scale_for(uniform ? gmax : amax[row]);
-    if (lane == 0) O.wsinv[row] = 1.f / ps;             // exact: ps is a power of two
-    for (int c = lane; c < O.d_pad64; c += 32) {
+    if (lane == 0) {
+        O.wsinv[row] = 1.f / ps;             // exact: ps is a power of two
+        // fold operand of the fp16 kernel (one extra kind::tf32 MMA adds 2^a_r * (2^b_k bias_k) to the accumulator, so its
+        // epilogue only compares): three TF32 pieces of bias_k * 2^b_k in the first 16-byte K chunk of the neuron's row
+        // of the no-swizzle K-major image [128-neuron block][K chunk 0 | K chunk 1][8-row group] (bmu_tc3.cuh)
+        const float bs = bk * ps;                                      // +inf stays +inf on padding neurons
+        float f0 = tf32_rna(bs), f1 = 0.f, f2 = 0.f;
+        if (isfinite(bs)) { f1 = tf32_rna(bs - f0); f2 = tf32_rna((bs - f0) - f1); } else f0 = bs;
+        float *blk = O.wfold + (size_t)(row >> 7) * 1024 + (size_t)((row & 127) >> 3) * 64 + (size_t)(row & 7) * 4;
+        *reinterpret_cast<float4 *>(blk) = make_float4(f0, f1, f2, 0.f);            // K chunk 0
+        *reinterpret_cast<float4 *>(blk + 32) = make_float4(0.f, 0.f, 0.f, 0.f);   // K chunk 1 (+128 bytes)
+    }
+    if (d <= 16) {
+        // packed operand of the fp16 kernel for short rows: ONE 64-column tile carries the three products of the
+        // split as three 16-column K steps, x^ = [hi | lo | hi | 0] against w^ = [hi | hi | lo | 0]
+        const int c = lane & 15;
         float v = 0.f;
         if (real && c < d) v = W[(int64_t)row * d + c] * scale * ps;
-        const __half hi = __float2half_rn(v);
-        O.w16hi[(int64_t)row * O.d_pad64 + c] = hi;
-        O.w16lo[(int64_t)row * O.d_pad64 + c] = __float2half_rn(v - __half2float(hi));
+        const __half hi = __float2half_rn(v), lo = __float2half_rn(v - __half2float(hi));
+        __half *dst = O.w16hi + (int64_t)row * O.d_pad64;
+        if (lane < 16) { dst[c] = hi; dst[16 + c] = hi; }
+        else           { dst[32 + c] = lo; dst[48 + c] = __float2half_rn(0.f); }
+    } else {
+        for (int c = lane; c < O.d_pad64; c += 32) {
+            float v = 0.f;
+            if (real && c < d) v = W[(int64_t)row * d + c] * scale * ps;
+            const __half hi = __float2half_rn(v);
+            O.w16hi[(int64_t)row * O.d_pad64 + c] = hi;
+            O.w16lo[(int64_t)row * O.d_pad64 + c] = __float2half_rn(v - __half2float(hi));
+        }
     }
 }
 
@@ -168,6 +192,52 @@ row_scale_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, flo
             for (int o = 16; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o));
             if (lane == 0) xscale[r] = pow2_scale_for(amax);
         }
+    }
+}
+
+// per-column largest magnitude of the samples (the scales of the exact accumulation, common.cuh: ExactAcc):
+// colmax_bits[c] = max(colmax_bits[c], bits(|x[r, c]|)) over the rows -- non-negative floats order like their bit
+// patterns, so the running maximum is an integer atomicMax.  One HBM pass, once per upload.  L threads (a power of
+// two) cover the columns (float4 groups when VEC), 256 / L rows are in flight per CTA.
+template <bool VEC>
+__global__ void __launch_bounds__(256)
+column_absmax_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, unsigned int *__restrict__ colmax_bits, int L) {
+    __shared__ unsigned int cm[1024];
+    const int t = threadIdx.x, R = 256 / L, sub = t / L, cl = t % L;
+    const int units = VEC ? (d >> 2) : d;                   // column units: float4 groups or single columns
+    for (int u0 = 0; u0 < units; u0 += L) {
+        const int u = u0 + cl;
+        float m0 = 0.f, m1 = 0.f, m2 = 0.f, m3 = 0.f;
+        if (u < units)
+            for (int64_t r = (int64_t)blockIdx.x * R + sub; r < n; r += (int64_t)gridDim.x * R) {
+                if (VEC) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(X + r * ldx) + u);
+                    m0 = fmaxf(m0, fabsf(v.x)); m1 = fmaxf(m1, fabsf(v.y)); m2 = fmaxf(m2, fabsf(v.z)); m3 = fmaxf(m3, fabsf(v.w));
+                    // fmaxf drops NaNs: keep them visible (a NaN column gets scale 1 and poisons its sums, as in numpy)
+                    if (v.x != v.x) m0 = v.x; if (v.y != v.y) m1 = v.y; if (v.z != v.z) m2 = v.z; if (v.w != v.w) m3 = v.w;
+                } else {
+                    const float v = __ldg(X + r * ldx + u);
+                    m0 = fmaxf(m0, fabsf(v));
+                    if (v != v) m0 = v;
+                }
+            }
+        const int per = VEC ? 4 : 1;
+        for (int i = t; i < L * per; i += 256) cm[i] = 0u;
+        __syncthreads();
+        if (u < units) {
+            atomicMax(&cm[cl * per], __float_as_uint(fabsf(m0)));
+            if (VEC) {
+                atomicMax(&cm[cl * 4 + 1], __float_as_uint(fabsf(m1)));
+                atomicMax(&cm[cl * 4 + 2], __float_as_uint(fabsf(m2)));
+                atomicMax(&cm[cl * 4 + 3], __float_as_uint(fabsf(m3)));
+            }
+        }
+        __syncthreads();
+        for (int i = t; i < L * per; i += 256) {
+            const int col = u0 * per + i;
+            if (col < d && cm[i]) atomicMax(colmax_bits + col, cm[i]);
+        }
+        __syncthreads();
     }
 }
 

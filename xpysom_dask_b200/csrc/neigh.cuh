@@ -115,12 +115,14 @@ __device__ __forceinline__ float neigh_eval(const NeighParams &P, float inv_d, f
 // mexican hat, K = 2500, D = 128: 2 K^2 D = 1.6 GFLOP per epoch).
 constexpr int NB_K = 16, NB_THREADS = 256;
 
-// One output tile: neurons [k0, k0 + 16 RM) x features [n0, n0 + 16 RN), BMUs [b_begin, b_end).  `atomic`: several
-// BMU slices add into the same tile; `with_den`: this tile also produces den (one tile per neuron range does).
+// One output tile: neurons [k0, k0 + 16 RM) x features [n0, n0 + 16 RN), BMUs [b_begin, b_end), written with plain
+// stores to num / den -- when the reduction over BMUs is sliced, the caller passes the slice's own partial buffers
+// and the slices are summed afterwards in slice order (no atomics: the result does not depend on scheduling).
+// `with_den`: this tile also produces den (one tile per neuron range does).
 template <int RM, int RN>
 __device__ __forceinline__ void neigh_apply_tile(const NeighParams &P, float inv_d, float two_over_d, float eta,
                                                  const float *S, const float *c, float *num, float *den,
-                                                 int k0, int n0, int b_begin, int b_end, bool atomic, bool with_den) {
+                                                 int k0, int n0, int b_begin, int b_end, bool with_den) {
     constexpr int TM = 16 * RM, TN = 16 * RN;
     __shared__ __align__(16) float Hs[NB_K][TM + 4];
     __shared__ __align__(16) float Ss[NB_K][TN + 4];
@@ -205,15 +207,9 @@ __device__ __forceinline__ void neigh_apply_tile(const NeighParams &P, float inv
 #pragma unroll
         for (int bb = 0; bb < RN; ++bb) {
             const int col = n0 + tx * RN + bb;
-            if (col < D) {                                                    // g = h * eta (xpysom.py:434)
-                if (!atomic) num[(int64_t)kk * D + col] = acc[a][bb] * eta;
-                else         atomicAdd(num + (int64_t)kk * D + col, acc[a][bb] * eta);
-            }
+            if (col < D) num[(int64_t)kk * D + col] = acc[a][bb] * eta;       // g = h * eta (xpysom.py:434)
         }
-        if (tx == 0 && with_den) {
-            if (!atomic) den[kk] = dacc[a] * eta;
-            else         atomicAdd(den + kk, dacc[a] * eta);
-        }
+        if (tx == 0 && with_den) den[kk] = dacc[a] * eta;
     }
     __syncthreads();       // the shared tiles may be reused by the caller's next tile
 }
@@ -221,16 +217,33 @@ __device__ __forceinline__ void neigh_apply_tile(const NeighParams &P, float inv
 template <int RM, int RN>
 __global__ void __launch_bounds__(NB_THREADS)
 neigh_apply_kernel(NeighParams P, const float *__restrict__ S, const float *__restrict__ c,
-                   float *__restrict__ num, float *__restrict__ den, int b_per_slice) {
+                   float *__restrict__ num, float *__restrict__ den, float *__restrict__ partials, int b_per_slice) {
     pdl_wait(); pdl_trigger();
     float inv_d, two_over_d, eta;
     neigh_resolve(P, inv_d, two_over_d, eta);
-    // gridDim.z slices the reduction over BMUs so that small maps still fill the GPU
+    // gridDim.z slices the reduction over BMUs so that small maps still fill the GPU; slice z writes its own
+    // partial [num | den] block, slice_reduce_kernel sums them in slice order
     const int K = P.gx * P.gy;
     const int b_begin = blockIdx.z * b_per_slice;
     const int b_end = min(K, b_begin + b_per_slice);
+    if (gridDim.z != 1) {
+        num = partials + (size_t)blockIdx.z * ((size_t)K * P.d + K);
+        den = num + (size_t)K * P.d;
+    }
     neigh_apply_tile<RM, RN>(P, inv_d, two_over_d, eta, S, c, num, den, blockIdx.x * 16 * RM, blockIdx.y * 16 * RN, b_begin, b_end,
-                             gridDim.z != 1, blockIdx.y == 0);
+                             blockIdx.y == 0);
+}
+
+// [num | den] = sum over the slices, in slice order (fixed association: bit-reproducible)
+__global__ void slice_reduce_kernel(const float *__restrict__ partials, int slices, int K, int D,
+                                    float *__restrict__ num, float *__restrict__ den) {
+    pdl_wait(); pdl_trigger();
+    const size_t block = (size_t)K * D + K;
+    for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < block; e += (size_t)gridDim.x * blockDim.x) {
+        float a = 0.f;
+        for (int z = 0; z < slices; ++z) a += partials[(size_t)z * block + e];
+        if (e < (size_t)K * D) num[e] = a; else den[e - (size_t)K * D] = a;
+    }
 }
 
 // ---- separable path -------------------------------------------------------------------------------
@@ -296,6 +309,29 @@ inline size_t neigh_table_floats(int gx, int gy) {
     return (size_t)2 * ((size_t)3 * gx * gx + (size_t)gy * gy) + 64;
 }
 
+// How the direct kernel slices the reduction over BMUs on a device with `sm_count` SMs (>= 2 CTAs per SM, at least
+// 64 BMUs per slice) and the scratch its per-slice partial [num | den] blocks need.
+struct SliceGeom { int tm, tn, slices, b_per_slice; };
+inline SliceGeom neigh_slice_geom(int K, int d, int sm_count) {
+    SliceGeom g;
+    const bool big = d > 64 && K >= 512;                         // 128 x 128 tiles, 8 x 8 per thread
+    g.tm = big ? 128 : 64; g.tn = big ? 128 : 64;
+    const int gxy = (int)(ceil_div(K, g.tm) * ceil_div(d, g.tn));
+    int slices = (2 * sm_count + gxy - 1) / gxy;
+    const int max_slices = (int)ceil_div(K, 4 * 16);
+    if (slices > max_slices) slices = max_slices;
+    if (slices < 1) slices = 1;
+    g.b_per_slice = (int)round_up(ceil_div(K, slices), 16);
+    g.slices = (int)ceil_div(K, g.b_per_slice);
+    return g;
+}
+constexpr int kSmCountBound = 192;        // sizing bound for the partial blocks (B200: 148 SMs)
+inline size_t neigh_partial_floats(int gx, int gy, int d) {
+    const int K = gx * gy;
+    const SliceGeom g = neigh_slice_geom(K, d, kSmCountBound);
+    return g.slices > 1 ? (size_t)g.slices * ((size_t)K * d + K) : 0;
+}
+
 // host: everything of NeighParams that does not depend on a device-side schedule; the factor tables live in `tables`
 inline void neigh_params(NeighParams &P, int gx, int gy, int d, int topology, int kind, double sigma, double eta,
                          double std_coeff, int compact, float *tables) {
@@ -314,8 +350,8 @@ inline void neigh_params(NeighParams &P, int gx, int gy, int d, int topology, in
 
 inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, int d, int topology, int kind,
                               double sigma, double eta, double std_coeff, int compact,
-                              float *num, float *den, float *tables, float *scratch, int sm_count, cudaStream_t st,
-                              const double *sched = nullptr, const int *epoch = nullptr) {
+                              float *num, float *den, float *tables, float *scratch, float *partials, size_t partial_floats,
+                              int sm_count, cudaStream_t st, const double *sched = nullptr, const int *epoch = nullptr) {
     NeighParams P;
     neigh_params(P, gx, gy, d, topology, kind, sigma, eta, std_coeff, compact, tables);
     P.sched = sched; P.epoch = epoch;
@@ -339,29 +375,24 @@ inline int launch_neigh_apply(const float *S, const float *c, int gx, int gy, in
         if ((rc = launch_axis_contract(T, TX, gx, 1, gx, gx, (int64_t)gy * d, P.eta, sched, epoch, num, st))) return rc;
         return launch_axis_contract(Tc, TX, gx, 1, gx, gx, gy, P.eta, sched, epoch, den, st);
     }
-    const bool big = d > 64 && K >= 512;                         // 128 x 128 tiles, 8 x 8 per thread
-    const int tm = big ? 128 : 64, tn = big ? 128 : 64;
-    const int gxy = (int)(ceil_div(K, tm) * ceil_div(d, tn));
-    int slices = (2 * sm_count + gxy - 1) / gxy;                 // aim for >= 2 CTAs per SM
-    const int max_slices = (int)ceil_div(K, 4 * NB_K);           // at least 64 BMUs per slice
-    if (slices > max_slices) slices = max_slices;
-    if (slices < 1) slices = 1;
-    const int b_per_slice = (int)round_up(ceil_div(K, slices), NB_K);
-    slices = (int)ceil_div(K, b_per_slice);
-    if (slices > 1) {
-        // num and den are contiguous in the host class's [num | den] buffer, but the ABI does not
-        // require it: clear them separately
-        rc = check_cuda(cudaMemsetAsync(num, 0, (size_t)K * d * sizeof(float), st), "memset num");
-        if (rc) return rc;
-        rc = check_cuda(cudaMemsetAsync(den, 0, (size_t)K * sizeof(float), st), "memset den");
-        if (rc) return rc;
+    SliceGeom g = neigh_slice_geom(K, d, sm_count);
+    if (g.slices > 1 && (partials == nullptr || partial_floats < (size_t)g.slices * ((size_t)K * d + K))) {
+        g.slices = 1; g.b_per_slice = (int)round_up(K, NB_K);    // no room for partial blocks: one slice (still exact)
     }
-    dim3 grid((unsigned)ceil_div(K, tm), (unsigned)ceil_div(d, tn), (unsigned)slices);
+    const bool big = g.tm == 128;
+    dim3 grid((unsigned)ceil_div(K, g.tm), (unsigned)ceil_div(d, g.tn), (unsigned)g.slices);
     if (big)
-        return check_cuda(launch_pdl(neigh_apply_kernel<8, 8>, grid, dim3(NB_THREADS), 0, st, P, S, c, num, den, b_per_slice),
-                          "neigh_apply_kernel<8,8> launch");
-    return check_cuda(launch_pdl(neigh_apply_kernel<4, 4>, grid, dim3(NB_THREADS), 0, st, P, S, c, num, den, b_per_slice),
-                      "neigh_apply_kernel<4,4> launch");
+        rc = check_cuda(launch_pdl(neigh_apply_kernel<8, 8>, grid, dim3(NB_THREADS), 0, st, P, S, c, num, den, partials, g.b_per_slice),
+                        "neigh_apply_kernel<8,8> launch");
+    else
+        rc = check_cuda(launch_pdl(neigh_apply_kernel<4, 4>, grid, dim3(NB_THREADS), 0, st, P, S, c, num, den, partials, g.b_per_slice),
+                        "neigh_apply_kernel<4,4> launch");
+    if (rc || g.slices == 1) return rc;
+    const size_t block = (size_t)K * d + K;
+    int blocks = (int)ceil_div((int64_t)block, 256);
+    if (blocks > sm_count * 8) blocks = sm_count * 8;
+    return check_cuda(launch_pdl(slice_reduce_kernel, dim3(blocks), dim3(256), 0, st, (const float *)partials, g.slices, K, d, num, den),
+                      "slice_reduce_kernel launch");
 }
 
 }  // namespace somb200

@@ -55,25 +55,36 @@ static int device_info(DevInfo &out) {
 }
 
 static int launch_tc(int use, const float *X, int64_t n, int d, int64_t ldx, const float *xscale, int k,
-                     const WsLayout &L, uint8_t *ws, int32_t *bmu, float *best, float *S, float *c, int sm_count,
+                     const WsLayout &L, uint8_t *ws, int32_t *bmu, float *best, const AccTarget &T, int sm_count,
                      cudaStream_t st) {
     if (use == SOM_ALGO_TC_3XF16)
-        return tc3::launch_bmu_tc3(X, n, d, ldx, xscale, k, L, ws, bmu, best, S, c, sm_count, st);
-    return tc2::launch_bmu_tc2(X, n, d, ldx, k, L, ws, bmu, best, S, c, sm_count, st);
+        return tc3::launch_bmu_tc3(X, n, d, ldx, xscale, k, L, ws, bmu, best, T, sm_count, st);
+    return tc2::launch_bmu_tc2(X, n, d, ldx, k, L, ws, bmu, best, T, sm_count, st);
+}
+
+// the accumulator the ABI hands over: [S: k * acc_ld(d) words | counts: k words]
+static AccTarget acc_target(uint64_t *acc_dev, const float *qscale_dev, int k, int d) {
+    AccTarget T;
+    T.S = reinterpret_cast<unsigned long long *>(acc_dev);
+    T.cnt = T.S + (size_t)k * acc_ld(d);
+    T.qscale = qscale_dev;
+    return T;
 }
 
 static bool known_dist(int k) { return k >= SOM_DIST_EUCLIDEAN && k <= SOM_DIST_NORM_P; }
 
-// AUTO: a tensor-core kernel for the two contraction distances whenever TMA can address X — the
-// fp16-split one when the row scales are available and D fills its 64-feature blocks reasonably,
-// the TF32 one (32-feature blocks) otherwise.
-static int pick_algo(int algo, int dist_kind, const float *X, int64_t n, int d, int64_t ldx, const float *xscale) {
+// AUTO: a tensor-core kernel for the two contraction distances whenever TMA can address X -- the
+// fp16-split one when the row scales are available (short rows, D <= 16, in its packed mode), the TF32 one otherwise.
+static int pick_algo_rule(int algo, int dist_kind, int d, bool tma_ok, bool has_xscale) {
     const bool contraction = dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE;
     if (algo == SOM_ALGO_AUTO) {
-        if (!(contraction && tc::shape_ok(X, n, d, ldx) && d >= 8)) return SOM_ALGO_SIMT_FP32;
-        return (xscale != nullptr && d > 32) ? SOM_ALGO_TC_3XF16 : SOM_ALGO_TC_3XTF32;
+        if (!(contraction && tma_ok && d >= 8)) return SOM_ALGO_SIMT_FP32;
+        return has_xscale ? SOM_ALGO_TC_3XF16 : SOM_ALGO_TC_3XTF32;
     }
     return algo;
+}
+static int pick_algo(int algo, int dist_kind, const float *X, int64_t n, int d, int64_t ldx, const float *xscale) {
+    return pick_algo_rule(algo, dist_kind, d, tc::shape_ok(X, n, d, ldx), xscale != nullptr);
 }
 
 }  // namespace somb200
@@ -83,6 +94,10 @@ using namespace somb200;
 extern "C" {
 
 int som_b200_abi_version(void) { return SOM_B200_ABI_VERSION; }
+
+int som_b200_pick_algo(int algo, int dist_kind, int d, int rows_tma_addressable, int has_row_scales) {
+    return pick_algo_rule(algo, dist_kind, d, rows_tma_addressable != 0, has_row_scales != 0);
+}
 
 const char *som_b200_last_error(void) { return g_err; }
 
@@ -113,7 +128,19 @@ size_t som_b200_neigh_table_floats(int gx, int gy) {
 
 size_t som_b200_neigh_scratch_floats(int gx, int gy, int d) {
     if (gx <= 0 || gy <= 0 || d <= 0) return 0;
-    return neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d);
+    return neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d) + neigh_partial_floats(gx, gy, d);
+}
+
+// the caller's neighbourhood scratch: [factor tables | intermediates of the separable path | per-slice partial blocks];
+// a buffer that ends early simply turns the later parts off (direct kernel / one slice)
+struct NeighScratch { float *sep = nullptr, *partials = nullptr; size_t partial_floats = 0; };
+static NeighScratch carve_scratch(float *base, size_t floats, int gx, int gy, int d) {
+    NeighScratch n;
+    size_t off = neigh_table_floats(gx, gy);
+    const size_t sepf = neigh_separable_floats(gx, gy, d);
+    if (floats >= off + sepf) { n.sep = base + off; off += sepf; } else return n;
+    if (floats > off) { n.partials = base + off; n.partial_floats = floats - off; }
+    return n;
 }
 
 static SplitOut split_out(const WsLayout &L, uint8_t *ws) {
@@ -121,6 +148,7 @@ static SplitOut split_out(const WsLayout &L, uint8_t *ws) {
     O.whi = reinterpret_cast<float *>(ws + L.whi_off); O.wlo = reinterpret_cast<float *>(ws + L.wlo_off);
     O.w16hi = reinterpret_cast<__half *>(ws + L.w16hi_off); O.w16lo = reinterpret_cast<__half *>(ws + L.w16lo_off);
     O.wsinv = reinterpret_cast<float *>(ws + L.wsinv_off);
+    O.wfold = reinterpret_cast<float *>(ws + L.wfold_off);
     O.d_pad = L.d_pad; O.d_pad64 = L.d_pad64;
     static const int no_fold = tc::env_int("SOM_B200_NO_FOLD");
     O.allow_fold = no_fold ? 0 : 1;
@@ -136,7 +164,7 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
     SOM_REQUIRE(ws_bytes >= L.total, SOM_E_WORKSPACE, "prepare_codebook: workspace %zu < %zu bytes", ws_bytes, L.total);
     uint8_t *ws = static_cast<uint8_t *>(ws_dev);
     const bool split = dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE;
-    SOM_CUDA(cudaMemsetAsync(ws + L.cnt_off, 0, L.amax_off - L.cnt_off, (cudaStream_t)stream));   // counts, ticket, stats
+    SOM_CUDA(cudaMemsetAsync(ws + L.done_off, 0, L.amax_off - L.done_off, (cudaStream_t)stream));   // grid barrier of the fused tail, statistics
     const int threads = 256, warps_per_block = threads / 32;
     const int blocks = (int)ceil_div(L.k_pad, warps_per_block);
     float *aux = reinterpret_cast<float *>(ws + L.aux_off), *amax = reinterpret_cast<float *>(ws + L.amax_off);
@@ -151,19 +179,81 @@ int som_b200_prepare_codebook(const float *w_dev, int k, int d, int dist_kind, f
                       "codebook_split_kernel launch");
 }
 
-int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, void *stream) {
+int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, float *xscale_dev, float *colmax_dev,
+                             void *stream) {
     SOM_REQUIRE(n >= 0 && d > 0 && ldx >= d, SOM_E_BADARG, "prepare_samples: bad argument");
     if (n == 0) return 0;
-    SOM_REQUIRE(x_dev && xscale_dev, SOM_E_BADARG, "prepare_samples: NULL pointer");
+    SOM_REQUIRE(x_dev && (xscale_dev || colmax_dev), SOM_E_BADARG, "prepare_samples: NULL pointer");
     const bool vec = (d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_dev) & 15) == 0);
-    int lpr = 1;
-    while (lpr < 32 && lpr < d / 4) lpr <<= 1;
-    int64_t blocks = ceil_div(n, vec ? 8 * (32 / lpr) : 8);
-    if (blocks > 148 * 16) blocks = 148 * 16;
-    if (blocks < 1) blocks = 1;
-    if (vec) row_scale_kernel<true><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, n, d, ldx, xscale_dev, lpr);
-    else     row_scale_kernel<false><<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(x_dev, n, d, ldx, xscale_dev, 32);
-    return check_cuda(cudaGetLastError(), "row_scale_kernel launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (xscale_dev) {
+        int lpr = 1;
+        while (lpr < 32 && lpr < d / 4) lpr <<= 1;
+        int64_t blocks = ceil_div(n, vec ? 8 * (32 / lpr) : 8);
+        if (blocks > 148 * 16) blocks = 148 * 16;
+        if (blocks < 1) blocks = 1;
+        if (vec) row_scale_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x_dev, n, d, ldx, xscale_dev, lpr);
+        else     row_scale_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x_dev, n, d, ldx, xscale_dev, 32);
+        SOM_CUDA(cudaGetLastError());
+    }
+    if (colmax_dev) {
+        const int units = vec ? d / 4 : d;
+        int L = 1;
+        while (L < units && L < 256) L <<= 1;
+        int64_t blocks = ceil_div(n, 256 / L * 16);           // ~16 rows per thread
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks < 1) blocks = 1;
+        unsigned int *bits = reinterpret_cast<unsigned int *>(colmax_dev);
+        if (vec) column_absmax_kernel<true><<<(unsigned)blocks, 256, 0, st>>>(x_dev, n, d, ldx, bits, L);
+        else     column_absmax_kernel<false><<<(unsigned)blocks, 256, 0, st>>>(x_dev, n, d, ldx, bits, L);
+        SOM_CUDA(cudaGetLastError());
+    }
+    return 0;
+}
+
+size_t som_b200_accum_words(int k, int d) {
+    if (k <= 0 || d <= 0) return 0;
+    return (size_t)k * acc_ld(d) + (size_t)k;
+}
+
+int som_b200_accum_scales(const float *colmax_dev, int d, double n_total, float *qscale_dev, float *qinv_dev, void *stream) {
+    SOM_REQUIRE(colmax_dev && qscale_dev && qinv_dev && d > 0 && n_total >= 0, SOM_E_BADARG, "accum_scales: bad argument");
+    const int d_pad = (int)round_up(d, 4);
+    accum_scales_kernel<<<(d_pad + 127) / 128, 128, 0, (cudaStream_t)stream>>>(colmax_dev, d, d_pad, n_total < 1 ? 1.0 : n_total,
+                                                                             qscale_dev, qinv_dev);
+    return check_cuda(cudaGetLastError(), "accum_scales_kernel launch");
+}
+
+int som_b200_accum_finalize(uint64_t *acc_dev, const float *qinv_dev, int k, int d, float *s_dev, float *c_dev, void *stream) {
+    SOM_REQUIRE(acc_dev && qinv_dev && s_dev && c_dev && k > 0 && d > 0, SOM_E_BADARG, "accum_finalize: bad argument");
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    const AccTarget T = acc_target(acc_dev, nullptr, k, d);
+    return check_cuda(launch_pdl(accum_finalize_kernel, dim3(grid_for((int64_t)k * acc_ld(d), di.sm)), dim3(256), 0,
+                                 (cudaStream_t)stream, T.S, T.cnt, qinv_dev, k, d, acc_ld(d), s_dev, c_dev, 1),
+                      "accum_finalize_kernel launch");
+}
+
+int som_b200_accum_fold(uint64_t *acc_dev, const float *qinv_dev, int k, int d, double *sd_dev, void *stream) {
+    SOM_REQUIRE(acc_dev && qinv_dev && sd_dev && k > 0 && d > 0, SOM_E_BADARG, "accum_fold: bad argument");
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    const AccTarget T = acc_target(acc_dev, nullptr, k, d);
+    accum_fold_kernel<<<grid_for((int64_t)k * acc_ld(d), di.sm), 256, 0, (cudaStream_t)stream>>>(
+        T.S, T.cnt, qinv_dev, k, d, acc_ld(d), sd_dev, sd_dev + (size_t)k * d);
+    return check_cuda(cudaGetLastError(), "accum_fold_kernel launch");
+}
+
+int som_b200_accum_finalize_f64(double *sd_dev, int k, int d, float *s_dev, float *c_dev, void *stream) {
+    SOM_REQUIRE(sd_dev && s_dev && c_dev && k > 0 && d > 0, SOM_E_BADARG, "accum_finalize_f64: bad argument");
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    accum_finalize_f64_kernel<<<grid_for((int64_t)k * d, di.sm), 256, 0, (cudaStream_t)stream>>>(
+        sd_dev, sd_dev + (size_t)k * d, k, d, s_dev, c_dev);
+    return check_cuda(cudaGetLastError(), "accum_finalize_f64_kernel launch");
 }
 
 int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float *xscale_dev, const float *w_dev, int k,
@@ -183,7 +273,7 @@ int som_b200_bmu(const float *x_dev, int64_t n, int d, int64_t ldx, const float 
     if (use == SOM_ALGO_TC_3XTF32 || use == SOM_ALGO_TC_3XF16) {
         SOM_REQUIRE(dist_kind == SOM_DIST_EUCLIDEAN || dist_kind == SOM_DIST_COSINE, SOM_E_SHAPE,
                     "the tensor-core kernels compute contraction distances only (euclidean, cosine)");
-        return launch_tc(use, x_dev, n, d, ldx, xscale_dev, k, L, ws, bmu_dev, best_dev, nullptr, nullptr, di.sm,
+        return launch_tc(use, x_dev, n, d, ldx, xscale_dev, k, L, ws, bmu_dev, best_dev, AccTarget(), di.sm,
                          (cudaStream_t)stream);
     }
     SOM_REQUIRE(use == SOM_ALGO_SIMT_FP32, SOM_E_BADARG, "bmu: unknown algo %d", algo);
@@ -227,22 +317,26 @@ int som_b200_top2(const float *x_dev, int64_t n, int d, int64_t ldx, const float
 }
 
 int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const int32_t *bmu_dev, int k,
-                        float *s_dev, float *c_dev, void *stream) {
-    SOM_REQUIRE(s_dev && c_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "accumulate: bad argument");
+                        const float *qscale_dev, uint64_t *acc_dev, void *stream) {
+    SOM_REQUIRE(qscale_dev && acc_dev && k > 0 && d > 0 && n >= 0 && ldx >= d, SOM_E_BADARG, "accumulate: bad argument");
     if (n == 0) return 0;
     SOM_REQUIRE(x_dev && bmu_dev, SOM_E_BADARG, "accumulate: NULL input");
+    SOM_REQUIRE((reinterpret_cast<uintptr_t>(acc_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(qscale_dev) & 15) == 0,
+                SOM_E_SHAPE, "accumulate: the accumulator and the scales must be 16-byte aligned");
     DevInfo di;
     int rc = device_info(di);
     if (rc) return rc;
-    return launch_accumulate(x_dev, n, d, ldx, bmu_dev, k, s_dev, c_dev, di.sm, (cudaStream_t)stream);
+    return launch_accumulate(x_dev, n, d, ldx, bmu_dev, k, acc_target(acc_dev, qscale_dev, k, d), di.sm, (cudaStream_t)stream);
 }
 
 int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const float *xscale_dev,
-                              const float *w_dev, int k, int dist_kind, float p, int algo, float *s_dev, float *c_dev,
-                              int32_t *bmu_dev, void *ws_dev, size_t ws_bytes, void *stream) {
+                              const float *w_dev, int k, int dist_kind, float p, int algo, const float *qscale_dev,
+                              uint64_t *acc_dev, int32_t *bmu_dev, void *ws_dev, size_t ws_bytes, void *stream) {
     SOM_REQUIRE(n >= 0 && k > 0 && d > 0 && ldx >= d, SOM_E_BADARG, "epoch_accumulate: bad argument");
     if (n == 0) return 0;
-    SOM_REQUIRE(x_dev && w_dev && s_dev && c_dev && ws_dev, SOM_E_BADARG, "epoch_accumulate: NULL pointer");
+    SOM_REQUIRE(x_dev && w_dev && qscale_dev && acc_dev && ws_dev, SOM_E_BADARG, "epoch_accumulate: NULL pointer");
+    SOM_REQUIRE((reinterpret_cast<uintptr_t>(acc_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(qscale_dev) & 15) == 0,
+                SOM_E_SHAPE, "epoch_accumulate: the accumulator and the scales must be 16-byte aligned");
     SOM_REQUIRE(known_dist(dist_kind), SOM_E_BADARG, "epoch_accumulate: unknown distance kind %d", dist_kind);
     const WsLayout L = ws_layout(k, d);
     const int use = pick_algo(algo, dist_kind, x_dev, n, d, ldx, xscale_dev);
@@ -253,8 +347,8 @@ int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
         DevInfo di;
         int rc = device_info(di);
         if (rc) return rc;
-        return launch_tc(use, x_dev, n, d, ldx, xscale_dev, k, L, static_cast<uint8_t *>(ws_dev), bmu_dev, nullptr, s_dev,
-                         c_dev, di.sm, (cudaStream_t)stream);
+        return launch_tc(use, x_dev, n, d, ldx, xscale_dev, k, L, static_cast<uint8_t *>(ws_dev), bmu_dev, nullptr,
+                         acc_target(acc_dev, qscale_dev, k, d), di.sm, (cudaStream_t)stream);
     }
     int32_t *bmu = bmu_dev;
     if (!bmu) {
@@ -265,7 +359,7 @@ int som_b200_epoch_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx,
     }
     int rc = som_b200_bmu(x_dev, n, d, ldx, xscale_dev, w_dev, k, dist_kind, p, algo, bmu, nullptr, ws_dev, ws_bytes, stream);
     if (rc) return rc;
-    return som_b200_accumulate(x_dev, n, d, ldx, bmu, k, s_dev, c_dev, stream);
+    return som_b200_accumulate(x_dev, n, d, ldx, bmu, k, qscale_dev, acc_dev, stream);
 }
 
 static int neigh_check(int topology, int neigh_kind, int gx, int gy, int compact_support) {
@@ -294,11 +388,9 @@ int som_b200_neigh_apply(const float *s_dev, const float *c_dev, int gx, int gy,
                 "neigh_apply: scratch of %zu floats < %zu", tables_floats, neigh_table_floats(gx, gy));
     DevInfo di;
     if ((rc = device_info(di))) return rc;
-    // the two-pass separable path needs room for its intermediates after the factor tables
-    float *scratch = tables_floats >= neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d)
-                         ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
+    const NeighScratch ns = carve_scratch(tables_dev, tables_floats, gx, gy, d);
     return launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support,
-                              num_dev, den_dev, tables_dev, scratch, di.sm, (cudaStream_t)stream);
+                              num_dev, den_dev, tables_dev, ns.sep, ns.partials, ns.partial_floats, di.sm, (cudaStream_t)stream);
 }
 
 // same as som_b200_neigh_apply, with sigma and eta read ON THE DEVICE from sched_dev[2e], sched_dev[2e+1],
@@ -316,20 +408,22 @@ int som_b200_neigh_apply_sched(const float *s_dev, const float *c_dev, int gx, i
                 "neigh_apply_sched: scratch of %zu floats < %zu", tables_floats, neigh_table_floats(gx, gy));
     DevInfo di;
     if ((rc = device_info(di))) return rc;
-    float *scratch = tables_floats >= neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d)
-                         ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
+    const NeighScratch ns = carve_scratch(tables_dev, tables_floats, gx, gy, d);
     return launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, 1.0, 1.0, std_coeff, compact_support,
-                              num_dev, den_dev, tables_dev, scratch, di.sm, (cudaStream_t)stream, sched_dev, epoch_dev);
+                              num_dev, den_dev, tables_dev, ns.sep, ns.partials, ns.partial_floats, di.sm, (cudaStream_t)stream,
+                              sched_dev, epoch_dev);
 }
 
 // Fused epoch tail (epoch_tail.cuh) when the map is small enough for one co-resident grid; otherwise the same
 // work as separate launches.  Either way, on return (stream order): W holds the merged codebook, the workspace
-// holds its statistics and operand copies (as after som_b200_prepare_codebook), and S, c are zero.
-int som_b200_epoch_tail(float *s_dev, float *c_dev, float *w_dev, int gx, int gy, int d, int topology, int neigh_kind,
-                        double sigma, double eta, double std_coeff, int compact_support, int dist_kind, float p,
-                        float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats,
+// holds its statistics and operand copies (as after som_b200_prepare_codebook), S and c hold the fp32 per-BMU sums
+// of the epoch just finished and the exact accumulator (when one was given) is zero again.
+int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, float *c_dev, float *w_dev, int gx, int gy,
+                        int d, int topology, int neigh_kind, double sigma, double eta, double std_coeff, int compact_support,
+                        int dist_kind, float p, float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats,
                         void *ws_dev, size_t ws_bytes, void *stream) {
     SOM_REQUIRE(s_dev && c_dev && w_dev && num_dev && den_dev && tables_dev && ws_dev, SOM_E_BADARG, "epoch_tail: NULL pointer");
+    SOM_REQUIRE(acc_dev == nullptr || qinv_dev != nullptr, SOM_E_BADARG, "epoch_tail: an accumulator needs its inverse scales");
     SOM_REQUIRE(gx > 0 && gy > 0 && d > 0 && sigma != 0.0 && std_coeff != 0.0, SOM_E_BADARG, "epoch_tail: bad argument");
     SOM_REQUIRE(known_dist(dist_kind), SOM_E_BADARG, "epoch_tail: unknown distance kind %d", dist_kind);
     const int K = gx * gy;
@@ -342,30 +436,29 @@ int som_b200_epoch_tail(float *s_dev, float *c_dev, float *w_dev, int gx, int gy
     if ((rc = device_info(di))) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     uint8_t *ws = static_cast<uint8_t *>(ws_dev);
-    const bool has_scratch = tables_floats >= neigh_table_floats(gx, gy) + neigh_separable_floats(gx, gy, d);
-    const bool separable = has_scratch && neigh_is_separable(topology, neigh_kind, gx, gy);
+    const NeighScratch ns = carve_scratch(tables_dev, tables_floats, gx, gy, d);
+    const bool separable = ns.sep != nullptr && neigh_is_separable(topology, neigh_kind, gx, gy);
     // Measured on B200 (same box, bench.py --steps 10): fused 0.426 vs 0.438 ms per epoch at config 2, 0.996 vs 1.003 at
     // config 3; with the 128x128 apply tiles (more than 64 features) the persistent grid LOSES 2.5 % at config 5, so
-    // those maps keep the separate launches.  SOM_B200_TAIL_SEPARATE=1 forces them everywhere (A/B measurements).
+    // those maps keep the separate launches (experiments builds: SOM_B200_TAIL_SEPARATE=1 forces them everywhere).
     static const int no_fuse = tc::env_int("SOM_B200_TAIL_SEPARATE");
     const bool wide = d > 64 && K >= 512;
     const bool fused = !no_fuse && !separable && !wide && (int64_t)K * d <= (int64_t)1 << 20;
     auto separate_launches = [&]() -> int {
-        float *scratch = has_scratch ? tables_dev + neigh_table_floats(gx, gy) : nullptr;
         int r;
+        if (acc_dev && (r = som_b200_accum_finalize(acc_dev, qinv_dev, K, d, s_dev, c_dev, stream))) return r;
         if ((r = launch_neigh_apply(s_dev, c_dev, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support,
-                                    num_dev, den_dev, tables_dev, scratch, di.sm, st))) return r;
+                                    num_dev, den_dev, tables_dev, ns.sep, ns.partials, ns.partial_floats, di.sm, st))) return r;
         if ((r = som_b200_merge(w_dev, num_dev, den_dev, K, d, stream))) return r;
-        if ((r = som_b200_prepare_codebook(w_dev, K, d, dist_kind, p, ws_dev, ws_bytes, stream))) return r;
-        SOM_CUDA(cudaMemsetAsync(s_dev, 0, (size_t)K * d * sizeof(float), st));
-        SOM_CUDA(cudaMemsetAsync(c_dev, 0, (size_t)K * sizeof(float), st));
-        return 0;
+        return som_b200_prepare_codebook(w_dev, K, d, dist_kind, p, ws_dev, ws_bytes, stream);
     };
     if (!fused) return separate_launches();
     TailArgs A;
     neigh_params(A.P, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact_support, tables_dev);
     A.sigma = sigma; A.dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
     A.S = s_dev; A.c = c_dev; A.num = num_dev; A.den = den_dev; A.W = w_dev;
+    const AccTarget T = acc_target(acc_dev, nullptr, K, d);
+    A.Si = acc_dev ? T.S : nullptr; A.ci = acc_dev ? T.cnt : nullptr; A.qinv = qinv_dev; A.lds = acc_ld(d);
     A.k = K; A.d = d; A.dist_kind = dist_kind; A.k_pad = L.k_pad;
     A.aux = reinterpret_cast<float *>(ws + L.aux_off); A.bias = reinterpret_cast<float *>(ws + L.bias_off);
     A.amax = reinterpret_cast<float *>(ws + L.amax_off); A.gstat = reinterpret_cast<unsigned int *>(ws + L.gstat_off);
@@ -386,6 +479,11 @@ int som_b200_epoch_tail(float *s_dev, float *c_dev, float *w_dev, int gx, int gy
     const int max_slices = (int)ceil_div(K, 4 * NB_K);           // at least 64 BMUs per slice
     if (slices > max_slices) slices = max_slices;
     if (slices < 1) slices = 1;
+    // every slice writes its own partial block; without room for them the reduction is not sliced
+    const size_t block = (size_t)K * d + K;
+    if (slices > 1 && ns.partial_floats / block < (size_t)slices) slices = (int)(ns.partial_floats / block);
+    if (slices < 1) slices = 1;
+    A.partials = ns.partials;
     A.b_per_slice = (int)round_up(ceil_div(K, slices), NB_K);
     A.slices = (int)ceil_div(K, A.b_per_slice);
     void *args[] = {&A};
@@ -452,6 +550,12 @@ int som_b200_distance_map(const float *w_dev, int gx, int gy, int d, int topolog
 
 int som_b200_debug_timeline(long long *host_out, int n) {
     SOM_REQUIRE(host_out && n > 0 && n <= 8 * 256, SOM_E_BADARG, "debug_timeline: bad argument");
+#ifdef SOM_B200_EXPERIMENTS
+    if (tc::env_int("SOM_B200_DBG") == 8) {          // scatter-warp timeline (6 stamps per batch)
+        SOM_CUDA(cudaMemcpyFromSymbol(host_out, g_scat_dbg, (size_t)(n < 8 * 64 ? n : 8 * 64) * sizeof(long long)));
+        return 0;
+    }
+#endif
     SOM_CUDA(cudaMemcpyFromSymbol(host_out, tc::g_dbg, (size_t)n * sizeof(long long)));
     return 0;
 }
@@ -463,12 +567,16 @@ int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_ho
     const int d = cfg->d, K = cfg->gx * cfg->gy;
     SOM_REQUIRE(d > 0 && K > 0 && ldx >= d, SOM_E_BADARG, "train_host: bad shape");
     struct Bufs {
-        float *x = nullptr, *w = nullptr, *sc = nullptr, *nd = nullptr, *tab = nullptr, *xs = nullptr;
+        float *x = nullptr, *w = nullptr, *sc = nullptr, *nd = nullptr, *tab = nullptr, *xs = nullptr, *q = nullptr;
+        uint64_t *acc = nullptr;
         uint8_t *ws = nullptr; cudaStream_t st = nullptr;
-        ~Bufs() { cudaFree(x); cudaFree(w); cudaFree(sc); cudaFree(nd); cudaFree(tab); cudaFree(xs); cudaFree(ws); if (st) cudaStreamDestroy(st); }
+        ~Bufs() { cudaFree(x); cudaFree(w); cudaFree(sc); cudaFree(nd); cudaFree(tab); cudaFree(xs); cudaFree(q); cudaFree(acc);
+                  cudaFree(ws); if (st) cudaStreamDestroy(st); }
     } b;
     const int64_t dld = round_up(d, 4);                 // device row stride: 16-byte aligned rows for TMA / float4
     const size_t ws_bytes = som_b200_shard_workspace_bytes(n, K, d);
+    const size_t words = som_b200_accum_words(K, d);
+    const size_t dq = (size_t)round_up(d, 4);
     SOM_CUDA(cudaStreamCreateWithFlags(&b.st, cudaStreamNonBlocking));
     SOM_CUDA(cudaMalloc(&b.x, (size_t)n * dld * 4));
     SOM_CUDA(cudaMalloc(&b.w, (size_t)K * d * 4));
@@ -477,28 +585,28 @@ int som_b200_train_host(const float *x_host, int64_t n, int64_t ldx, float *w_ho
     SOM_CUDA(cudaMalloc(&b.tab, som_b200_neigh_scratch_floats(cfg->gx, cfg->gy, d) * 4));
     SOM_CUDA(cudaMalloc(&b.ws, ws_bytes));
     SOM_CUDA(cudaMalloc(&b.xs, (size_t)n * 4));
+    SOM_CUDA(cudaMalloc(&b.q, 3 * dq * 4));             // column maxima | 2^q | 2^-q
+    SOM_CUDA(cudaMalloc(&b.acc, words * 8));
     if (dld != d) SOM_CUDA(cudaMemsetAsync(b.x, 0, (size_t)n * dld * 4, b.st));
     SOM_CUDA(cudaMemcpy2DAsync(b.x, dld * 4, x_host, ldx * 4, (size_t)d * 4, (size_t)n, cudaMemcpyHostToDevice, b.st));
     SOM_CUDA(cudaMemcpyAsync(b.w, w_host, (size_t)K * d * 4, cudaMemcpyHostToDevice, b.st));
+    SOM_CUDA(cudaMemsetAsync(b.q, 0, 3 * dq * 4, b.st));
+    SOM_CUDA(cudaMemsetAsync(b.acc, 0, words * 8, b.st));
     float *S = b.sc, *c = b.sc + (size_t)K * d, *num = b.nd, *den = b.nd + (size_t)K * d;
-    {
-        int rc = som_b200_prepare_samples(b.x, n, d, dld, b.xs, b.st);
-        if (rc) return rc;
-    }
-    // epoch = BMU search + per-BMU sums -> everything else (som_b200_epoch_tail leaves the workspace prepared for the
-    // next search and S, c cleared)
-    if (n_epochs > 0) {
-        SOM_CUDA(cudaMemsetAsync(b.sc, 0, ((size_t)K * d + K) * 4, b.st));
-        const int rc = som_b200_prepare_codebook(b.w, K, d, cfg->dist_kind, cfg->p, b.ws, ws_bytes, b.st);
-        if (rc) return rc;
-    }
+    float *colmax = b.q, *qscale = b.q + dq, *qinv = b.q + 2 * dq;
+    int rc;
+    if ((rc = som_b200_prepare_samples(b.x, n, d, dld, b.xs, colmax, b.st))) return rc;
+    if ((rc = som_b200_accum_scales(colmax, d, (double)n, qscale, qinv, b.st))) return rc;
+    // epoch = BMU search + exact per-BMU sums -> everything else (som_b200_epoch_tail leaves the workspace prepared for
+    // the next search and the accumulator cleared)
+    if (n_epochs > 0 && (rc = som_b200_prepare_codebook(b.w, K, d, cfg->dist_kind, cfg->p, b.ws, ws_bytes, b.st))) return rc;
     for (int e = 0; e < n_epochs; ++e) {
-        int rc;
-        if ((rc = som_b200_epoch_accumulate(b.x, n, d, dld, b.xs, b.w, K, cfg->dist_kind, cfg->p, cfg->algo, S, c, nullptr,
-                                            b.ws, ws_bytes, b.st))) return rc;
-        if ((rc = som_b200_epoch_tail(S, c, b.w, cfg->gx, cfg->gy, d, cfg->topology, cfg->neigh_kind, sigma_per_epoch[e],
-                                      eta_per_epoch[e], cfg->std_coeff, cfg->compact_support, cfg->dist_kind, cfg->p, num, den,
-                                      b.tab, som_b200_neigh_scratch_floats(cfg->gx, cfg->gy, d), b.ws, ws_bytes, b.st)))
+        if ((rc = som_b200_epoch_accumulate(b.x, n, d, dld, b.xs, b.w, K, cfg->dist_kind, cfg->p, cfg->algo, qscale, b.acc,
+                                            nullptr, b.ws, ws_bytes, b.st))) return rc;
+        if ((rc = som_b200_epoch_tail(b.acc, qinv, S, c, b.w, cfg->gx, cfg->gy, d, cfg->topology, cfg->neigh_kind,
+                                      sigma_per_epoch[e], eta_per_epoch[e], cfg->std_coeff, cfg->compact_support, cfg->dist_kind,
+                                      cfg->p, num, den, b.tab, som_b200_neigh_scratch_floats(cfg->gx, cfg->gy, d), b.ws, ws_bytes,
+                                      b.st)))
             return rc;
     }
     SOM_CUDA(cudaMemcpyAsync(w_host, b.w, (size_t)K * d * 4, cudaMemcpyDeviceToHost, b.st));

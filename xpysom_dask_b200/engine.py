@@ -69,15 +69,53 @@ class CudaEngine:
                                                           ws.numel(), self._stream()), "som_b200_prepare_codebook")
         self.launches += 1
 
-    def prepare_samples(self, x, out=None):
-        """Per-row power-of-two scales for the fp16-split kernel (one pass over x)."""
+    def prepare_samples(self, x, want_scale=True, out=None, colmax=None):
+        """One-time statistics of an uploaded sample matrix: the per-row power-of-two scales of the fp16-split kernel
+        (want_scale) and the per-column largest magnitudes the exact accumulation derives its scales from
+        (max-accumulated into `colmax` when one is passed: the parts of one upload share it).  -> (xscale | None, colmax)"""
         n, d = x.shape
-        xs = out if out is not None else self.empty(max(n, 1))
+        xs = None
+        if want_scale:
+            xs = out if out is not None else self.empty(max(n, 1))
+        if colmax is None:
+            colmax = self.zeros((d + 3) // 4 * 4)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.som_b200_prepare_samples(self._p(x), n, d, x.stride(0), self._p(xs), self._stream()),
-                       "som_b200_prepare_samples")
+            _lib.check(self.lib.som_b200_prepare_samples(self._p(x), n, d, x.stride(0), self._p(xs), self._p(colmax),
+                                                         self._stream()), "som_b200_prepare_samples")
+        self.launches += 2 if want_scale else 1
+        return xs, colmax
+
+    def accum_scales(self, colmax, d, n_total):
+        """(qscale, qinv): 2^q_c and 2^-q_c per feature column for the exact accumulation of n_total samples."""
+        dq = (d + 3) // 4 * 4
+        q = self.empty(2 * dq)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_accum_scales(self._p(colmax), d, float(n_total), self._p(q[:dq]), self._p(q[dq:]),
+                                                      self._stream()), "som_b200_accum_scales")
         self.launches += 1
-        return xs
+        return q[:dq], q[dq:]
+
+    def accumulator(self, k, d):
+        """Zeroed exact accumulator [S | counts] of som_b200_accum_words(k, d) 64-bit words."""
+        return self.zeros(self.lib.som_b200_accum_words(int(k), int(d)), dtype=torch.int64)
+
+    def accum_finalize(self, acc, qinv, k, d, s, c):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_accum_finalize(self._p(acc), self._p(qinv), k, d, self._p(s), self._p(c),
+                                                        self._stream()), "som_b200_accum_finalize")
+        self.launches += 1
+
+    def accum_fold(self, acc, qinv, k, d, sd):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_accum_fold(self._p(acc), self._p(qinv), k, d, self._p(sd), self._stream()),
+                       "som_b200_accum_fold")
+        self.launches += 1
+
+    def accum_finalize_f64(self, sd, k, d, s, c):
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_accum_finalize_f64(self._p(sd), k, d, self._p(s), self._p(c), self._stream()),
+                       "som_b200_accum_finalize_f64")
+        self.launches += 1
 
     def bmu(self, x, w, dist_kind, p, algo, ws, bmu_out=None, best_out=None, xscale=None):
         n, d = x.shape
@@ -114,23 +152,22 @@ class CudaEngine:
         self.launches += 2
         return out
 
-    def accumulate(self, x, bmu, k, s, c):
+    def accumulate(self, x, bmu, k, qscale, acc):
         n, d = x.shape
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.som_b200_accumulate(self._p(x), n, d, x.stride(0), self._p(bmu), k, self._p(s),
-                                                    self._p(c), self._stream()), "som_b200_accumulate")
+            _lib.check(self.lib.som_b200_accumulate(self._p(x), n, d, x.stride(0), self._p(bmu), k, self._p(qscale),
+                                                    self._p(acc), self._stream()), "som_b200_accumulate")
         self.launches += 1
 
-    def epoch_accumulate(self, x, w, dist_kind, p, algo, s, c, ws, bmu_out=None, xscale=None):
+    def epoch_accumulate(self, x, w, dist_kind, p, algo, qscale, acc, ws, bmu_out=None, xscale=None):
         n, d = x.shape
         k = w.shape[0]
         with torch.cuda.device(self.device):
             _lib.check(self.lib.som_b200_epoch_accumulate(self._p(x), n, d, x.stride(0), self._p(xscale), self._p(w), k,
-                                                          dist_kind,
-                                                          float(p), algo, self._p(s), self._p(c), self._p(bmu_out),
-                                                          self._p(ws), ws.numel(), self._stream()),
+                                                          dist_kind, float(p), algo, self._p(qscale), self._p(acc),
+                                                          self._p(bmu_out), self._p(ws), ws.numel(), self._stream()),
                        "som_b200_epoch_accumulate")
-        self.launches += 2
+        self.launches += 1
 
     def neigh_apply(self, s, c, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, num, den, tables):
         with torch.cuda.device(self.device):
@@ -141,11 +178,13 @@ class CudaEngine:
                        "som_b200_neigh_apply")
         self.launches += 2
 
-    def epoch_tail(self, s, c, w, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, dist_kind, p,
+    def epoch_tail(self, acc, qinv, s, c, w, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, dist_kind, p,
                    num, den, tables, ws):
-        """neigh_apply + merge + prepare_codebook(new W) + clear S, c: one cooperative kernel on small maps."""
+        """accum_finalize (acc is not None) + neigh_apply + merge + prepare_codebook(new W): one cooperative kernel on
+        small maps.  The accumulator is left cleared; s, c hold the epoch's fp32 sums."""
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.som_b200_epoch_tail(self._p(s), self._p(c), self._p(w), gx, gy, d, topology, neigh_kind,
+            _lib.check(self.lib.som_b200_epoch_tail(self._p(acc), self._p(qinv), self._p(s), self._p(c), self._p(w), gx, gy, d,
+                                                    topology, neigh_kind,
                                                     float(sigma), float(eta), float(std_coeff), int(bool(compact)),
                                                     dist_kind, float(p), self._p(num), self._p(den), self._p(tables),
                                                     tables.numel(), self._p(ws), ws.numel(), self._stream()),

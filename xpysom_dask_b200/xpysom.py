@@ -22,7 +22,6 @@ callers may assign to between calls, exactly as with the reference
 from collections import Counter, defaultdict
 from warnings import warn
 
-import os
 import weakref
 
 import numpy as np
@@ -37,6 +36,7 @@ _NEIGHBORHOODS = {
 }
 _DISTANCES = ("euclidean", "euclidean_no_opt", "manhattan", "manhattan_no_opt", "cosine", "norm_p",
               "norm_p_no_opt", "chebyshev")                       # distances.py:162-170 + chebyshev
+_UNPICKLED_SHARDED = 'sharded (unpickled)'
 _DEFAULT_N_PARALLEL = 148 * 2048     # SMs x max threads/SM on B200: the rule of utils.py:4-11
 
 
@@ -64,7 +64,8 @@ class XPySom:
                  decay_function='exponential', neighborhood_function='gaussian', std_coeff=0.5,
                  topology='rectangular', activation_distance='euclidean', activation_distance_kwargs={},
                  random_seed=None, n_parallel=0, compact_support=False, xp=None, use_dask=False,
-                 dask_chunks='auto', *, device=None, algo='auto', process_group=None, use_cuda_graph=False):
+                 dask_chunks='auto', *, device=None, algo='auto', process_group=None, use_cuda_graph=False,
+                 max_resident_bytes=None):
         """Same arguments as the reference constructor (xpysom.py:73-82).
 
         Keyword-only additions: ``device`` (CUDA device of this process),
@@ -72,7 +73,9 @@ class XPySom:
         (a torch.distributed group, or True for the default group: this process
         holds one shard of the samples) and ``use_cuda_graph`` (replay one
         captured CUDA graph per epoch instead of launching the epoch's ~10 kernels one by one; capture
-        costs a few milliseconds, so it only pays off for runs of several hundred epochs on small maps).
+        costs a few milliseconds, so it only pays off for runs of several hundred epochs on small maps) and
+        ``max_resident_bytes`` (host arrays larger than this -- default: 80 % of the free device memory -- are
+        streamed through two block buffers every epoch instead of being uploaded once).
         """
         if sigma >= x or sigma >= y:
             warn('Warning: sigma is too high for the dimension of the map.')
@@ -129,6 +132,7 @@ class XPySom:
         self._process_group = process_group
         self._engine = None                # the CudaEngine of this process, created on first use
         self._use_cuda_graph = bool(use_cuda_graph)
+        self._max_resident_bytes = max_resident_bytes
         self._profile = False              # bench.py: record CUDA events around the BMU / accumulate kernels
         self._profile_events = []
         self.stats = {}
@@ -160,23 +164,10 @@ class XPySom:
             return None
         import torch.distributed as dist
         if not dist.is_initialized():
-            raise RuntimeError("process_group given but torch.distributed is not initialised")
-        return dist.group.WORLD if pg is True else pg
-
-    def _peer_reducer(self, eng, group, floats):
-        """The cached one-shot all-reduce for buffers of ``floats`` values, or None when NCCL should be used."""
-        from . import peer
-        import torch.distributed as dist
-        if floats * 4 > peer.ONE_SHOT_MAX_BYTES or dist.get_world_size(group) < 2:
-            return None
-        key = (id(group), floats, str(eng.device))
-        cached = getattr(self, '_peer_cache', None)
-        if cached is None or cached[0] != key:
-            if cached is not None:
-                cached[1].close()
-            cached = (key, peer.PeerReducer(eng, group, floats))
-            self._peer_cache = cached
-        return cached[1] if cached[1].active else None
+            raise RuntimeError("this model trains one shard of a sharded job (process_group was set%s) but "
+                               "torch.distributed is not initialised" % (", then pickled" if pg == _UNPICKLED_SHARDED else ""))
+        # a pickled sharded model comes back attached to the default group (group handles do not pickle)
+        return dist.group.WORLD if (pg is True or pg == _UNPICKLED_SHARDED) else pg
 
     def _shape(self):
         gx, gy, d = self._weights.shape
@@ -237,13 +228,60 @@ class XPySom:
             raise ValueError('num_iteration must be > 1')
 
     # ------------------------------------------------------------------ training
+    def _sample_stats(self, eng, x, want_scale, group, cache_key=None):
+        """Per-upload statistics of a device-resident sample matrix: row scales of the fp16-split kernel and the column
+        scales of the exact accumulation (one pass each, engine.prepare_samples).  Sharded runs agree on the column
+        scales through one MAX all-reduce of the column maxima and one SUM of the row counts.  A caller-owned device
+        tensor that has not been written since the last call keeps its statistics (torch's version counter catches
+        in-place changes; the cache holds a weak reference, so a freed tensor whose address is reused cannot hit it)."""
+        cached = getattr(self, '_stats_cache', None)
+        gkey = id(group) if group is not None else None
+        if (cache_key is not None and cached is not None and cached[0]() is cache_key and cached[1] == cache_key._version
+                and cached[2] == (gkey, want_scale)):
+            return cached[3]
+        n, d = x.shape
+        if n == 0 and group is None:
+            stats = (None, eng.zeros((d + 3) // 4 * 4), eng.zeros((d + 3) // 4 * 4))
+        else:
+            xscale, colmax = eng.prepare_samples(x, want_scale) if n > 0 else (None, eng.zeros((d + 3) // 4 * 4))
+            n_total = n
+            if group is not None:
+                import torch.distributed as dist
+                cnt = torch.tensor([float(n)], dtype=torch.float64, device=colmax.device)
+                dist.all_reduce(colmax, op=dist.ReduceOp.MAX, group=group)
+                dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+                n_total = int(cnt.item())
+            qscale, qinv = eng.accum_scales(colmax, d, max(n_total, 1))
+            stats = (xscale, qscale, qinv)
+        self._stats_cache = ((weakref.ref(cache_key), cache_key._version, (gkey, want_scale), stats)
+                             if cache_key is not None else None)
+        return stats
+
+    def _device_budget(self, eng):
+        """Bytes of samples this process may keep resident (the rest of the job streams through two block buffers)."""
+        if self._max_resident_bytes is not None:
+            return int(self._max_resident_bytes)
+        if getattr(eng, 'name', '') != 'cuda':
+            return 1 << 62
+        free, _ = torch.cuda.mem_get_info(eng.device)
+        return int(free * 0.8)
+
     def train(self, data, num_epochs, iter_beg=0, iter_end=None, verbose=False):
         """Batch-SOM training, epochs [iter_beg, iter_end) of a num_epochs schedule
         (xpysom.py:458-594).  With ``process_group`` set, ``data`` is this
-        process's shard of the samples."""
+        process's shard of the samples.
+
+        Where the samples live decides how an epoch reads them:
+          * device tensors, and host arrays that fit, are RESIDENT: uploaded once, one fused BMU + accumulate kernel per
+            epoch.  Host arrays of >= 32 MB go up in chunks on a copy stream and the first epoch consumes each chunk as
+            it lands;
+          * host arrays larger than the device budget are STREAMED every epoch through two block buffers (pinned
+            registration, copy of block i+1 under the compute of block i) -- what the reference's chunk loop
+            (xpysom.py:560-569) and Dask blocks (:546) do for data of any size."""
         if iter_end is None:
             iter_end = num_epochs
         eng = self._get_engine()
+        cuda = getattr(eng, 'name', '') == 'cuda'
         gx, gy, d = self._shape()
         K = gx * gy
         dist_kind, p = self._dist_kind()
@@ -251,46 +289,30 @@ class XPySom:
         topo = _lib.TOPO[self.topology]
         neigh = _lib.NEIGH[self.neighborhood_func_name]
         group = self._group()
+        want_scale = self._wants_xscale(dist_kind)
 
         w = self._weights_to_device(eng)
         n_ep = iter_end - iter_beg
         prof = self._profile_events if getattr(self, '_profile', False) else None
-        graphed = (self._use_cuda_graph and prof is None and not verbose and n_ep >= 3
-                   and getattr(eng, 'name', '') == 'cuda')
-        # Large host-resident samples are uploaded in chunks on a copy stream and the FIRST epoch consumes
-        # each chunk as it lands (the per-BMU sums accumulate over chunks), so the H2D copy overlaps compute.
-        chunks = None
+        graphed = self._use_cuda_graph and prof is None and not verbose and n_ep >= 3 and cuda
         host = _as_f32_matrix(data)
-        if (host.device.type == 'cpu' and getattr(eng, 'name', '') == 'cuda' and not graphed and n_ep >= 1
-                and host.shape[1] == d and host.numel() * 4 >= (32 << 20)):
-            x, chunks = self._upload_in_chunks(eng, host)
-        else:
-            x = self._data_to_device(eng, host)
-        if x.shape[1] != d:
-            raise ValueError('Received %d features, expected %d.' % (x.shape[1], d))
-        n = x.shape[0]
+        if host.shape[1] != d:
+            raise ValueError('Received %d features, expected %d.' % (host.shape[1], d))
+        n = host.shape[0]
+        on_host = host.device.type == 'cpu' and cuda
+        mode = 'resident'
+        if on_host and n_ep >= 1 and n > 0:
+            if host.numel() * 4 > self._device_budget(eng):
+                mode = 'stream'
+            elif not graphed and host.numel() * 4 >= (32 << 20):
+                mode = 'chunked'
 
-        sc = eng.zeros(K * d + K)            # [S | c], one buffer -> one all-reduce
+        acc = eng.accumulator(K, d)          # exact [S | counts], 64-bit fixed point (cleared by every epoch tail)
+        sc = eng.empty(K * d + K)            # fp32 [S | c] the neighbourhood apply reads
         nd = eng.empty(K * d + K)            # [num | den]
         S, c = sc[:K * d], sc[K * d:]
         num, den = nd[:K * d], nd[K * d:]
         ws = eng.workspace(0, K, d)
-        bmu = eng.empty(n, dtype=torch.int32)
-        # per-row power-of-two scales for the fp16-split contraction: once per upload, not per epoch
-        if not self._wants_xscale(dist_kind) or n == 0:
-            xscale = None
-        elif chunks is None:
-            # a device tensor that has not been written since the last call keeps its scales (one pass over the
-            # samples per upload, not per train() call); torch's version counter catches in-place changes
-            # (the cache holds a weak reference: a freed tensor whose address is reused cannot hit it)
-            cached = getattr(self, '_xscale_cache', None)
-            if cached is not None and cached[0]() is x and cached[1] == x._version:
-                xscale = cached[2]
-            else:
-                xscale = eng.prepare_samples(x)
-                self._xscale_cache = (weakref.ref(x), x._version, xscale) if x is data else None
-        else:
-            xscale = eng.empty(n)                  # filled chunk by chunk during the first epoch
         tables = eng.neigh_tables(gx, gy, d)
 
         def schedule(t):
@@ -298,82 +320,181 @@ class XPySom:
             sig_t = self._decay_function(self._sigma, self._sigmaN, t, num_epochs)   # same rule (xpysom.py:541-543)
             return sig_t, eta_t
 
-        # the one exchange step of the sharded path: NCCL by default (NVLS on NVSwitch: 28 us for config 2's
-        # 0.26 MB on 8 B200s); SOM_B200_PEER=1 routes small buffers through the library's own one-shot all-reduce
-        # over NVLink peer memory (peer.py: 16 us vs 20 us on 2 GPUs, 40 us vs 28 us on 8)
-        reducer = None
-        if (group is not None and not graphed and getattr(eng, 'name', '') == 'cuda'
-                and os.environ.get('SOM_B200_PEER') == '1'):
-            reducer = self._peer_reducer(eng, group, sc.numel())
-
-        def reduce_shards():
-            if reducer is not None:
-                reducer.all_reduce_(sc)
-            elif group is not None:
+        def all_reduce(t):
+            # the one exchange step of the sharded path.  Resident epochs reduce the INTEGER accumulator: the sum is
+            # exact, so every rank -- and a single GPU holding all the rows -- ends up with the same bits.
+            if group is not None:
                 import torch.distributed as dist
-                dist.all_reduce(sc, op=dist.ReduceOp.SUM, group=group)
+                dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
 
-        if graphed:
-            # One CUDA graph of the whole epoch, replayed n_ep - 1 times: sigma / eta live in a device-side
-            # schedule indexed by a device-side epoch counter, so the captured launches never change.
-            sched = eng.to_device(torch.tensor([[float(v) for v in schedule(t)] for t in range(iter_beg, iter_end)],
-                                               dtype=torch.float64))
-            epoch_idx = eng.zeros(1, dtype=torch.int32)
+        def tail(t, from_acc, qinv):
+            sig, eta = schedule(t)
+            eng.epoch_tail(acc if from_acc else None, qinv, S, c, w, gx, gy, d, topo, neigh, sig, eta, self._std_coeff,
+                           self.compact_support, dist_kind, p, num, den, tables, ws)
+            if verbose:
+                print('\r [ %d / %d ]' % (t + 1, num_epochs), end='')
 
-            def epoch_body():
-                sc.zero_()
-                eng.prepare_codebook(w, dist_kind, p, ws)
-                if n > 0:
-                    eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
-                reduce_shards()
-                eng.neigh_apply_sched(S, c, gx, gy, d, topo, neigh, sched, epoch_idx, self._std_coeff,
-                                      self.compact_support, num, den, tables)
-                eng.merge(w, num, den)
-                eng.epoch_advance(epoch_idx)
-
-            launches0 = eng.launches
-            epoch_body()                               # first epoch eagerly: warms up every kernel / NCCL
-            per_epoch = eng.launches - launches0
-            graph = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(graph):
-                epoch_body()                           # captured, not executed
-            for _ in range(n_ep - 1):
-                graph.replay()
-            eng.launches = launches0 + per_epoch * n_ep    # kernels actually executed (capture launches none)
+        if mode == 'stream':
+            self._train_streamed(eng, host, w, acc, S, c, ws, dist_kind, p, algo, want_scale, group, all_reduce, tail,
+                                 iter_beg, iter_end, K, d)
         else:
-            # epoch = BMU search + per-BMU sums (one fused kernel) -> all-reduce of the shards -> everything else
-            # (eng.epoch_tail: apply, merge, preparation of the new codebook for the next search, clean S / c)
+            if mode == 'chunked':
+                x, chunks = self._upload_in_chunks(eng, host)
+            else:
+                x, chunks = self._data_to_device(eng, host), None
+            bmu = eng.empty(n, dtype=torch.int32)
             if n_ep > 0:
-                eng.prepare_codebook(w, dist_kind, p, ws)        # sc is already zero (eng.zeros above)
-            for t in range(iter_beg, iter_end):
-                sig, eta = schedule(t)
-                if prof is not None:
-                    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-                    ev[0].record()
-                # K1/K2 + K3: distance + argmin + per-BMU sums (one fused kernel on the tensor-core path)
-                if chunks is not None and t == iter_beg:
-                    cur = torch.cuda.current_stream(eng.device)
-                    for r0, r1, landed in chunks:
-                        cur.wait_event(landed)
-                        xs_c = None
-                        if xscale is not None:
-                            xs_c = eng.prepare_samples(x[r0:r1], out=xscale[r0:r1])
-                        eng.epoch_accumulate(x[r0:r1], w, dist_kind, p, algo, S, c, ws, bmu_out=bmu[r0:r1], xscale=xs_c)
-                elif n > 0:                 # a rank may hold an EMPTY shard: it still joins the all-reduce and the tail
-                    eng.epoch_accumulate(x, w, dist_kind, p, algo, S, c, ws, bmu_out=bmu, xscale=xscale)
-                if prof is not None:
-                    ev[1].record()
-                    prof.append(ev)
-                reduce_shards()
-                eng.epoch_tail(S, c, w, gx, gy, d, topo, neigh, sig, eta, self._std_coeff, self.compact_support,
-                               dist_kind, p, num, den, tables, ws)
-                if verbose:
-                    print('\r [ %d / %d ]' % (t + 1, num_epochs), end='')
+                eng.prepare_codebook(w, dist_kind, p, ws)
+            first = iter_beg
+            if chunks is not None:
+                # first epoch: every chunk is searched and accumulated as it lands, with its own column scales, and
+                # folded into running fp64 sums (chunk order: deterministic); the statistics of the whole matrix fall
+                # out of the same pass for the epochs after it
+                sd = eng.zeros(K * d + K, dtype=torch.float64)
+                xscale = eng.empty(n) if want_scale else None
+                colmax = eng.zeros((d + 3) // 4 * 4)
+                cur = torch.cuda.current_stream(eng.device)
+                for r0, r1, landed in chunks:
+                    cur.wait_event(landed)
+                    xs_c, cm_c = eng.prepare_samples(x[r0:r1], want_scale, out=xscale[r0:r1] if want_scale else None)
+                    qs_c, qi_c = eng.accum_scales(cm_c, d, r1 - r0)
+                    eng.epoch_accumulate(x[r0:r1], w, dist_kind, p, algo, qs_c, acc, ws, bmu_out=bmu[r0:r1], xscale=xs_c)
+                    eng.accum_fold(acc, qi_c, K, d, sd)
+                    torch.maximum(colmax, cm_c, out=colmax)
+                all_reduce(sd)
+                eng.accum_finalize_f64(sd, K, d, S, c)
+                tail(first, False, None)
+                first += 1
+                n_total = n
+                if group is not None:
+                    import torch.distributed as dist
+                    cnt = torch.tensor([float(n)], dtype=torch.float64, device=colmax.device)
+                    dist.all_reduce(colmax, op=dist.ReduceOp.MAX, group=group)
+                    dist.all_reduce(cnt, op=dist.ReduceOp.SUM, group=group)
+                    n_total = int(cnt.item())
+                qscale, qinv = eng.accum_scales(colmax, d, max(n_total, 1))
+            else:
+                xscale, qscale, qinv = self._sample_stats(eng, x, want_scale, group, cache_key=x if x is data else None)
+
+            if graphed:
+                # One CUDA graph of the whole epoch, replayed n_ep - 1 times: sigma / eta live in a device-side
+                # schedule indexed by a device-side epoch counter, so the captured launches never change.
+                sched = eng.to_device(torch.tensor([[float(v) for v in schedule(t)] for t in range(iter_beg, iter_end)],
+                                                   dtype=torch.float64))
+                epoch_idx = eng.zeros(1, dtype=torch.int32)
+
+                def epoch_body():
+                    eng.prepare_codebook(w, dist_kind, p, ws)
+                    if n > 0:
+                        eng.epoch_accumulate(x, w, dist_kind, p, algo, qscale, acc, ws, bmu_out=bmu, xscale=xscale)
+                    all_reduce(acc)
+                    eng.accum_finalize(acc, qinv, K, d, S, c)
+                    eng.neigh_apply_sched(S, c, gx, gy, d, topo, neigh, sched, epoch_idx, self._std_coeff,
+                                          self.compact_support, num, den, tables)
+                    eng.merge(w, num, den)
+                    eng.epoch_advance(epoch_idx)
+
+                launches0 = eng.launches
+                epoch_body()                               # first epoch eagerly: warms up every kernel / NCCL
+                per_epoch = eng.launches - launches0
+                graph = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph):
+                    epoch_body()                           # captured, not executed
+                for _ in range(n_ep - 1):
+                    graph.replay()
+                eng.launches = launches0 + per_epoch * n_ep    # kernels actually executed (capture launches none)
+            else:
+                # epoch = BMU search + exact per-BMU sums (one fused kernel) -> integer all-reduce of the shards ->
+                # everything else (eng.epoch_tail: finalize, apply, merge, preparation of the new codebook)
+                for t in range(first, iter_end):
+                    if prof is not None:
+                        ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                        ev[0].record()
+                    if n > 0:               # a rank may hold an EMPTY shard: it still joins the all-reduce and the tail
+                        eng.epoch_accumulate(x, w, dist_kind, p, algo, qscale, acc, ws, bmu_out=bmu, xscale=xscale)
+                    if prof is not None:
+                        ev[1].record()
+                        prof.append(ev)
+                    all_reduce(acc)
+                    tail(t, True, qinv)
 
         self._weights = w.cpu().numpy().reshape(gx, gy, d)      # synchronises; fp32 like xpysom.py:580-583
         if verbose:
             print('\n quantization error:', self.quantization_error(data))
         return self
+
+    def _train_streamed(self, eng, host, w, acc, S, c, ws, dist_kind, p, algo, want_scale, group, all_reduce, tail,
+                        iter_beg, iter_end, K, d):
+        """Out-of-core epochs: the samples stay in (page-locked) host memory and every epoch streams them through two
+        device block buffers; block i+1 is copied while block i is searched and accumulated.  Each block has its own
+        column scales (computed when it is first seen, then kept: they are a few hundred bytes) and is folded into
+        running fp64 sums in block order, so the result does not depend on timing."""
+        n = host.shape[0]
+        ld = (d + 3) // 4 * 4
+        budget = max(self._device_budget(eng), 4 * 256 * ld * 4)
+        rows = max(256, (budget // (2 * ld * 4)) // 256 * 256)
+        rows = min(rows, (n + 255) // 256 * 256)
+        nblocks = -(-n // rows)
+        host = host.contiguous()
+        registered = False
+        if not host.is_pinned():
+            rc = torch.cuda.cudart().cudaHostRegister(host.data_ptr(), host.numel() * 4, 0)
+            registered = int(rc) == 0
+        bufs = [torch.empty((rows, ld), dtype=torch.float32, device=eng.device) for _ in range(min(2, nblocks))]
+        if ld != d:
+            for b in bufs:
+                b.zero_()
+        copy_stream = torch.cuda.Stream(device=eng.device)
+        cur = torch.cuda.current_stream(eng.device)
+        sd = eng.zeros(K * d + K, dtype=torch.float64)
+        xscale_all = eng.empty(n) if want_scale else None
+        bmu = eng.empty(rows, dtype=torch.int32)
+        block_scales = [None] * nblocks
+        freed = [None, None]                       # event: the compute that last read buffer j has finished
+        self.stats['streamed_blocks'] = nblocks
+        self.stats['streamed_block_rows'] = rows
+        try:
+            eng.prepare_codebook(w, dist_kind, p, ws)
+            for t in range(iter_beg, iter_end):
+                landed = [None] * nblocks
+
+                def issue(i):
+                    j = i % len(bufs)
+                    r0, r1 = i * rows, min(n, (i + 1) * rows)
+                    with torch.cuda.stream(copy_stream):
+                        if freed[j] is not None:
+                            copy_stream.wait_event(freed[j])
+                        bufs[j][:r1 - r0, :d].copy_(host[r0:r1], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(copy_stream)
+                    landed[i] = ev
+
+                copy_stream.wait_stream(cur)
+                issue(0)
+                for i in range(nblocks):
+                    if i + 1 < nblocks:
+                        issue(i + 1)
+                    j = i % len(bufs)
+                    r0, r1 = i * rows, min(n, (i + 1) * rows)
+                    xb = bufs[j][:r1 - r0, :d]
+                    cur.wait_event(landed[i])
+                    if block_scales[i] is None:
+                        xs_b, cm_b = eng.prepare_samples(xb, want_scale, out=xscale_all[r0:r1] if want_scale else None)
+                        block_scales[i] = eng.accum_scales(cm_b, d, r1 - r0)
+                    xs_b = xscale_all[r0:r1] if want_scale else None
+                    qs_b, qi_b = block_scales[i]
+                    eng.epoch_accumulate(xb, w, dist_kind, p, algo, qs_b, acc, ws, bmu_out=bmu[:r1 - r0], xscale=xs_b)
+                    eng.accum_fold(acc, qi_b, K, d, sd)
+                    ev = torch.cuda.Event()
+                    ev.record(cur)
+                    freed[j] = ev
+                all_reduce(sd)
+                eng.accum_finalize_f64(sd, K, d, S, c)
+                tail(t, False, None)
+            torch.cuda.current_stream(eng.device).synchronize()
+        finally:
+            if registered:
+                torch.cuda.cudart().cudaHostUnregister(host.data_ptr())
 
     def train_batch(self, data, num_iteration, verbose=False):
         """Compatibility with MiniSom, alias for train (xpysom.py:597-599)."""
@@ -394,7 +515,7 @@ class XPySom:
         x = self._data_to_device(eng, data)
         ws = eng.workspace(0, gx * gy, d)
         eng.prepare_codebook(w, dist_kind, p, ws)
-        xscale = eng.prepare_samples(x) if self._wants_xscale(dist_kind) else None
+        xscale = eng.prepare_samples(x, True)[0] if (self._wants_xscale(dist_kind) and x.shape[0] > 0) else None
         bmu = eng.bmu(x, w, dist_kind, p, _lib.ALGO[self._algo], ws, xscale=xscale)
         return bmu, x, w, eng
 
@@ -542,9 +663,8 @@ class XPySom:
     def __getstate__(self):
         state = self.__dict__.copy()
         state['_engine'] = None            # device handles are rebuilt on demand
-        state['_process_group'] = None
-        state.pop('_peer_cache', None)
-        state.pop('_xscale_cache', None)
+        state['_process_group'] = None if self._process_group in (None, False) else _UNPICKLED_SHARDED
+        state.pop('_stats_cache', None)
         state['_profile_events'] = []
         state['xp'] = None
         return state
