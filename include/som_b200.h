@@ -223,18 +223,24 @@ int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, 
                         float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats,
                         void *ws_dev, size_t ws_bytes, void *stream);
 
-/* ---- sharded path: the one exchange step -------------------------------------------------------
+/* ---- sharded path: the one exchange step, fused into the epoch tail ---------------------------
  * The reference sums the per-block partial updates with Dask (`sum(...)` over the delayed `_update`
- * results, xpysom.py:574-583).  With one process per GPU that sum is ONE all-reduce of [S | c]
- * (K*D + K floats) per epoch.  For the small buffers of most maps an NCCL all-reduce is pure latency,
- * so the library offers a one-shot all-reduce over NVLink peer memory (single node, CUDA IPC):
- * every rank creates a communicator, the 64-byte handles are exchanged by the host (any transport),
- * every rank connects, and from then on som_b200_peer_allreduce sums `floats` values in place on the
- * caller's stream, in rank order (bitwise identical on all ranks).  Larger buffers / several nodes:
- * keep using NCCL. */
-int som_b200_peer_create(int64_t max_floats, int world, int rank, void **comm_out, void *handle_out_64_bytes);
+ * results, xpysom.py:545-558).  With one process per GPU that is ONE sum of the exact accumulators
+ * [S | counts] across the ranks per epoch: an all-reduce of the integer buffer by the caller (NCCL),
+ * or -- single node, small maps, where that all-reduce is pure latency -- accumulators that live in
+ * NVLink peer memory (CUDA IPC) and are summed over the ranks by the finalize phase itself:
+ *   every rank creates a communicator for `acc_words` (som_b200_accum_words) 64-bit words, the 64-byte
+ *   handles are exchanged by the host (any transport), every rank connects;
+ *   per epoch every rank passes som_b200_peer_accumulator(comm) as `acc_dev` to
+ *   som_b200_epoch_accumulate and then to som_b200_epoch_tail (or som_b200_accum_finalize), which
+ *   recognise it, wait for all ranks' accumulators of this exchange and read them over NVLink.  The
+ *   pointer alternates between two buffers, so ask again every epoch.  Integer sums are exact:
+ *   every rank gets the same bits, equal to one GPU holding all the rows.
+ * All ranks must make the same sequence of calls.  Before som_b200_peer_destroy the caller must make
+ * sure (a barrier over the ranks) that no peer is still inside an exchange. */
+int som_b200_peer_create(size_t acc_words, int world, int rank, void **comm_out, void *handle_out_64_bytes);
 int som_b200_peer_connect(void *comm, const void *all_handles_world_x_64_bytes);
-int som_b200_peer_allreduce(void *comm, float *data_dev, int64_t floats, void *stream);
+uint64_t *som_b200_peer_accumulator(void *comm);
 int som_b200_peer_destroy(void *comm);
 
 /* quantization / quantization_error support (xpysom.py:620-707): for each row,

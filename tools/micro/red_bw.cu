@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(128) k_u64(const float *X, const int *bmu, int
 // bulk: each warp owns NBUF staging buffers of PIECE columns (int64); a row is sent as ceil(d / PIECE) bulk reductions
 constexpr int PIECE = 128, NBUF = 4;
 __global__ void __launch_bounds__(128) k_bulk(const float *X, const int *bmu, int64_t n, int d, const float *scale,
-                                              unsigned long long *S) {
+                                              unsigned long long *S, int R, size_t rep_stride) {
+    S += (size_t)(blockIdx.x % R) * rep_stride;       // R replicas of the accumulator spread hot rows over R L2 lines
     __shared__ __align__(128) long long stage[4][NBUF][PIECE];
     const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, d4 = d >> 2;
     const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -122,14 +123,17 @@ int main() {
             CK(cudaMemcpy(scale, hs.data(), c.d * 4, cudaMemcpyHostToDevice));
             cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
             const int grid = sms * 4;
-            for (int which = 0; which < 3; ++which) {
+            const int RMAX = 16;
+            cudaFree(S64); CK(cudaMalloc(&S64, (size_t)c.k * c.d * 8 * RMAX));
+            for (int which = 0; which < 6; ++which) {
+                const int R = which < 3 ? 1 : which == 3 ? 4 : which == 4 ? 8 : 16;
                 float best = 1e30f;
                 for (int rep = 0; rep < 4; ++rep) {
-                    CK(cudaMemset(S32, 0, (size_t)c.k * c.d * 4)); CK(cudaMemset(S64, 0, (size_t)c.k * c.d * 8));
+                    CK(cudaMemset(S32, 0, (size_t)c.k * c.d * 4)); CK(cudaMemset(S64, 0, (size_t)c.k * c.d * 8 * RMAX));
                     CK(cudaEventRecord(e0));
                     if (which == 0) k_f32v4<<<grid, 128>>>(X, bmu, c.n, c.d, S32);
                     else if (which == 1) k_u64<<<grid, 128>>>(X, bmu, c.n, c.d, scale, S64);
-                    else k_bulk<<<grid, 128>>>(X, bmu, c.n, c.d, scale, S64);
+                    else k_bulk<<<grid, 128>>>(X, bmu, c.n, c.d, scale, S64, R, (size_t)c.k * c.d);
                     CK(cudaEventRecord(e1)); CK(cudaEventSynchronize(e1)); CK(cudaGetLastError());
                     float ms; CK(cudaEventElapsedTime(&ms, e0, e1));
                     if (rep > 0 && ms < best) best = ms;
@@ -137,10 +141,10 @@ int main() {
                 // checksum: total of S must equal the total of x (fixed point: exactly)
                 double tot = 0;
                 if (which == 0) { std::vector<float> h((size_t)c.k * c.d); CK(cudaMemcpy(h.data(), S32, h.size() * 4, cudaMemcpyDeviceToHost)); for (float v : h) tot += v; }
-                else { std::vector<long long> h((size_t)c.k * c.d); CK(cudaMemcpy(h.data(), S64, h.size() * 8, cudaMemcpyDeviceToHost)); for (long long v : h) tot += (double)v / 1099511627776.0; }
+                else { std::vector<long long> h((size_t)c.k * c.d * RMAX); CK(cudaMemcpy(h.data(), S64, h.size() * 8, cudaMemcpyDeviceToHost)); for (long long v : h) tot += (double)v / 1099511627776.0; }
                 double ref = 0; for (float v : hx) ref += v;
                 printf("%-5s %s  %-22s %8.3f ms  %6.2f elem/clk/SM(@1.965GHz)  %7.1f GB/s of x   sum rel err %.2e\n", c.name,
-                       hot ? "hot " : "unif", which == 0 ? "red.v4.f32" : which == 1 ? "red.u64 scalar" : "bulk reduce u64",
+                       hot ? "hot " : "unif", which == 0 ? "red.v4.f32" : which == 1 ? "red.u64 scalar" : which == 2 ? "bulk reduce u64" : which == 3 ? "bulk u64, 4 replicas" : which == 4 ? "bulk u64, 8 replicas" : "bulk u64, 16 replicas",
                        best, (double)c.n * c.d / (best * 1e-3) / 1.965e9 / sms, (double)c.n * c.d * 4 / (best * 1e-3) / 1e9,
                        (tot - ref) / ref);
             }

@@ -1,9 +1,11 @@
-"""Multi-GPU check of the one-shot NVLink all-reduce (run under torchrun on >= 2 GPUs of one box):
+"""Multi-GPU check of the sharded path's exchange step (run under torchrun on >= 2 GPUs of one box):
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 tools/peer_check.py
 
-Compares it with NCCL on several sizes (values, bitwise agreement across ranks, latency) and trains a small
-map through XPySom both ways.
+Trains several maps through XPySom with the accumulators in NVLink peer memory (the exchange fused into the epoch
+tail, csrc/peer.cuh) and with the NCCL all-reduce of the integer accumulator, and checks that both give the SAME bits,
+that every rank holds the same bits, and that they equal ONE GPU training on all the rows; then times both on the
+config-2 shard.
 """
 import os
 import sys
@@ -14,15 +16,13 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from xpysom_dask_b200 import XPySom            # noqa: E402
-from xpysom_dask_b200.engine import CudaEngine  # noqa: E402
-from xpysom_dask_b200.peer import PeerReducer   # noqa: E402
 
 rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
 torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", rank)))
 dist.init_process_group("nccl", device_id=torch.device("cuda", torch.cuda.current_device()))
 dev = torch.device("cuda", torch.cuda.current_device())
-eng = CudaEngine(dev)
 ok = True
+quick = "--quick" in sys.argv
 
 
 def log(*a):
@@ -30,66 +30,82 @@ def log(*a):
         print(*a, flush=True)
 
 
-for n in (1, 5, 27200, 1024 * 65, 1 << 20):
-    red = PeerReducer(eng, dist.group.WORLD, n)
-    if not red.active:
-        log("peer all-reduce NOT active (IPC unavailable?) -> NCCL fallback would be used")
-        ok = False
-        break
-    g = torch.Generator(device="cpu").manual_seed(1000 * n + rank)
-    worst = 0.0
-    for it in range(20):
-        x = torch.randn(n, generator=g).to(dev)
-        ref = x.clone()
-        dist.all_reduce(ref)
-        red.all_reduce_(x)
-        worst = max(worst, float((x - ref).abs().max() / ref.abs().max().clamp_min(1e-30)))
-        gathered = [torch.empty_like(x) for _ in range(world)]
-        dist.all_gather(gathered, x)
-        same = all(torch.equal(gathered[0], t) for t in gathered)
-        if not same or worst > 1e-5:
-            ok = False
-    # latency, back to back on one stream
-    x = torch.randn(n, generator=g).to(dev)
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    reps = 200
-    torch.cuda.synchronize(); dist.barrier()
-    ev[0].record()
-    for _ in range(reps):
-        red.all_reduce_(x)
-    ev[1].record()
-    torch.cuda.synchronize(); dist.barrier()
-    ev[2].record()
-    for _ in range(reps):
-        dist.all_reduce(x)
-    ev[3].record()
-    torch.cuda.synchronize()
-    log("n=%8d floats: max rel diff vs NCCL %.2e, identical on all ranks %s | one-shot %.1f us, NCCL %.1f us per call"
-        % (n, worst, same, ev[0].elapsed_time(ev[1]) * 1e3 / reps, ev[2].elapsed_time(ev[3]) * 1e3 / reps))
-    red.close()
+def same_everywhere(t):
+    lo, hi = t.clone(), t.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return bool(torch.equal(lo, hi))
 
-# the host class, both ways
-# deterministic set-up (small-integer samples: exact per-BMU sums whatever the order of the atomics; a 64-neuron map:
-# un-sliced neighbourhood apply), so that two runs can be compared tightly instead of drifting apart chaotically
-rng = np.random.RandomState(21)
-centres = rng.randint(0, 8, size=(24, 32))
-data = (centres[rng.randint(24, size=16000)] + rng.randint(0, 2, size=(16000, 32))).astype(np.float32)
-shard = data[rank::world]
-res = {}
-for mode in ("peer", "nccl"):
-    os.environ["SOM_B200_PEER"] = "0" if mode == "nccl" else "1"
-    som = XPySom(8, 8, 32, sigma=2.0, random_seed=4, device=dev, process_group=True)
-    som.train(shard, 6)
-    res[mode] = torch.as_tensor(som.get_weights()).to(dev)
-    used = getattr(som, "_peer_cache", None)
-    log("XPySom.train (%s): peer reducer %s" % (mode, "active" if used is not None and used[1].active else "not used"))
-diff = float((res["peer"] - res["nccl"]).abs().max() / res["nccl"].abs().max())
-gath = [torch.empty_like(res["peer"]) for _ in range(world)]
-dist.all_gather(gath, res["peer"])
-replicated = all(torch.equal(gath[0], t) for t in gath)
-log("codebook after 6 epochs: peer vs NCCL max rel diff %.2e; replicated bit-exactly across ranks: %s" % (diff, replicated))
-if diff > 1e-6 or not replicated:
-    ok = False
+
+CASES = [
+    # (gx, gy, d, rows per rank, kwargs): fused cooperative tail | separate launches (wide) | hexagonal | tiny D
+    (16, 16, 64, 20000, {}),
+    (24, 25, 100, 12000, {"neighborhood_function": "bubble"}),
+    (12, 11, 24, 9000, {"topology": "hexagonal", "activation_distance": "cosine"}),
+    (40, 40, 16, 30000, {"decay_function": "linear"}),
+    (9, 9, 7, 5000, {"activation_distance": "manhattan"}),
+]
+for gx, gy, d, n, kw in CASES:
+    rng = np.random.RandomState(100 + rank)
+    shard = torch.from_numpy(rng.random_sample((n + 37 * rank, d)).astype(np.float32)).to(dev)    # ragged shards
+    res = {}
+    for mode in ("peer", "nccl"):
+        os.environ["SOM_B200_PEER"] = "0" if mode == "nccl" else "1"
+        som = XPySom(gx, gy, d, random_seed=4, device=dev, process_group=True, **kw)
+        som.train(shard, 7)
+        som.train(shard, 12, iter_beg=7, iter_end=12)            # a second call on the same communicator
+        res[mode] = torch.as_tensor(som.get_weights()).to(dev)
+        used = getattr(som, "_peer_cache", None)
+        active = used is not None and used[1].active
+        if mode == "peer" and not active:
+            log("  peer accumulators NOT active (IPC unavailable?)")
+            ok = False
+        if used is not None:
+            used[1].close()
+            som._peer_cache = None
+    sizes = [torch.zeros(1, dtype=torch.int64, device=dev) for _ in range(world)]
+    dist.all_gather(sizes, torch.tensor([shard.shape[0]], dtype=torch.int64, device=dev))
+    parts = [torch.empty((int(s.item()), d), dtype=torch.float32, device=dev) for s in sizes]
+    dist.all_gather(parts, shard)
+    single = XPySom(gx, gy, d, random_seed=4, device=dev, **kw)
+    single.train(torch.cat(parts), 7)
+    single.train(torch.cat(parts), 12, iter_beg=7, iter_end=12)
+    one = torch.as_tensor(single.get_weights()).to(dev)
+    a = torch.equal(res["peer"], res["nccl"])
+    b = same_everywhere(res["peer"])
+    c = torch.equal(res["peer"], one)
+    rel = float((res["peer"] - one).abs().max() / one.abs().max())
+    log("%2dx%-2d d=%-3d %s: peer == NCCL bitwise %s | identical on all ranks %s | == one GPU on all rows %s (rel %.1e)"
+        % (gx, gy, d, kw or "", a, b, c, rel))
+    if not (a and b and c):
+        ok = False
+
+if not quick:
+    # timing on the config-2 shard (1M x 64 per rank, 32 x 32)
+    x = torch.rand((1_000_000, 64), device=dev)
+    for mode in ("peer", "nccl", "peer", "nccl"):
+        os.environ["SOM_B200_PEER"] = "0" if mode == "nccl" else "1"
+        som = XPySom(32, 32, 64, random_seed=0, device=dev, process_group=True)
+        som.train(x, 200, iter_beg=0, iter_end=5)
+        ts = []
+        for rep in range(5):
+            torch.cuda.synchronize(); dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            som.train(x, 200, iter_beg=5, iter_end=55)
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / 50], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ts.append(float(t.item()))
+        log("config 2 shard on %d GPUs, %-4s: %.4f ms per epoch (median of 5 x 50 epochs; all: %s)"
+            % (world, mode, float(np.median(ts)), " ".join("%.4f" % v for v in ts)))
+        used = getattr(som, "_peer_cache", None)
+        if used is not None:
+            used[1].close()
+            som._peer_cache = None
+
 log("PEER CHECK", "PASSED" if ok else "FAILED")
+dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)

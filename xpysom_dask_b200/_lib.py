@@ -64,10 +64,10 @@ SIGNATURES = {
                                            ctypes.c_int, ctypes.c_double, ctypes.c_double, ctypes.c_double, ctypes.c_int,
                                            ctypes.c_int, ctypes.c_float, c_f32p, c_f32p, c_f32p, ctypes.c_size_t,
                                            ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
-    "som_b200_peer_create": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+    "som_b200_peer_create": (ctypes.c_int, [ctypes.c_size_t, ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
                                             ctypes.c_void_p]),
     "som_b200_peer_connect": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p]),
-    "som_b200_peer_allreduce": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int64, ctypes.c_void_p]),
+    "som_b200_peer_accumulator": (ctypes.c_void_p, [ctypes.c_void_p]),
     "som_b200_peer_destroy": (ctypes.c_int, [ctypes.c_void_p]),
     "som_b200_quantize": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int,
                                          c_i32p, c_f32p, c_f32p, ctypes.c_void_p]),

@@ -15,6 +15,7 @@
 //                             streamed out-of-core blocks), accum_finalize_f64_kernel rounds those once
 #pragma once
 #include "common.cuh"
+#include "peer.cuh"
 
 namespace somb200 {
 
@@ -73,24 +74,14 @@ inline int launch_accumulate(const float *X, int64_t n, int d, int64_t ldx, cons
     return check_cuda(cudaGetLastError(), "accumulate_kernel launch");
 }
 
-// int64 sums -> the fp32 S (K, D) and c (K) the neighbourhood apply reads; the integers are cleared for the next
-// epoch when `clear` is set.  double(S_int) * 2^-q is exact up to 2^53, then rounded ONCE to fp32.
-__global__ void accum_finalize_kernel(unsigned long long *__restrict__ Si, unsigned long long *__restrict__ ci,
-                                      const float *__restrict__ qinv, int k, int d, int lds, float *__restrict__ S,
-                                      float *__restrict__ c, int clear) {
+// int64 sums -> the fp32 S (K, D) and c (K) the neighbourhood apply reads (peer.cuh: accum_finalize_elements); the
+// integers are cleared for the next epoch when `clear` is set.  With a PeerView the sums run over the accumulators of
+// all ranks (the sharded path's exchange step, fused in here).
+__global__ void accum_finalize_kernel(unsigned long long *__restrict__ Si, const float *__restrict__ qinv, int k, int d,
+                                      int lds, float *__restrict__ S, float *__restrict__ c, int clear, const PeerView V) {
     pdl_wait(); pdl_trigger();
-    const int64_t tot = (int64_t)k * lds;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(e / lds), col = (int)(e % lds);
-        const long long v = (long long)Si[e];
-        if (col < d) S[(int64_t)row * d + col] = (float)((double)v * (double)qinv[col]);
-        if (clear && v) Si[e] = 0ull;
-    }
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k; e += gridDim.x * blockDim.x) {
-        const unsigned long long v = ci[e];
-        c[e] = (float)v;
-        if (clear && v) ci[e] = 0ull;
-    }
+    accum_finalize_elements(Si, qinv, k, d, lds, S, c, clear, V, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
+                            (int64_t)gridDim.x * blockDim.x);
 }
 
 // one part of a multi-part epoch (its own column scales): Sd += double(S_int) * 2^-q, cd += count; integers cleared

@@ -20,6 +20,7 @@
 // all CTAs are co-resident (the launch fails otherwise, it cannot deadlock), and the wait is bounded.
 #pragma once
 #include "common.cuh"
+#include "peer.cuh"
 #include "neigh.cuh"
 #include "misc.cuh"
 
@@ -29,7 +30,8 @@ struct TailArgs {
     NeighParams P;
     double sigma, dd;
     float *S, *c, *num, *den, *W;
-    unsigned long long *Si, *ci;        // exact sums / counts (nullptr: S and c already hold this epoch's fp32 values)
+    unsigned long long *Si;             // exact sums, then counts (nullptr: S and c already hold this epoch's fp32 values)
+    PeerView peer;                      // world > 0: the sums run over all ranks' accumulators (peer.cuh)
     const float *qinv;
     int lds;
     float *partials;                    // [slices][K*D + K] when slices > 1
@@ -74,20 +76,8 @@ epoch_tail_kernel(TailArgs A) {
     // ---- phase 0 ----
     neigh_tables_fill(A.P.gx, A.P.gy, A.P.kind, A.P.compact, A.P.shifted, A.sigma, A.dd, const_cast<float *>(A.P.tx),
                       const_cast<float *>(A.P.ty), const_cast<float *>(A.P.mx), const_cast<float *>(A.P.my), tid, nthr);
-    if (A.Si != nullptr) {
-        const int64_t tot = (int64_t)K * A.lds;
-        for (int64_t e = tid; e < tot; e += nthr) {
-            const int row = (int)(e / A.lds), col = (int)(e % A.lds);
-            const long long v = (long long)A.Si[e];
-            if (col < D) A.S[(int64_t)row * D + col] = (float)((double)v * (double)A.qinv[col]);
-            if (v) A.Si[e] = 0ull;
-        }
-        for (int e = tid; e < K; e += nthr) {
-            const unsigned long long v = A.ci[e];
-            A.c[e] = (float)v;
-            if (v) A.ci[e] = 0ull;
-        }
-    }
+    if (A.Si != nullptr)
+        accum_finalize_elements(A.Si, A.qinv, K, D, A.lds, A.S, A.c, 1, A.peer, tid, nthr);
     if (tid < 4) A.gstat[tid] = 0u;
     grid_barrier(A.bar);
     // ---- phase 1: apply ----

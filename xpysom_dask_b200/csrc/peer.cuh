@@ -1,41 +1,56 @@
-// One-shot all-reduce of the per-epoch [S | c] partials over NVLink peer memory (single node).
+// The one exchange step of the sharded path, fused into the epoch tail: exact accumulators in NVLink peer memory.
 //
-// The reference reduces its per-block partial updates with a Dask `sum` (xpysom.py:574-583); the sharded
-// path here needs ONE sum of K*D + K floats per epoch across the ranks.  At config 2 that is 0.26 MB: an NCCL
-// all-reduce of that size is pure latency (~0.1 ms per epoch against a 0.42 ms epoch).  Every rank owns a
-// "mailbox" in its own HBM, opened by all peers through CUDA IPC:
+// The reference sums the per-block partial updates with a Dask `sum` (xpysom.py:545-558); with one process per GPU
+// that is ONE sum of the per-BMU accumulators [S | counts] across the ranks per epoch.  For the small buffers of
+// most maps (config 2: 0.5 MB of int64) an NCCL all-reduce is pure latency plus a stream hand-over in the middle of
+// the epoch's launch chain.  Here the accumulator of every rank lives in a "mailbox" in its own HBM that all peers of
+// the node have opened through CUDA IPC:
 //
-//     [0, 512)        flags[2][world]  u32   (written by the peers: "rank r published sequence number seq")
-//     [512, 520)      block counters of the two parities (local)
-//     [1024, ...)     buf[2][n_pad]    f32   (this rank's published partials, double-buffered by seq parity)
+//     [0, 512)          flags[2][world]  u32   written by the peers: "rank r has finished accumulating exchange seq"
+//     [1024, ...)       acc[2][words]    u64   this rank's exact accumulators, alternating by exchange parity
 //
-// One kernel per call, on the caller's stream:  copy the local partials into buf[seq & 1]; the last block to
-// finish publishes `seq` into every peer's flag row (release, system scope); every block waits until all `world`
-// flags of its own mailbox carry `seq` (acquire, system scope); then each block sums its slice over the ranks IN
-// RANK ORDER (bitwise identical on every rank) straight from the peers' mailboxes and writes it back in place.
-// Double buffering makes one barrier per call enough: a rank overwrites buf[p] for seq + 2 only after it has seen
-// every peer's flag for seq + 1, which a peer publishes only after it has finished reading seq.
-// Waits are bounded: a missing peer traps (-> CUDA error on the host), it never hangs the GPU.
+// and the kernel that rounds the integer sums to the fp32 S, c of the neighbourhood apply (phase 0 of
+// epoch_tail_kernel, or accum_finalize_kernel on large maps) reads the accumulators of ALL ranks directly:
+//   1. one block tells every peer that this rank's BMU kernel of exchange `seq` is complete (stream order; release,
+//      system scope);
+//   2. every block waits until its own mailbox holds all `world` flags of `seq` (acquire, system scope);
+//   3. every element is the INTEGER sum over the ranks' accumulators (remote loads, all in flight at once) -- exact,
+//      so every rank, and one GPU holding all the rows, produce the same bits without any ordering rule;
+//   4. the rank clears its accumulator of the PREVIOUS exchange (the other parity): a peer publishes `seq` only
+//      after it has finished reading `seq - 1`, so nobody can still be reading it, and the next epoch accumulates
+//      into a clean buffer while slower peers are still reading this epoch's.
+// No separate all-reduce kernel, no NCCL call, no extra copy.  Waits are bounded: a missing peer traps (a CUDA
+// error on the host), it never hangs the GPU.
 #pragma once
+#include <string.h>
 #include "common.cuh"
 
 namespace somb200 {
 
 constexpr int PEER_MAX_WORLD = 16;
-constexpr int PEER_FLAGS_OFF = 0, PEER_CTR_OFF = 512, PEER_DATA_OFF = 1024;
-constexpr int PEER_THREADS = 256, PEER_MAX_BLOCKS = 64;       // all blocks must be co-resident (they wait on each other)
+constexpr int PEER_FLAGS_OFF = 0, PEER_DATA_OFF = 1024;
 
-struct PeerTable { uint8_t *p[PEER_MAX_WORLD]; };
+// what the finalize phase needs on the device (passed by value; world == 0: not sharded this way)
+struct PeerView {
+    int world = 0, rank = 0;
+    unsigned seq = 0;
+    int par = 0;                       // flag row and accumulator of this exchange
+    size_t words = 0;                  // 64-bit words per accumulator
+    uint8_t *p[PEER_MAX_WORLD] = {};
+};
 
 struct PeerComm {
     int world = 0, rank = 0;
-    int64_t floats = 0, n_pad = 0;
-    size_t bytes = 0;
+    size_t words = 0, bytes = 0;
     uint8_t *mailbox = nullptr;
-    PeerTable table{};
+    uint8_t *table[PEER_MAX_WORLD] = {};
     bool opened[PEER_MAX_WORLD] = {};
-    unsigned seq = 0;
+    unsigned seq = 0;                  // exchanges completed so far
     bool connected = false;
+    unsigned long long *acc(int par) const {
+        return reinterpret_cast<unsigned long long *>(mailbox + PEER_DATA_OFF) + (size_t)par * words;
+    }
+    int next_par() const { return (int)((seq + 1u) & 1u); }
 };
 
 __device__ __forceinline__ void st_release_sys(unsigned *p, unsigned v) {
@@ -46,81 +61,100 @@ __device__ __forceinline__ unsigned ld_acquire_sys(const unsigned *p) {
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ float4 ld_volatile_f4(const float4 *p) {
-    float4 v;
-    asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
-    return v;
-}
-__device__ __forceinline__ float ld_volatile_f1(const float *p) {
-    float v;
-    asm volatile("ld.volatile.global.f32 %0, [%1];" : "=f"(v) : "l"(p));
+__device__ __forceinline__ unsigned long long ld_peer_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
-__global__ void __launch_bounds__(PEER_THREADS)
-peer_allreduce_kernel(PeerTable T, int world, int rank, float *__restrict__ data, int64_t n, int64_t n_pad, unsigned seq) {
-    const int par = (int)(seq & 1u);
-    uint8_t *mine = T.p[rank];
-    float *mybuf = reinterpret_cast<float *>(mine + PEER_DATA_OFF) + (int64_t)par * n_pad;
-    const int64_t n4 = n >> 2;
-    const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nthr = (int64_t)gridDim.x * blockDim.x;
+__device__ __forceinline__ const unsigned long long *peer_acc(const PeerView &V, int r) {
+    return reinterpret_cast<const unsigned long long *>(V.p[r] + PEER_DATA_OFF) + (size_t)V.par * V.words;
+}
 
-    // 1. publish the local partials
-    for (int64_t i = tid; i < n4; i += nthr)
-        reinterpret_cast<float4 *>(mybuf)[i] = reinterpret_cast<const float4 *>(data)[i];
-    for (int64_t i = (n4 << 2) + tid; i < n; i += nthr) mybuf[i] = data[i];
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned *ctr = reinterpret_cast<unsigned *>(mine + PEER_CTR_OFF) + par;
-        if (atomicAdd(ctr, 1u) == gridDim.x - 1) {          // last block: everything of this rank is in its mailbox
-            *ctr = 0u;                                      // (next used two calls from now)
-            __threadfence_system();
-            for (int r = 0; r < world; ++r)
-                st_release_sys(reinterpret_cast<unsigned *>(T.p[r] + PEER_FLAGS_OFF) + par * world + rank, seq);
-        }
+// steps 1 and 2; every thread of the grid calls it before reading any accumulator
+__device__ __forceinline__ void peer_exchange_begin(const PeerView &V) {
+    if (blockIdx.x == 0 && (int)threadIdx.x < V.world) {
+        __threadfence_system();
+        st_release_sys(reinterpret_cast<unsigned *>(V.p[threadIdx.x] + PEER_FLAGS_OFF) + V.par * V.world + V.rank, V.seq);
     }
-    // 2. wait for every rank's flag in MY mailbox
-    if (threadIdx.x < world) {
-        const unsigned *f = reinterpret_cast<const unsigned *>(mine + PEER_FLAGS_OFF) + par * world + threadIdx.x;
+    if ((int)threadIdx.x < V.world) {
+        const unsigned *f = reinterpret_cast<const unsigned *>(V.p[V.rank] + PEER_FLAGS_OFF) + V.par * V.world + threadIdx.x;
         const long long t0 = clock64();
-        while (ld_acquire_sys(f) != seq) {
-            if (clock64() - t0 > 6000000000LL) {            // ~3 s: a peer never arrived
-                printf("som_b200: peer all-reduce timeout (rank %d waiting for rank %d, seq %u, saw %u)\n", rank,
-                       (int)threadIdx.x, seq, ld_acquire_sys(f));
+        while (ld_acquire_sys(f) != V.seq) {
+            if (clock64() - t0 > 20000000000LL) {            // ~10 s: a peer never arrived
+                printf("som_b200: peer exchange timeout (rank %d waiting for rank %d, seq %u, saw %u)\n", V.rank,
+                       (int)threadIdx.x, V.seq, ld_acquire_sys(f));
                 __trap();
             }
-            __nanosleep(100);
         }
     }
     __syncthreads();
-    // 3. sum over the ranks in rank order, in place
-    for (int64_t i = tid; i < n4; i += nthr) {
-        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int r = 0; r < world; ++r) {
-            const float4 v = ld_volatile_f4(reinterpret_cast<const float4 *>(T.p[r] + PEER_DATA_OFF) + (int64_t)par * (n_pad >> 2) + i);
-            a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
-        }
-        reinterpret_cast<float4 *>(data)[i] = a;
+}
+
+// step 3 for one element: the integer sum over the ranks, four remote loads in flight per thread and round
+__device__ __forceinline__ long long peer_sum(const PeerView &V, size_t e) {
+    unsigned long long s = 0ull;
+    for (int r = 0; r < V.world; r += 4) {
+        unsigned long long v[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) v[u] = (r + u < V.world) ? ld_peer_u64(peer_acc(V, r + u) + e) : 0ull;
+        s += (v[0] + v[1]) + (v[2] + v[3]);
     }
-    for (int64_t i = (n4 << 2) + tid; i < n; i += nthr) {
-        float a = 0.f;
-        for (int r = 0; r < world; ++r)
-            a += ld_volatile_f1(reinterpret_cast<const float *>(T.p[r] + PEER_DATA_OFF) + (int64_t)par * n_pad + i);
-        data[i] = a;
+    return (long long)s;
+}
+
+// The finalize phase shared by accum_finalize_kernel and phase 0 of epoch_tail_kernel (grid-stride over `nthr`
+// threads): int64 sums -> the fp32 S (K, D) and c (K); double(S_int) * 2^-q is exact up to 2^53, then rounded ONCE.
+// Local accumulator (V.world == 0): cleared as it is read.  Peer accumulators: summed over the ranks, the OTHER
+// parity's local accumulator is cleared (step 4).
+__device__ __forceinline__ void accum_finalize_elements(unsigned long long *Si, const float *qinv, int k, int d, int lds,
+                                                        float *S, float *c, int clear, const PeerView &V, int64_t tid,
+                                                        int64_t nthr) {
+    const int64_t tot = (int64_t)k * lds, all = tot + k;
+    if (V.world > 0) {
+        peer_exchange_begin(V);
+        unsigned long long *old = reinterpret_cast<unsigned long long *>(V.p[V.rank] + PEER_DATA_OFF) + (size_t)(V.par ^ 1) * V.words;
+        for (int64_t e = tid; e < all; e += nthr) {
+            const long long v = peer_sum(V, (size_t)e);
+            if (e < tot) {
+                const int row = (int)(e / lds), col = (int)(e % lds);
+                if (col < d) S[(int64_t)row * d + col] = (float)((double)v * (double)qinv[col]);
+            } else {
+                c[e - tot] = (float)(unsigned long long)v;
+            }
+            if (old[e]) old[e] = 0ull;
+        }
+        return;
+    }
+    for (int64_t e = tid; e < all; e += nthr) {
+        const long long v = (long long)Si[e];
+        if (e < tot) {
+            const int row = (int)(e / lds), col = (int)(e % lds);
+            if (col < d) S[(int64_t)row * d + col] = (float)((double)v * (double)qinv[col]);
+        } else {
+            c[e - tot] = (float)(unsigned long long)v;
+        }
+        if (clear && v) Si[e] = 0ull;
     }
 }
 
-inline int peer_create(int64_t floats, int world, int rank, PeerComm **out, void *handle64) {
-    SOM_REQUIRE(floats > 0 && world >= 2 && world <= PEER_MAX_WORLD && rank >= 0 && rank < world && out && handle64,
+// ---- host side ---------------------------------------------------------------------------------------------
+static PeerComm *g_peer_comms[8] = {};          // communicators of this process (one per model being trained)
+
+inline int peer_create(size_t words, int world, int rank, PeerComm **out, void *handle64) {
+    SOM_REQUIRE(words > 0 && world >= 2 && world <= PEER_MAX_WORLD && rank >= 0 && rank < world && out && handle64,
                 SOM_E_BADARG, "peer_create: bad argument (world %d, rank %d)", world, rank);
     static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    int slot = -1;
+    for (int i = 0; i < 8; ++i) if (!g_peer_comms[i]) { slot = i; break; }
+    SOM_REQUIRE(slot >= 0, SOM_E_BADARG, "peer_create: too many live communicators in this process");
     PeerComm *c = new PeerComm();
-    c->world = world; c->rank = rank; c->floats = floats;
-    c->n_pad = (floats + 63) / 64 * 64;
-    c->bytes = (size_t)PEER_DATA_OFF + (size_t)2 * c->n_pad * sizeof(float);
+    c->world = world; c->rank = rank;
+    c->words = (words + 63) / 64 * 64;
+    c->bytes = (size_t)PEER_DATA_OFF + (size_t)2 * c->words * 8;
     cudaError_t e = cudaMalloc(reinterpret_cast<void **>(&c->mailbox), c->bytes);
     if (e == cudaSuccess) e = cudaMemset(c->mailbox, 0, c->bytes);
+    if (e == cudaSuccess) e = cudaDeviceSynchronize();
     cudaIpcMemHandle_t h;
     if (e == cudaSuccess) e = cudaIpcGetMemHandle(&h, c->mailbox);
     if (e != cudaSuccess) {
@@ -129,7 +163,8 @@ inline int peer_create(int64_t floats, int world, int rank, PeerComm **out, void
         return check_cuda(e, "peer_create (cudaMalloc / cudaIpcGetMemHandle)");
     }
     memcpy(handle64, &h, 64);
-    c->table.p[rank] = c->mailbox;
+    c->table[rank] = c->mailbox;
+    g_peer_comms[slot] = c;
     *out = c;
     return 0;
 }
@@ -143,30 +178,40 @@ inline int peer_connect(PeerComm *c, const void *all_handles) {
         void *p = nullptr;
         cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
         if (e != cudaSuccess) return check_cuda(e, "cudaIpcOpenMemHandle");
-        c->table.p[r] = static_cast<uint8_t *>(p);
+        c->table[r] = static_cast<uint8_t *>(p);
         c->opened[r] = true;
     }
     c->connected = true;
     return 0;
 }
 
-inline int peer_allreduce(PeerComm *c, float *data, int64_t floats, cudaStream_t st) {
-    SOM_REQUIRE(c && c->connected && data && floats > 0 && floats <= c->floats, SOM_E_BADARG,
-                "peer_allreduce: bad argument (floats %lld, capacity %lld)", (long long)floats, (long long)(c ? c->floats : 0));
-    SOM_REQUIRE((reinterpret_cast<uintptr_t>(data) & 15) == 0, SOM_E_SHAPE, "peer_allreduce: data must be 16-byte aligned");
-    c->seq += 1;
-    if (c->seq == 0) c->seq = 2;                                  // wrap-around keeps the parity alternating
-    int blocks = (int)ceil_div(floats, (int64_t)PEER_THREADS * 4);
-    if (blocks > PEER_MAX_BLOCKS) blocks = PEER_MAX_BLOCKS;
-    peer_allreduce_kernel<<<blocks, PEER_THREADS, 0, st>>>(c->table, c->world, c->rank, data, floats, c->n_pad, c->seq);
-    return check_cuda(cudaGetLastError(), "peer_allreduce_kernel launch");
+// the communicator whose NEXT exchange accumulates into `acc` (nullptr: a plain local accumulator)
+inline PeerComm *peer_lookup(const void *acc) {
+    if (!acc) return nullptr;
+    for (int i = 0; i < 8; ++i) {
+        PeerComm *c = g_peer_comms[i];
+        if (c && c->connected && acc == (const void *)c->acc(c->next_par())) return c;
+    }
+    return nullptr;
 }
 
+// the view of the next exchange; the caller launches exactly one finalize phase with it
+inline PeerView peer_next_exchange(PeerComm *c) {
+    PeerView V;
+    c->seq += 1;
+    if (c->seq == 0) c->seq = 2;                                  // wrap-around keeps the parity alternating
+    V.world = c->world; V.rank = c->rank; V.seq = c->seq; V.par = (int)(c->seq & 1u); V.words = c->words;
+    for (int r = 0; r < c->world; ++r) V.p[r] = c->table[r];
+    return V;
+}
+
+// The caller guarantees (with a barrier over the ranks) that no peer is still reading this rank's mailbox.
 inline int peer_destroy(PeerComm *c) {
     if (!c) return 0;
     cudaDeviceSynchronize();
+    for (int i = 0; i < 8; ++i) if (g_peer_comms[i] == c) g_peer_comms[i] = nullptr;
     for (int r = 0; r < c->world; ++r)
-        if (c->opened[r]) cudaIpcCloseMemHandle(c->table.p[r]);
+        if (c->opened[r]) cudaIpcCloseMemHandle(c->table[r]);
     if (c->mailbox) cudaFree(c->mailbox);
     delete c;
     return 0;

@@ -230,8 +230,14 @@ int som_b200_accum_finalize(uint64_t *acc_dev, const float *qinv_dev, int k, int
     int rc = device_info(di);
     if (rc) return rc;
     const AccTarget T = acc_target(acc_dev, nullptr, k, d);
-    return check_cuda(launch_pdl(accum_finalize_kernel, dim3(grid_for((int64_t)k * acc_ld(d), di.sm)), dim3(256), 0,
-                                 (cudaStream_t)stream, T.S, T.cnt, qinv_dev, k, d, acc_ld(d), s_dev, c_dev, 1),
+    // an accumulator handed out by som_b200_peer_accumulator: the sums run over all ranks (peer.cuh)
+    PeerComm *pc = peer_lookup(acc_dev);
+    SOM_REQUIRE(pc == nullptr || pc->words >= som_b200_accum_words(k, d), SOM_E_SHAPE, "accum_finalize: the peer accumulator is too small");
+    const PeerView V = pc ? peer_next_exchange(pc) : PeerView();
+    int grid = grid_for((int64_t)k * acc_ld(d) + k, di.sm);
+    if (pc && grid > di.sm) grid = di.sm;          // every block polls the flags: all of them co-resident
+    return check_cuda(launch_pdl(accum_finalize_kernel, dim3(grid), dim3(256), 0,
+                                 (cudaStream_t)stream, T.S, qinv_dev, k, d, acc_ld(d), s_dev, c_dev, 1, V),
                       "accum_finalize_kernel launch");
 }
 
@@ -458,7 +464,7 @@ int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, 
     A.sigma = sigma; A.dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
     A.S = s_dev; A.c = c_dev; A.num = num_dev; A.den = den_dev; A.W = w_dev;
     const AccTarget T = acc_target(acc_dev, nullptr, K, d);
-    A.Si = acc_dev ? T.S : nullptr; A.ci = acc_dev ? T.cnt : nullptr; A.qinv = qinv_dev; A.lds = acc_ld(d);
+    A.Si = acc_dev ? T.S : nullptr; A.qinv = qinv_dev; A.lds = acc_ld(d);
     A.k = K; A.d = d; A.dist_kind = dist_kind; A.k_pad = L.k_pad;
     A.aux = reinterpret_cast<float *>(ws + L.aux_off); A.bias = reinterpret_cast<float *>(ws + L.bias_off);
     A.amax = reinterpret_cast<float *>(ws + L.amax_off); A.gstat = reinterpret_cast<unsigned int *>(ws + L.gstat_off);
@@ -486,11 +492,16 @@ int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, 
     A.partials = ns.partials;
     A.b_per_slice = (int)round_up(ceil_div(K, slices), NB_K);
     A.slices = (int)ceil_div(K, A.b_per_slice);
+    PeerComm *pc = peer_lookup(acc_dev);
+    SOM_REQUIRE(pc == nullptr || pc->words >= som_b200_accum_words(K, d), SOM_E_SHAPE, "epoch_tail: the peer accumulator is too small");
+    const unsigned seq_before = pc ? pc->seq : 0u;
+    if (pc) A.peer = peer_next_exchange(pc);
     void *args[] = {&A};
     // cooperative launch: all CTAs co-resident or the launch fails -- the grid barriers cannot deadlock
     const cudaError_t e = cudaLaunchCooperativeKernel((const void *)epoch_tail_kernel<4, 4>, dim3(grid), dim3(NB_THREADS), args, 0, st);
     if (e == cudaErrorCooperativeLaunchTooLarge || e == cudaErrorNotSupported) {
         (void)cudaGetLastError();                   // the GPU is shared / partitioned: same work, separate launches
+        if (pc) pc->seq = seq_before;               // (the exchange was not launched)
         return separate_launches();
     }
     return check_cuda(e, "epoch_tail_kernel launch");
@@ -513,9 +524,9 @@ int som_b200_merge(float *w_dev, const float *num_dev, const float *den_dev, int
     return check_cuda(cudaGetLastError(), "merge_kernel launch");
 }
 
-int som_b200_peer_create(int64_t max_floats, int world, int rank, void **comm_out, void *handle_out_64_bytes) {
+int som_b200_peer_create(size_t acc_words, int world, int rank, void **comm_out, void *handle_out_64_bytes) {
     PeerComm *c = nullptr;
-    const int rc = peer_create(max_floats, world, rank, &c, handle_out_64_bytes);
+    const int rc = peer_create(acc_words, world, rank, &c, handle_out_64_bytes);
     if (rc == 0) *comm_out = c;
     return rc;
 }
@@ -524,8 +535,10 @@ int som_b200_peer_connect(void *comm, const void *all_handles) {
     return peer_connect(static_cast<PeerComm *>(comm), all_handles);
 }
 
-int som_b200_peer_allreduce(void *comm, float *data_dev, int64_t floats, void *stream) {
-    return peer_allreduce(static_cast<PeerComm *>(comm), data_dev, floats, (cudaStream_t)stream);
+uint64_t *som_b200_peer_accumulator(void *comm) {
+    PeerComm *c = static_cast<PeerComm *>(comm);
+    if (!c || !c->connected) return nullptr;
+    return reinterpret_cast<uint64_t *>(c->acc(c->next_par()));
 }
 
 int som_b200_peer_destroy(void *comm) { return peer_destroy(static_cast<PeerComm *>(comm)); }

@@ -38,7 +38,9 @@ class CudaEngine:
 
     @staticmethod
     def _p(t):
-        return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+        if t is None or isinstance(t, ctypes.c_void_p):        # (a raw device address: peer accumulators)
+            return t
+        return ctypes.c_void_p(t.data_ptr())
 
     def empty(self, *shape, dtype=torch.float32):
         return torch.empty(*shape, dtype=dtype, device=self.device)

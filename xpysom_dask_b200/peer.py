@@ -1,16 +1,12 @@
-"""One-shot all-reduce of the per-epoch ``[S | c]`` partials over NVLink peer memory.
+"""Exact accumulators in NVLink peer memory: the sharded path's one exchange step, fused into the epoch tail.
 
-The sharded path has exactly one exchange step per epoch: the sum of the per-rank partial updates (the
-reference does it with a Dask ``sum`` over its per-block ``_update`` results, xpysom.py:574-583).  For the
-small buffers of most maps (config 2: 0.26 MB) an NCCL all-reduce is pure latency, so on a single node
-the ranks open each other's mailboxes through CUDA IPC once (handles travel through the process group)
-and ``libsom_b200``'s ``som_b200_peer_allreduce`` does the sum in one kernel on the compute stream.
-Large buffers, several nodes, CUDA-graph replay or any set-up failure on ANY rank: NCCL is used instead
-(the decision is agreed on by an all-reduce, so the ranks never disagree).
-
-Measured (tools/peer_check.py, B200, back-to-back calls): 2 GPUs 16 us vs NCCL 20 us at 0.27 MB; 8 GPUs 40 us vs
-NCCL 28 us (NVLS reduces inside the switch; this kernel reads seven remote mailboxes one after the other).  NCCL
-therefore stays the default and this path is opt-in (``SOM_B200_PEER=1``).
+The sharded path has exactly one exchange step per epoch: the sum of the per-rank accumulators (the reference does
+it with a Dask ``sum`` over its per-block ``_update`` results, xpysom.py:545-558).  For the small buffers of most
+maps (config 2: 0.5 MB) an NCCL all-reduce is pure latency and a stream hand-over in the middle of the epoch's launch
+chain, so on a single node the ranks open each other's accumulators through CUDA IPC once (handles travel through the
+process group) and the finalize phase of ``som_b200_epoch_tail`` sums them over the ranks itself (csrc/peer.cuh).
+Large buffers, several nodes, CUDA-graph replay or any set-up failure on ANY rank: NCCL all-reduces the integer
+accumulator instead (the decision is agreed on by an all-reduce, so the ranks never disagree).
 """
 import ctypes
 import socket
@@ -20,27 +16,27 @@ import torch
 
 from . import _lib
 
-# above this size the 'every rank reads every mailbox' pattern loses to NCCL's ring / NVLS all-reduce (measured on
-# 2 B200s: 16 us vs 20 us at 0.27 MB, 50 us vs 37 us at 4 MB): config 4's 31 MB buffer stays on NCCL
-ONE_SHOT_MAX_BYTES = 1 << 20
+# above this size the 'every rank reads every accumulator' pattern loses to NCCL's ring / NVLS all-reduce
+# (world - 1 remote reads of the whole buffer per rank): config 4's 63 MB accumulator stays on NCCL
+PEER_MAX_BYTES = 4 << 20
 
 
-class PeerReducer:
-    """In-place sum of a device fp32 buffer across the ranks of ``group`` (all on one node)."""
+class PeerAccumulator:
+    """Accumulators of ``words`` 64-bit words on every rank of ``group`` (all on one node), readable by all of them."""
 
-    def __init__(self, eng, group, floats):
+    def __init__(self, eng, group, words):
         import torch.distributed as dist
-        self.eng, self.group, self.floats = eng, group, int(floats)
+        self.eng, self.group, self.words = eng, group, int(words)
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         self.comm = None
         ok = 1
         handle = (ctypes.c_uint8 * 64)()
         comm = ctypes.c_void_p()
         try:
-            if self.world > 16:
-                raise _lib.SomB200Error("peer all-reduce disabled")
+            if self.world > 16 or self.world < 2:
+                raise _lib.SomB200Error("peer accumulators disabled")
             with torch.cuda.device(eng.device):
-                _lib.check(eng.lib.som_b200_peer_create(self.floats, self.world, self.rank, ctypes.byref(comm),
+                _lib.check(eng.lib.som_b200_peer_create(self.words, self.world, self.rank, ctypes.byref(comm),
                                                         ctypes.cast(handle, ctypes.c_void_p)), "som_b200_peer_create")
         except _lib.SomB200Error:
             ok = 0
@@ -70,21 +66,34 @@ class PeerReducer:
     def active(self):
         return self.comm is not None
 
-    def all_reduce_(self, t):
-        assert t.dtype == torch.float32 and t.is_contiguous() and t.numel() <= self.floats
-        eng = self.eng
-        with torch.cuda.device(eng.device):
-            _lib.check(eng.lib.som_b200_peer_allreduce(self.comm, ctypes.c_void_p(t.data_ptr()), t.numel(),
-                                                       eng._stream()), "som_b200_peer_allreduce")
-        eng.launches += 1
+    def current(self):
+        """Device address of the accumulator of the NEXT epoch (alternates: ask every epoch)."""
+        p = self.eng.lib.som_b200_peer_accumulator(self.comm)
+        if not p:
+            raise _lib.SomB200Error("som_b200_peer_accumulator: communicator not connected")
+        return ctypes.c_void_p(p)
+
+    def fence(self):
+        """Every rank has finished reading every accumulator (call before the ranks may diverge: end of train())."""
+        import torch.distributed as dist
+        t = torch.zeros(1, dtype=torch.int32, device=self.eng.device)
+        dist.all_reduce(t, group=self.group)
 
     def close(self):
+        """Collective: all ranks close together (no peer may still be inside an exchange)."""
         if self.comm is not None:
-            self.eng.lib.som_b200_peer_destroy(self.comm)
-            self.comm = None
+            try:
+                self.fence()
+                torch.cuda.synchronize(self.eng.device)
+            finally:
+                self.eng.lib.som_b200_peer_destroy(self.comm)
+                self.comm = None
 
     def __del__(self):
+        # every train() call ends with fence(): nobody is inside an exchange when the object is collected
         try:
-            self.close()
+            if self.comm is not None:
+                self.eng.lib.som_b200_peer_destroy(self.comm)
+                self.comm = None
         except Exception:
             pass

@@ -22,6 +22,7 @@ callers may assign to between calls, exactly as with the reference
 from collections import Counter, defaultdict
 from warnings import warn
 
+import os
 import weakref
 
 import numpy as np
@@ -169,6 +170,23 @@ class XPySom:
         # a pickled sharded model comes back attached to the default group (group handles do not pickle)
         return dist.group.WORLD if (pg is True or pg == _UNPICKLED_SHARDED) else pg
 
+    def _peer_accumulator(self, eng, group, words):
+        """The cached peer-memory accumulators of a sharded model (peer.py), or None when NCCL should all-reduce.
+        Collective: every rank takes the same decision (same sizes, and the set-up itself agrees by all-reduce)."""
+        from . import peer
+        import torch.distributed as dist
+        if (words * 8 > peer.PEER_MAX_BYTES or dist.get_world_size(group) < 2 or getattr(eng, 'name', '') != 'cuda'
+                or os.environ.get('SOM_B200_PEER', '1') == '0'):
+            return None
+        key = (id(group), words, str(eng.device))
+        cached = getattr(self, '_peer_cache', None)
+        if cached is None or cached[0] != key:
+            if cached is not None:
+                cached[1].close()
+            cached = (key, peer.PeerAccumulator(eng, group, words))
+            self._peer_cache = cached
+        return cached[1] if cached[1].active else None
+
     def _shape(self):
         gx, gy, d = self._weights.shape
         return gx, gy, d
@@ -257,12 +275,19 @@ class XPySom:
                              if cache_key is not None else None)
         return stats
 
-    def _device_budget(self, eng):
-        """Bytes of samples this process may keep resident (the rest of the job streams through two block buffers)."""
+    def _device_budget(self, eng, nbytes=None):
+        """Bytes of samples this process may keep resident (the rest of the job streams through two block buffers).
+        With ``nbytes`` given the answer only has to be right about ``nbytes <= budget``: a matrix below 1/8 of what
+        torch has not reserved of the device's memory is accepted without asking the driver (cudaMemGetInfo takes a
+        driver-wide lock: 0.1 - 1 ms per train() call when something else is polling the GPU)."""
         if self._max_resident_bytes is not None:
             return int(self._max_resident_bytes)
         if getattr(eng, 'name', '') != 'cuda':
             return 1 << 62
+        if nbytes is not None:
+            total = torch.cuda.get_device_properties(eng.device).total_memory
+            if nbytes * 8 <= total - torch.cuda.memory_reserved(eng.device):
+                return int(nbytes)
         free, _ = torch.cuda.mem_get_info(eng.device)
         return int(free * 0.8)
 
@@ -291,7 +316,6 @@ class XPySom:
         group = self._group()
         want_scale = self._wants_xscale(dist_kind)
 
-        w = self._weights_to_device(eng)
         n_ep = iter_end - iter_beg
         prof = self._profile_events if getattr(self, '_profile', False) else None
         graphed = self._use_cuda_graph and prof is None and not verbose and n_ep >= 3 and cuda
@@ -302,11 +326,13 @@ class XPySom:
         on_host = host.device.type == 'cpu' and cuda
         mode = 'resident'
         if on_host and n_ep >= 1 and n > 0:
-            if host.numel() * 4 > self._device_budget(eng):
+            if host.numel() * 4 > self._device_budget(eng, host.numel() * 4):
                 mode = 'stream'
             elif not graphed and host.numel() * 4 >= (32 << 20):
                 mode = 'chunked'
+        uploaded = self._upload_in_chunks(eng, host) if mode == 'chunked' else None     # the copies start first
 
+        w = self._weights_to_device(eng)
         acc = eng.accumulator(K, d)          # exact [S | counts], 64-bit fixed point (cleared by every epoch tail)
         sc = eng.empty(K * d + K)            # fp32 [S | c] the neighbourhood apply reads
         nd = eng.empty(K * d + K)            # [num | den]
@@ -329,7 +355,7 @@ class XPySom:
 
         def tail(t, from_acc, qinv):
             sig, eta = schedule(t)
-            eng.epoch_tail(acc if from_acc else None, qinv, S, c, w, gx, gy, d, topo, neigh, sig, eta, self._std_coeff,
+            eng.epoch_tail(from_acc, qinv, S, c, w, gx, gy, d, topo, neigh, sig, eta, self._std_coeff,
                            self.compact_support, dist_kind, p, num, den, tables, ws)
             if verbose:
                 print('\r [ %d / %d ]' % (t + 1, num_epochs), end='')
@@ -339,7 +365,7 @@ class XPySom:
                                  iter_beg, iter_end, K, d)
         else:
             if mode == 'chunked':
-                x, chunks = self._upload_in_chunks(eng, host)
+                x, chunks = uploaded
             else:
                 x, chunks = self._data_to_device(eng, host), None
             bmu = eng.empty(n, dtype=torch.int32)
@@ -363,7 +389,7 @@ class XPySom:
                     torch.maximum(colmax, cm_c, out=colmax)
                 all_reduce(sd)
                 eng.accum_finalize_f64(sd, K, d, S, c)
-                tail(first, False, None)
+                tail(first, None, None)
                 first += 1
                 n_total = n
                 if group is not None:
@@ -404,19 +430,26 @@ class XPySom:
                     graph.replay()
                 eng.launches = launches0 + per_epoch * n_ep    # kernels actually executed (capture launches none)
             else:
-                # epoch = BMU search + exact per-BMU sums (one fused kernel) -> integer all-reduce of the shards ->
-                # everything else (eng.epoch_tail: finalize, apply, merge, preparation of the new codebook)
+                # epoch = BMU search + exact per-BMU sums (one fused kernel) -> sum of the shards' integer accumulators
+                # -> everything else (eng.epoch_tail: finalize, apply, merge, preparation of the new codebook).
+                # The sum over the shards: on one node and small maps the accumulators live in NVLink peer memory and
+                # the tail's finalize phase reads all of them itself (peer.py); otherwise NCCL all-reduces the integers.
+                pacc = self._peer_accumulator(eng, group, acc.numel()) if (group is not None and first < iter_end) else None
                 for t in range(first, iter_end):
+                    a = pacc.current() if pacc is not None else acc
                     if prof is not None:
                         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                         ev[0].record()
-                    if n > 0:               # a rank may hold an EMPTY shard: it still joins the all-reduce and the tail
-                        eng.epoch_accumulate(x, w, dist_kind, p, algo, qscale, acc, ws, bmu_out=bmu, xscale=xscale)
+                    if n > 0:               # a rank may hold an EMPTY shard: it still joins the exchange and the tail
+                        eng.epoch_accumulate(x, w, dist_kind, p, algo, qscale, a, ws, bmu_out=bmu, xscale=xscale)
                     if prof is not None:
                         ev[1].record()
                         prof.append(ev)
-                    all_reduce(acc)
-                    tail(t, True, qinv)
+                    if pacc is None:
+                        all_reduce(acc)
+                    tail(t, a, qinv)
+                if pacc is not None:
+                    pacc.fence()            # nobody is still reading this rank's accumulators when train() returns
 
         self._weights = w.cpu().numpy().reshape(gx, gy, d)      # synchronises; fp32 like xpysom.py:580-583
         if verbose:
@@ -490,7 +523,7 @@ class XPySom:
                     freed[j] = ev
                 all_reduce(sd)
                 eng.accum_finalize_f64(sd, K, d, S, c)
-                tail(t, False, None)
+                tail(t, None, None)
             torch.cuda.current_stream(eng.device).synchronize()
         finally:
             if registered:
@@ -665,6 +698,7 @@ class XPySom:
         state['_engine'] = None            # device handles are rebuilt on demand
         state['_process_group'] = None if self._process_group in (None, False) else _UNPICKLED_SHARDED
         state.pop('_stats_cache', None)
+        state.pop('_peer_cache', None)
         state['_profile_events'] = []
         state['xp'] = None
         return state
