@@ -30,8 +30,10 @@
  *     associative, so the sums do not depend on the order of the GPU's atomics, on tiling, or on how the
  *     samples are sharded over GPUs (an integer all-reduce of the accumulator gives every rank the bits one
  *     GPU would have computed).  The accumulator is `som_b200_accum_words(k, d)` uint64 words:
- *     [S: k rows of (d rounded up to even) words | counts: k words], 16-byte aligned, zero before the first
- *     accumulate of an epoch.  som_b200_accum_finalize / som_b200_epoch_tail round it ONCE to the fp32
+ *     `som_b200_accum_replicas(k, d)` copies (4 for accumulators of up to 4 MB, else 1; each copy padded to an even
+ *     number of words) of [S: k rows of (d rounded up to even) words | counts: k words], 16-byte aligned, zero before
+ *     the first accumulate of an epoch.  The kernels spread their thread blocks over the copies -- samples that share
+ *     a BMU would otherwise serialise on the same L2 lines -- and the finalize sums them (integers: same bits).  som_b200_accum_finalize / som_b200_epoch_tail round it ONCE to the fp32
  *     S, c that the neighbourhood apply reads, and clear it.
  */
 #ifndef SOM_B200_H
@@ -110,6 +112,7 @@ int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, 
  * all shards) cannot overflow 63 bits.  Every shard of one job must use the same scales. */
 int    som_b200_accum_scales(const float *colmax_dev, int d, double n_total, float *qscale_dev, float *qinv_dev, void *stream);
 size_t som_b200_accum_words(int k, int d);
+int    som_b200_accum_replicas(int k, int d);
 
 /* Exact accumulator -> fp32 S (k, d) and c (k), one rounding per element; the accumulator is cleared. */
 int som_b200_accum_finalize(uint64_t *acc_dev, const float *qinv_dev, int k, int d, float *s_dev, float *c_dev, void *stream);

@@ -49,6 +49,8 @@ for n, d, K, dist in shapes:
     eng.epoch_accumulate(x, w, _lib.DIST[dist], 2.0, _lib.ALGO["auto"], qs, acc, ws, bmu_out=bmu, xscale=xs)
     e1.record()
     torch.cuda.synchronize()
-    cnt = acc[K * ((d + 1) // 2 * 2):].sum().item()
+    S_, c_ = eng.empty(K, d), eng.empty(K)
+    eng.accum_finalize(acc, qi, K, d, S_, c_)             # (sums the accumulator's replicas)
+    cnt = int(c_.sum(dtype=torch.float64).item())
     print("   fused auto: %.3f ms, counts sum %d (n=%d), bmu mismatch vs simt %.2e" %
           (e0.elapsed_time(e1), cnt, n, (bmu != ref).float().mean().item()), flush=True)

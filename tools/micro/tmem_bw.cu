@@ -26,7 +26,7 @@ __device__ __forceinline__ void wait_dep(uint32_t (&v)[32]) {
 // mode 0: loads only (xor-reduce so they are not dead); 1: + bias(smem) + 8-way running argmin;
 // 2: argmin without bias; 3: value-only min (no index)
 template <int MODE>
-__global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc, float *sink) {
+__global__ void __launch_bounds__(512, 1) k(int warps, int tiles, long long *cyc, float *sink) {
     __shared__ uint32_t slot;
     __shared__ __align__(16) float bias[256];
     const int warp = threadIdx.x >> 5;
@@ -46,8 +46,8 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
     long long t0 = 0, t1 = 0;
     if (warp < warps) {
         const int q = warp & 3, h = warp >> 2;
-        const int ncols = warps == 8 ? 128 : 256;
-        const uint32_t taddr = base + ((uint32_t)(q * 32) << 16) + (warps == 8 ? h * 128 : 0);
+        const int ncols = 256 / (warps / 4);
+        const uint32_t taddr = base + ((uint32_t)(q * 32) << 16) + h * ncols;
         t0 = clock64();
         for (int t = 0; t < tiles; ++t) {
             if (MODE == 6) {
@@ -62,7 +62,7 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
                     uint32_t v[32];
                     tmem_ld32(taddr + c * 32, v);
                     wait_dep(v);
-                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * 128 + c * 32) % 256);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * ncols + c * 32) % 256);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         const float4 b = b4[j4];
@@ -95,7 +95,7 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
                     // written by predicated FMA-pipe instructions
                     float *fi = reinterpret_cast<float *>(bi);
                     const float basef = (float)(t * 256 + c * 32);
-                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * 128 + c * 32) % 256);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * ncols + c * 32) % 256);
                     float one; asm volatile("mov.f32 %0, 0f3f800000;" : "=f"(one));
 #pragma unroll
                     for (int j = 0; j < 32; ++j) {
@@ -112,10 +112,43 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
                             asm("{\n .reg .pred p;\n setp.lt.f32 p, %2, %0;\n @p add.f32 %1, %3, %4;\n @p add.f32 %0, %2, 0f80000000;\n}"
                                 : "+f"(bv[j & 3]), "+f"(fi[j & 3]) : "f"(sc), "f"(basef), "f"(jf));
                     }
+                } else if (MODE == 13) {
+                    // non-negative scores compared as unsigned bits: ONE min-with-predicate (DPX) + one predicated index write
+                    uint32_t *kv = reinterpret_cast<uint32_t *>(bv);
+                    float *fi = reinterpret_cast<float *>(bi);
+                    const float basef = (float)(t * 256 + c * 32);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        bool keep;
+                        kv[j & 3] = __vibmin_u32(kv[j & 3], v[j], &keep);
+                        const float jf = (float)j;
+                        asm("{\n .reg .pred p;\n setp.eq.u32 p, %1, 0;\n @p add.f32 %0, %2, %3;\n}" : "+f"(fi[j & 3]) : "r"((uint32_t)keep), "f"(basef), "f"(jf));
+                    }
+                } else if (MODE == 11 || MODE == 12) {
+                    // group minimum first (3-input min: 2 ops per 4 scores, 4 per 8), then ONE compare and two predicated
+                    // FMA-pipe updates per group; the column inside the winning group is resolved after the sweep
+                    float *fi = reinterpret_cast<float *>(bi);
+                    const float basef = (float)(t * 256 + c * 32);
+                    constexpr int G = MODE == 11 ? 4 : 8;
+#pragma unroll
+                    for (int g = 0; g < 32 / G; ++g) {
+                        float m;
+                        asm("min.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(__uint_as_float(v[g * G])), "f"(__uint_as_float(v[g * G + 1])), "f"(__uint_as_float(v[g * G + 2])));
+                        if (G == 4) {
+                            m = fminf(m, __uint_as_float(v[g * G + 3]));
+                        } else {
+                            asm("min.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(__uint_as_float(v[g * G + 3])), "f"(__uint_as_float(v[g * G + 4])));
+                            asm("min.f32 %0, %0, %1, %2;" : "+f"(m) : "f"(__uint_as_float(v[g * G + 5])), "f"(__uint_as_float(v[g * G + 6])));
+                            m = fminf(m, __uint_as_float(v[g * G + 7]));
+                        }
+                        const float gf = (float)(g * G);
+                        asm("{\n .reg .pred p;\n setp.lt.f32 p, %2, %0;\n @p add.f32 %1, %3, %4;\n @p add.f32 %0, %2, 0f80000000;\n}"
+                            : "+f"(bv[g & 3]), "+f"(fi[g & 3]) : "f"(m), "f"(basef), "f"(gf));
+                    }
                 } else if (MODE == 4 || MODE == 5) {
                     // scaled score (2 FMA-pipe ops) made non-negative, compared as unsigned bits with the
                     // DPX min-with-predicate: 1 ALU op for the value + 1 for the index
-                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * 128 + c * 32) % 256);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * ncols + c * 32) % 256);
                     const float rs = 1.5f + threadIdx.x * 1e-3f, crow = 100.f;
                     uint32_t *kv = reinterpret_cast<uint32_t *>(bv);
 #pragma unroll
@@ -149,7 +182,7 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
                         }
                     }
                 } else {
-                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * 128 + c * 32) % 256);
+                    const float4 *b4 = reinterpret_cast<const float4 *>(bias + (h * ncols + c * 32) % 256);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         float4 b = MODE == 1 ? b4[j4] : make_float4(0, 0, 0, 0);
@@ -170,7 +203,7 @@ __global__ void __launch_bounds__(256, 1) k(int warps, int tiles, long long *cyc
 #pragma unroll
     for (int a = 0; a < 8; ++a) { s += bv[a]; si += bi[a] * 256 + li[a]; }
     if (sink && (x == 0x12345678 || s == 1.2345f)) sink[threadIdx.x] = s + si;
-    if (threadIdx.x % 32 == 0 && warp < warps) cyc[blockIdx.x * 8 + warp] = t1 - t0;
+    if (threadIdx.x % 32 == 0 && warp < warps) cyc[blockIdx.x * 16 + warp] = t1 - t0;
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(base), "r"(512));
@@ -296,21 +329,30 @@ void runc(const char *name, int nmma, int epi_on) {
 template <int MODE>
 void run(const char *name, int warps) {
     long long *cyc; float *sink;
-    cudaMalloc(&cyc, 148 * 8 * 8); cudaMalloc(&sink, 4096);
+    cudaMalloc(&cyc, 148 * 16 * 8); cudaMalloc(&sink, 4096);
     const int tiles = 200;
-    k<MODE><<<148, 256>>>(warps, tiles, cyc, sink);
-    k<MODE><<<148, 256>>>(warps, tiles, cyc, sink);
+    k<MODE><<<148, 512>>>(warps, tiles, cyc, sink);
+    k<MODE><<<148, 512>>>(warps, tiles, cyc, sink);
     cudaError_t e = cudaDeviceSynchronize();
-    long long h[148 * 8];
+    static long long h[148 * 16];
     cudaMemcpy(h, cyc, sizeof(h), cudaMemcpyDeviceToHost);
     long long mx = 0;
-    for (int b = 0; b < 148; ++b) for (int w = 0; w < warps; ++w) mx = h[b * 8 + w] > mx ? h[b * 8 + w] : mx;
+    for (int b = 0; b < 148; ++b) for (int w = 0; w < warps; ++w) mx = h[b * 16 + w] > mx ? h[b * 16 + w] : mx;
     printf("%-28s warps=%d: %7.1f cycles per 128x256 tile  (%.1f B/clk/SM, %.2f elem/clk/SM)  [%s]\n", name, warps,
            (double)mx / tiles, 131072.0 * tiles / mx, 32768.0 * tiles / mx, cudaGetErrorString(e));
     cudaFree(cyc); cudaFree(sink);
 }
 
 int main() {
+    run<0>("LDTM only", 8);
+    run<3>("LDTM + value-only min", 8);
+    run<9>("setp+@fadd.val+@fadd.idx", 8);
+    run<9>("setp+@fadd.val+@fadd.idx", 4);
+    run<9>("setp+@fadd.val+@fadd.idx", 16);
+    run<0>("LDTM only", 16);
+    run<11>("min3 groups of 4 + setp + 2 @fadd", 8);
+    run<12>("min3 groups of 8 + setp + 2 @fadd", 8);
+    return 0;
     runc<0>("epilogue alone", 0, 1);
     runc<0>("tf32 MMAs alone", 7, 0);
     runc<0>("tf32 MMAs alone", 12, 0);

@@ -30,6 +30,7 @@ SIGNATURES = {
                                                 ctypes.c_void_p]),
     "som_b200_accum_scales": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_double, c_f32p, c_f32p, ctypes.c_void_p]),
     "som_b200_accum_words": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
+    "som_b200_accum_replicas": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
     "som_b200_accum_finalize": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p,
                                                ctypes.c_void_p]),
     "som_b200_accum_fold": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,

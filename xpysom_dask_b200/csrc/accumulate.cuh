@@ -43,7 +43,8 @@ __global__ void accum_scales_kernel(const float *__restrict__ colmax, int d, int
 }
 
 __global__ void __launch_bounds__(ACC_THREADS)
-accumulate_kernel(ExactAcc A, const int32_t *__restrict__ bmu, int64_t n, int64_t rows_per_cta) {
+accumulate_kernel(const ExactAcc A0, const int32_t *__restrict__ bmu, int64_t n, int64_t rows_per_cta) {
+    const ExactAcc A = A0.for_cta(blockIdx.x);
     __shared__ __align__(128) long long stage[4][ACC_NBUF][ACC_PIECE];
     __shared__ int bm[128];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -65,6 +66,7 @@ inline int launch_accumulate(const float *X, int64_t n, int d, int64_t ldx, cons
     if (n <= 0) return 0;
     ExactAcc A;
     A.X = X; A.ldx = ldx; A.d = d; A.k = k; A.qscale = T.qscale; A.S = T.S; A.cnt = T.cnt; A.lds = acc_ld(d); A.dbg = 0;
+    A.reps = T.reps; A.rep_words = T.rep_words;
     A.vec = ((d % 4 == 0) && (ldx % 4 == 0) && ((reinterpret_cast<uintptr_t>(X) & 15) == 0)) ? 1 : 0;
     // a multiple of the SM count; each CTA takes a contiguous slab of whole 128-row tiles so its loads are sequential
     int64_t ctas = (int64_t)sm_count * 8;
@@ -77,29 +79,32 @@ inline int launch_accumulate(const float *X, int64_t n, int d, int64_t ldx, cons
 // int64 sums -> the fp32 S (K, D) and c (K) the neighbourhood apply reads (peer.cuh: accum_finalize_elements); the
 // integers are cleared for the next epoch when `clear` is set.  With a PeerView the sums run over the accumulators of
 // all ranks (the sharded path's exchange step, fused in here).
-__global__ void accum_finalize_kernel(unsigned long long *__restrict__ Si, const float *__restrict__ qinv, int k, int d,
-                                      int lds, float *__restrict__ S, float *__restrict__ c, int clear, const PeerView V) {
+__global__ void accum_finalize_kernel(unsigned long long *__restrict__ Si, int reps, size_t rep_words,
+                                      const float *__restrict__ qinv, int k, int d, int lds, float *__restrict__ S,
+                                      float *__restrict__ c, int clear, const PeerView V) {
     pdl_wait(); pdl_trigger();
-    accum_finalize_elements(Si, qinv, k, d, lds, S, c, clear, V, (int64_t)blockIdx.x * blockDim.x + threadIdx.x,
-                            (int64_t)gridDim.x * blockDim.x);
+    accum_finalize_elements(Si, reps, rep_words, qinv, k, d, lds, S, c, clear, V,
+                            (int64_t)blockIdx.x * blockDim.x + threadIdx.x, (int64_t)gridDim.x * blockDim.x);
 }
 
 // one part of a multi-part epoch (its own column scales): Sd += double(S_int) * 2^-q, cd += count; integers cleared
-__global__ void accum_fold_kernel(unsigned long long *__restrict__ Si, unsigned long long *__restrict__ ci,
-                                  const float *__restrict__ qinv, int k, int d, int lds, double *__restrict__ Sd,
-                                  double *__restrict__ cd) {
-    const int64_t tot = (int64_t)k * lds;
-    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < tot; e += (int64_t)gridDim.x * blockDim.x) {
-        const int row = (int)(e / lds), col = (int)(e % lds);
-        const long long v = (long long)Si[e];
-        if (v) {
-            if (col < d) Sd[(int64_t)row * d + col] += (double)v * (double)qinv[col];
-            Si[e] = 0ull;
+__global__ void accum_fold_kernel(unsigned long long *__restrict__ Si, int reps, size_t rep_words, const float *__restrict__ qinv,
+                                  int k, int d, int lds, double *__restrict__ Sd, double *__restrict__ cd) {
+    const int64_t tot = (int64_t)k * lds, all = tot + k;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < all; e += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long u = 0ull;
+        for (int r = 0; r < reps; ++r) {
+            const unsigned long long w = Si[(size_t)r * rep_words + e];
+            u += w;
+            if (w) Si[(size_t)r * rep_words + e] = 0ull;
         }
-    }
-    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < k; e += gridDim.x * blockDim.x) {
-        const unsigned long long v = ci[e];
-        if (v) { cd[e] += (double)v; ci[e] = 0ull; }
+        if (!u) continue;
+        if (e < tot) {
+            const int row = (int)(e / lds), col = (int)(e % lds);
+            if (col < d) Sd[(int64_t)row * d + col] += (double)(long long)u * (double)qinv[col];
+        } else {
+            cd[e - tot] += (double)u;
+        }
     }
 }
 

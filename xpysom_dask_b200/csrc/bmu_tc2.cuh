@@ -369,11 +369,12 @@ bmu_tc2_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int wq = warp - SCAT_WARP0;
             long long *stage = reinterpret_cast<long long *>(scat_stage) + wq * (tc::SCAT_NBUF * ACC_PIECE);
             uint32_t tile_it = 0, bulk_it = 0;
+            const FusedAcc racc = acc.for_cta(blockIdx.x >> 1);          // this pair's replica of the accumulator
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
                 const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                 tc::mbar_wait_relaxed(bfullq_bar(b), bph, 400);
                 const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
-                scatter_rows_exact<tc::SCAT_NBUF>(acc, bmu_s + b * BM, row0, BM, wq, 4, lane, stage, bulk_it);
+                scatter_rows_exact<tc::SCAT_NBUF>(racc, bmu_s + b * BM, row0, BM, wq, 4, lane, stage, bulk_it);
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
             }
@@ -413,6 +414,7 @@ inline int launch_bmu_tc2(const float *X, int64_t n, int d, int64_t ldx, int k, 
     FusedAcc acc;
     acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = T.S; acc.cnt = T.cnt; acc.qscale = T.qscale;
     acc.lds = acc_ld(d);
+    acc.reps = T.reps; acc.rep_words = T.rep_words;
     acc.vec = (d % 4 == 0) ? 1 : 0;              // X rows are 16-byte aligned here (tc::shape_ok)
     static const int dbg = tc::env_int("SOM_B200_DBG");
     acc.dbg = dbg;

@@ -521,10 +521,18 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     }
                 };
                 // (measured in round 2: a second tcgen05.ld buffer in flight, 64-column loads and 8 instead of 4 running
-                // minima all made this loop SLOWER or no faster -- the drain of a 128 x 256 tile takes ~1400 cycles, which
-                // is the TMEM read rate (~90 bytes per clock and SM), not instruction issue or dependency latency)
+                // minima all made this loop SLOWER or no faster.  The drain of a 128 x 256 tile takes ~1400 cycles here;
+                // tools/micro/tmem_bw.cu in isolation: 450 - 530 for the TMEM reads alone, 1106 with the compare and the two
+                // predicated writes per score on 8 warps, 951 on 16: instruction issue, with 2 warps per scheduler.)
+                // Chunks that hold only padding neurons (the last tile of a map whose size is not a multiple of 256) are
+                // skipped: their scores are +inf.  40 x 40 neurons: 6.25 instead of 7 tiles to drain per row tile.
+                int nch = ncols / 32;
+                {
+                    const int left = acc.k - col0;
+                    nch = left <= 0 ? 0 : (left + 31) >> 5 < nch ? (left + 31) >> 5 : nch;
+                }
 #pragma unroll 1
-                for (int c = 0; c < ncols / 32; ++c) {
+                for (int c = 0; c < nch; ++c) {
                     uint32_t v[32];
                     tc::tmem_ld32(taddr + c * 32, v);
                     tc::tmem_ld_wait_dep(v);
@@ -564,11 +572,12 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
             const int wq = warp - SCAT_WARP0;
             long long *stage = reinterpret_cast<long long *>(scat_stage) + wq * (tc::SCAT_NBUF * ACC_PIECE);
             uint32_t tile_it = 0, bulk_it = 0;
+            const FusedAcc racc = acc.for_cta(blockIdx.x >> 1);          // this pair's replica of the accumulator
             for (int pt = pair; pt < num_pair_tiles; pt += num_pairs, ++tile_it) {
                 const int b = tile_it & 1; const uint32_t bph = (tile_it >> 1) & 1;
                 tc::mbar_wait_relaxed(bfullq_bar(b), bph, 400);
                 const int64_t row0 = (int64_t)pt * (2 * BM) + (int64_t)rank * BM;
-                scatter_rows_exact<tc::SCAT_NBUF>(acc, bmu_s + b * BM, row0, BM, wq, 4, lane, stage, bulk_it);
+                scatter_rows_exact<tc::SCAT_NBUF>(racc, bmu_s + b * BM, row0, BM, wq, 4, lane, stage, bulk_it);
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(bemptyq_bar(b));
             }
@@ -631,6 +640,7 @@ inline int launch_bmu_tc3(const float *X, int64_t n, int d, int64_t ldx, const f
     FusedAcc acc;
     acc.X = X; acc.ldx = ldx; acc.d = d; acc.k = k; acc.S = T.S; acc.cnt = T.cnt; acc.qscale = T.qscale;
     acc.lds = acc_ld(d);
+    acc.reps = T.reps; acc.rep_words = T.rep_words;
     acc.vec = (d % 4 == 0) ? 1 : 0;              // X rows are 16-byte aligned here (tc::shape_ok)
     static const int dbg = tc::env_int("SOM_B200_DBG");
     acc.dbg = dbg;

@@ -134,6 +134,14 @@ struct ExactAcc {
     int lds;
     int vec;                        // rows of X are 16-byte aligned and d % 4 == 0: 128-bit loads
     int dbg;                        // experiments builds only (timeline probes); 0 in production
+    int reps;                       // replicas of [S | cnt], rep_words apart: CTA i adds into replica i % reps (see acc_replicas)
+    size_t rep_words;
+    // this CTA's replica
+    __device__ __forceinline__ ExactAcc for_cta(unsigned cta) const {
+        ExactAcc a = *this;
+        if (reps > 1 && S != nullptr) { const size_t off = (size_t)(cta % (unsigned)reps) * rep_words; a.S += off; a.cnt += off; }
+        return a;
+    }
 };
 #ifdef SOM_B200_EXPERIMENTS
 __device__ long long g_scat_dbg[8 * 64];
@@ -146,7 +154,17 @@ __device__ long long g_scat_dbg[8 * 64];
 struct AccTarget {
     unsigned long long *S = nullptr, *cnt = nullptr;
     const float *qscale = nullptr;
+    int reps = 1;
+    size_t rep_words = 0;
 };
+
+// Replicas of a small accumulator.  Samples that share a BMU add into the same rows of S, and reductions on one L2 line
+// serialise: with most rows on a few "hot" neurons (blob data on a young map) the bulk reductions ran at half their
+// rate (tools/micro/red_bw.cu, 90 % of the rows on 16 neurons: 0.352 ms against 0.242 ms at config 2; with 4 replicas
+// 0.242 ms again).  So accumulators of up to 4 MB are kept 4 times, CTAs spread over the copies, and the finalize
+// phase sums them -- integer sums, so the result is the same bits whatever the number of replicas.
+__host__ __device__ inline size_t acc_words_one(int k, int d) { return ((size_t)k * acc_ld(d) + (size_t)k + 1) & ~(size_t)1; }   // 16-byte replicas
+__host__ inline int acc_replicas(int k, int d) { return acc_words_one(k, d) * 8 <= ((size_t)4 << 20) ? 4 : 1; }
 
 // One warp scatters rows of a tile whose BMUs sit in shared memory (bm[r] < 0: no such row).  The warp takes the
 // rows r = first, first + stride, ... below `rows`; `stage` is THIS warp's staging area of NBUF * ACC_PIECE int64

@@ -31,6 +31,7 @@ struct TailArgs {
     double sigma, dd;
     float *S, *c, *num, *den, *W;
     unsigned long long *Si;             // exact sums, then counts (nullptr: S and c already hold this epoch's fp32 values)
+    int reps; size_t rep_words;         // replicas of a local accumulator (common.cuh: acc_replicas)
     PeerView peer;                      // world > 0: the sums run over all ranks' accumulators (peer.cuh)
     const float *qinv;
     int lds;
@@ -77,7 +78,7 @@ epoch_tail_kernel(TailArgs A) {
     neigh_tables_fill(A.P.gx, A.P.gy, A.P.kind, A.P.compact, A.P.shifted, A.sigma, A.dd, const_cast<float *>(A.P.tx),
                       const_cast<float *>(A.P.ty), const_cast<float *>(A.P.mx), const_cast<float *>(A.P.my), tid, nthr);
     if (A.Si != nullptr)
-        accum_finalize_elements(A.Si, A.qinv, K, D, A.lds, A.S, A.c, 1, A.peer, tid, nthr);
+        accum_finalize_elements(A.Si, A.reps, A.rep_words, A.qinv, K, D, A.lds, A.S, A.c, 1, A.peer, tid, nthr);
     if (tid < 4) A.gstat[tid] = 0u;
     grid_barrier(A.bar);
     // ---- phase 1: apply ----

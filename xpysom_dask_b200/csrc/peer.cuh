@@ -105,11 +105,11 @@ __device__ __forceinline__ long long peer_sum(const PeerView &V, size_t e) {
 
 // The finalize phase shared by accum_finalize_kernel and phase 0 of epoch_tail_kernel (grid-stride over `nthr`
 // threads): int64 sums -> the fp32 S (K, D) and c (K); double(S_int) * 2^-q is exact up to 2^53, then rounded ONCE.
-// Local accumulator (V.world == 0): cleared as it is read.  Peer accumulators: summed over the ranks, the OTHER
+// Local accumulator (V.world == 0): its `reps` replicas are summed and cleared as they are read.  Peer accumulators: summed over the ranks, the OTHER
 // parity's local accumulator is cleared (step 4).
-__device__ __forceinline__ void accum_finalize_elements(unsigned long long *Si, const float *qinv, int k, int d, int lds,
-                                                        float *S, float *c, int clear, const PeerView &V, int64_t tid,
-                                                        int64_t nthr) {
+__device__ __forceinline__ void accum_finalize_elements(unsigned long long *Si, int reps, size_t rep_words, const float *qinv,
+                                                        int k, int d, int lds, float *S, float *c, int clear, const PeerView &V,
+                                                        int64_t tid, int64_t nthr) {
     const int64_t tot = (int64_t)k * lds, all = tot + k;
     if (V.world > 0) {
         peer_exchange_begin(V);
@@ -127,14 +127,19 @@ __device__ __forceinline__ void accum_finalize_elements(unsigned long long *Si, 
         return;
     }
     for (int64_t e = tid; e < all; e += nthr) {
-        const long long v = (long long)Si[e];
+        unsigned long long u = 0ull;
+        for (int r = 0; r < reps; ++r) {                       // the replicas of a local accumulator (common.cuh)
+            const unsigned long long w = Si[(size_t)r * rep_words + e];
+            u += w;
+            if (clear && w) Si[(size_t)r * rep_words + e] = 0ull;
+        }
+        const long long v = (long long)u;
         if (e < tot) {
             const int row = (int)(e / lds), col = (int)(e % lds);
             if (col < d) S[(int64_t)row * d + col] = (float)((double)v * (double)qinv[col]);
         } else {
-            c[e - tot] = (float)(unsigned long long)v;
+            c[e - tot] = (float)u;
         }
-        if (clear && v) Si[e] = 0ull;
     }
 }
 

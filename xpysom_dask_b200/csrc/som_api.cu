@@ -62,12 +62,15 @@ static int launch_tc(int use, const float *X, int64_t n, int d, int64_t ldx, con
     return tc2::launch_bmu_tc2(X, n, d, ldx, k, L, ws, bmu, best, T, sm_count, st);
 }
 
-// the accumulator the ABI hands over: [S: k * acc_ld(d) words | counts: k words]
+// the accumulator the ABI hands over: acc_replicas(k, d) copies of [S: k * acc_ld(d) words | counts: k words]
+// (an accumulator in peer memory, som_b200_peer_accumulator, is used as ONE copy: every replica would be read by every rank)
 static AccTarget acc_target(uint64_t *acc_dev, const float *qscale_dev, int k, int d) {
     AccTarget T;
     T.S = reinterpret_cast<unsigned long long *>(acc_dev);
     T.cnt = T.S + (size_t)k * acc_ld(d);
     T.qscale = qscale_dev;
+    T.rep_words = acc_words_one(k, d);
+    T.reps = peer_lookup(acc_dev) ? 1 : acc_replicas(k, d);
     return T;
 }
 
@@ -213,8 +216,10 @@ int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, 
 
 size_t som_b200_accum_words(int k, int d) {
     if (k <= 0 || d <= 0) return 0;
-    return (size_t)k * acc_ld(d) + (size_t)k;
+    return acc_words_one(k, d) * (size_t)acc_replicas(k, d);
 }
+
+int som_b200_accum_replicas(int k, int d) { return (k <= 0 || d <= 0) ? 0 : acc_replicas(k, d); }
 
 int som_b200_accum_scales(const float *colmax_dev, int d, double n_total, float *qscale_dev, float *qinv_dev, void *stream) {
     SOM_REQUIRE(colmax_dev && qscale_dev && qinv_dev && d > 0 && n_total >= 0, SOM_E_BADARG, "accum_scales: bad argument");
@@ -232,12 +237,12 @@ int som_b200_accum_finalize(uint64_t *acc_dev, const float *qinv_dev, int k, int
     const AccTarget T = acc_target(acc_dev, nullptr, k, d);
     // an accumulator handed out by som_b200_peer_accumulator: the sums run over all ranks (peer.cuh)
     PeerComm *pc = peer_lookup(acc_dev);
-    SOM_REQUIRE(pc == nullptr || pc->words >= som_b200_accum_words(k, d), SOM_E_SHAPE, "accum_finalize: the peer accumulator is too small");
+    SOM_REQUIRE(pc == nullptr || pc->words >= acc_words_one(k, d), SOM_E_SHAPE, "accum_finalize: the peer accumulator is too small");
     const PeerView V = pc ? peer_next_exchange(pc) : PeerView();
     int grid = grid_for((int64_t)k * acc_ld(d) + k, di.sm);
     if (pc && grid > di.sm) grid = di.sm;          // every block polls the flags: all of them co-resident
     return check_cuda(launch_pdl(accum_finalize_kernel, dim3(grid), dim3(256), 0,
-                                 (cudaStream_t)stream, T.S, qinv_dev, k, d, acc_ld(d), s_dev, c_dev, 1, V),
+                                 (cudaStream_t)stream, T.S, T.reps, T.rep_words, qinv_dev, k, d, acc_ld(d), s_dev, c_dev, 1, V),
                       "accum_finalize_kernel launch");
 }
 
@@ -248,7 +253,7 @@ int som_b200_accum_fold(uint64_t *acc_dev, const float *qinv_dev, int k, int d, 
     if (rc) return rc;
     const AccTarget T = acc_target(acc_dev, nullptr, k, d);
     accum_fold_kernel<<<grid_for((int64_t)k * acc_ld(d), di.sm), 256, 0, (cudaStream_t)stream>>>(
-        T.S, T.cnt, qinv_dev, k, d, acc_ld(d), sd_dev, sd_dev + (size_t)k * d);
+        T.S, T.reps, T.rep_words, qinv_dev, k, d, acc_ld(d), sd_dev, sd_dev + (size_t)k * d);
     return check_cuda(cudaGetLastError(), "accum_fold_kernel launch");
 }
 
@@ -464,7 +469,7 @@ int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, 
     A.sigma = sigma; A.dd = 2.0 * std_coeff * std_coeff * sigma * sigma;
     A.S = s_dev; A.c = c_dev; A.num = num_dev; A.den = den_dev; A.W = w_dev;
     const AccTarget T = acc_target(acc_dev, nullptr, K, d);
-    A.Si = acc_dev ? T.S : nullptr; A.qinv = qinv_dev; A.lds = acc_ld(d);
+    A.Si = acc_dev ? T.S : nullptr; A.qinv = qinv_dev; A.lds = acc_ld(d); A.reps = T.reps; A.rep_words = T.rep_words;
     A.k = K; A.d = d; A.dist_kind = dist_kind; A.k_pad = L.k_pad;
     A.aux = reinterpret_cast<float *>(ws + L.aux_off); A.bias = reinterpret_cast<float *>(ws + L.bias_off);
     A.amax = reinterpret_cast<float *>(ws + L.amax_off); A.gstat = reinterpret_cast<unsigned int *>(ws + L.gstat_off);
@@ -493,7 +498,7 @@ int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, 
     A.b_per_slice = (int)round_up(ceil_div(K, slices), NB_K);
     A.slices = (int)ceil_div(K, A.b_per_slice);
     PeerComm *pc = peer_lookup(acc_dev);
-    SOM_REQUIRE(pc == nullptr || pc->words >= som_b200_accum_words(K, d), SOM_E_SHAPE, "epoch_tail: the peer accumulator is too small");
+    SOM_REQUIRE(pc == nullptr || pc->words >= acc_words_one(K, d), SOM_E_SHAPE, "epoch_tail: the peer accumulator is too small");
     const unsigned seq_before = pc ? pc->seq : 0u;
     if (pc) A.peer = peer_next_exchange(pc);
     void *args[] = {&A};
