@@ -274,6 +274,13 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
     auto bfullq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * MAXB + 2 * NACC + b); };
     auto bemptyq_bar = [&](int b) { return bar0 + 8u * (3 * NA + 2 * MAXB + 2 * NACC + 2 + b); };
     constexpr uint32_t kIdescF16 = idesc_f16(TBN);
+    // Narrow last tile (bias in the epilogue only): when the map is not a multiple of 256 neurons the last tile's MMAs
+    // cover just the real neurons rounded up to 16 (UMMA N granularity over a CTA pair) -- 16 instead of 256 columns at
+    // 100 x 100 neurons (2.3 % of that kernel's tensor work).  The pair's halves of such a tile are its first
+    // n_last / 2 B rows of EACH CTA, so CTA r loads neurons nt * 256 + r * n_last / 2 ...; accumulator column c is
+    // still neuron nt * 256 + c.  Columns the MMA did not write hold stale TMEM data, which the +inf bias of the padding
+    // neurons turns into +inf / NaN (never a minimum); with the bias folded into the contraction every tile stays full.
+    const int n_last = FOLD ? TBN : (int)round_up(acc.k - (num_n_tiles - 1) * TBN, 16);
     volatile uint32_t *tmem_slot = reinterpret_cast<volatile uint32_t *>(bars + NUM_BARS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -321,8 +328,9 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                         if (tc::elect_one()) {
                             // bytes of both CTAs: hi (+ lo unless packed) halves (+ the fold images)
                             if (leader) tc::mbar_expect_tx(bfull_bar(s), (packed ? 2 : 4) * TBNH * 128 + (FOLD ? 2 * FOLD_TILE_BYTES : 0));
-                            tma_load_2d_2sm(st, &map_whi, kb * BK, nt * TBN + (int)rank * TBNH, bfull_bar(s));
-                            if (!packed) tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nt * TBN + (int)rank * TBNH, bfull_bar(s));
+                            const int nrow = nt * TBN + (int)rank * ((nt == num_n_tiles - 1 ? n_last : TBN) / 2);
+                            tma_load_2d_2sm(st, &map_whi, kb * BK, nrow, bfull_bar(s));
+                            if (!packed) tma_load_2d_2sm(st + HALF_SLOT, &map_wlo, kb * BK, nrow, bfull_bar(s));
                             if (FOLD)      // this CTA's 4 KB fold image: 16 rows of 64 floats of the (k_pad / 8, 64) view, no swizzle
                                 tma_load_2d_2sm(bf_base + s * FOLD_TILE_BYTES, &map_fold, 0, (nt * 2 + (int)rank) * 16, bfull_bar(s));
                         }
@@ -359,6 +367,7 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
                     const int a = acc_it % NACC; const uint32_t aph = (acc_it / NACC) & 1;
                     tc::dbg_stamp(probe, 0, acc_it);                 // MMA: starts waiting for the tile's inputs
                     const uint32_t tmem_d = tmem_base + (uint32_t)(a * TBN);
+                    const uint32_t idesc = (FOLD || nt != num_n_tiles - 1) ? kIdescF16 : idesc_f16(n_last);
                     for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                         const uint32_t ia = resident ? (tile_it * (uint32_t)num_k_blocks + kb) : it;
                         const int sa = ia % NAR; const uint32_t pha = (ia / NAR) & 1;
@@ -382,16 +391,16 @@ bmu_tc3_kernel(const __grid_constant__ CUtensorMap map_x, const __grid_constant_
 #pragma unroll
                                 for (int kk = 0; kk < 3; ++kk) {
                                     const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);
-                                    umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, kIdescF16, kk != 0);
+                                    umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, idesc, kk != 0);
                                 }
                             } else {
 #pragma unroll
                                 for (int kk = 0; kk < BK / UMMA_K; ++kk) {
                                     if (kk >= kk_n) break;
                                     const uint64_t off = (uint64_t)((kk * UMMA_K * 2) >> 4);    // +32 B along K
-                                    umma_f16_2sm(tmem_d, a_lo + off, b_hi + off, kIdescF16, (kb | kk) != 0);
-                                    umma_f16_2sm(tmem_d, a_hi + off, b_lo + off, kIdescF16, 1);
-                                    umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, kIdescF16, 1);
+                                    umma_f16_2sm(tmem_d, a_lo + off, b_hi + off, idesc, (kb | kk) != 0);
+                                    umma_f16_2sm(tmem_d, a_hi + off, b_lo + off, idesc, 1);
+                                    umma_f16_2sm(tmem_d, a_hi + off, b_hi + off, idesc, 1);
                                 }
                             }
                             if (FOLD)      // acc += 2^a_r * (bias_k 2^b_k): one kind::tf32 step, K = 8 (three pieces + zeros)
