@@ -91,16 +91,23 @@ __device__ __forceinline__ void peer_exchange_begin(const PeerView &V) {
     __syncthreads();
 }
 
-// step 3 for one element: the integer sum over the ranks, four remote loads in flight per thread and round
-__device__ __forceinline__ long long peer_sum(const PeerView &V, size_t e) {
-    unsigned long long s = 0ull;
+// step 3 for two adjacent elements (16-byte remote loads): the integer sums over the ranks, four loads in flight per
+// thread and round
+__device__ __forceinline__ ulonglong2 ld_peer_u64x2(const unsigned long long *p) {
+    ulonglong2 v;
+    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];" : "=l"(v.x), "=l"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ ulonglong2 peer_sum2(const PeerView &V, size_t e) {
+    ulonglong2 s = make_ulonglong2(0ull, 0ull);
     for (int r = 0; r < V.world; r += 4) {
-        unsigned long long v[4];
+        ulonglong2 v[4];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) v[u] = (r + u < V.world) ? ld_peer_u64(peer_acc(V, r + u) + e) : 0ull;
-        s += (v[0] + v[1]) + (v[2] + v[3]);
+        for (int u = 0; u < 4; ++u) v[u] = (r + u < V.world) ? ld_peer_u64x2(peer_acc(V, r + u) + e) : make_ulonglong2(0ull, 0ull);
+        s.x += (v[0].x + v[1].x) + (v[2].x + v[3].x);
+        s.y += (v[0].y + v[1].y) + (v[2].y + v[3].y);
     }
-    return (long long)s;
+    return s;
 }
 
 // The finalize phase shared by accum_finalize_kernel and phase 0 of epoch_tail_kernel (grid-stride over `nthr`
@@ -114,15 +121,23 @@ __device__ __forceinline__ void accum_finalize_elements(unsigned long long *Si, 
     if (V.world > 0) {
         peer_exchange_begin(V);
         unsigned long long *old = reinterpret_cast<unsigned long long *>(V.p[V.rank] + PEER_DATA_OFF) + (size_t)(V.par ^ 1) * V.words;
-        for (int64_t e = tid; e < all; e += nthr) {
-            const long long v = peer_sum(V, (size_t)e);
-            if (e < tot) {
-                const int row = (int)(e / lds), col = (int)(e % lds);
-                if (col < d) S[(int64_t)row * d + col] = (float)((double)v * (double)qinv[col]);
-            } else {
-                c[e - tot] = (float)(unsigned long long)v;
+        // pairs of words (the accumulators are 16-byte aligned and `words` is even; a word past the last count is padding)
+        for (int64_t e = 2 * tid; e < all; e += 2 * nthr) {
+            const ulonglong2 s2 = peer_sum2(V, (size_t)e);
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                const int64_t eh = e + h;
+                if (eh >= all) break;
+                const unsigned long long u = h ? s2.y : s2.x;
+                if (eh < tot) {
+                    const int row = (int)(eh / lds), col = (int)(eh % lds);
+                    if (col < d) S[(int64_t)row * d + col] = (float)((double)(long long)u * (double)qinv[col]);
+                } else {
+                    c[eh - tot] = (float)u;
+                }
             }
-            if (old[e]) old[e] = 0ull;
+            const ulonglong2 o = *reinterpret_cast<const ulonglong2 *>(old + e);
+            if (o.x | o.y) *reinterpret_cast<ulonglong2 *>(old + e) = make_ulonglong2(0ull, 0ull);
         }
         return;
     }
