@@ -226,6 +226,25 @@ int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, 
                         float *num_dev, float *den_dev, float *tables_dev, size_t tables_floats,
                         void *ws_dev, size_t ws_bytes, void *stream);
 
+/* ---- long rows: one tensor-core pass + exact refinement (csrc/bmu_filter.cuh) -------------------
+ * For Euclidean maps with 256 <= d <= 1024 features and >= 1024 neurons the three-pass contraction is bound by the
+ * tensor pipe.  This path runs ONE fp16 pass on centred operands that yields, per (sample, neuron), an interval
+ * guaranteed to contain the score; neurons whose lower bound exceeds the row's smallest upper bound cannot be the
+ * BMU; the few survivors are re-scored exactly (fp64 sum of squared differences of the caller's fp32 arrays) and the
+ * first minimum wins.  Replaces _winner / _activate (xpysom.py:336-354,410-417) for those shapes.
+ *   som_b200_filter_prepare_samples   once per upload: centre, fp16 copy of the samples, per-row statistics
+ *   som_b200_bmu_filter               BMUs of all rows (the codebook side is prepared inside, every call)
+ * After som_b200_bmu_filter the workspace holds, at byte som_b200_filter_overflow_offset: int32 = rows whose candidate
+ * lists overflowed (their bmu is -1: the caller re-does them with som_b200_bmu), and at +8 a uint64 = candidates
+ * re-scored in that call (long lists make the refinement dearer than the two tensor passes it saves: the caller's
+ * policy input).  An epoch is then: som_b200_bmu_filter, fix the overflowed rows up, som_b200_accumulate. */
+int    som_b200_filter_eligible(const float *x_dev, int64_t n, int d, int64_t ldx, int k, int dist_kind);
+size_t som_b200_filter_workspace_bytes(int64_t n, int k, int d);
+size_t som_b200_filter_overflow_offset(int64_t n, int k, int d);
+int    som_b200_filter_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, void *fws_dev, size_t fws_bytes, void *stream);
+int    som_b200_bmu_filter(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int32_t *bmu_dev,
+                           void *fws_dev, size_t fws_bytes, void *stream);
+
 /* ---- sharded path: the one exchange step, fused into the epoch tail ---------------------------
  * The reference sums the per-block partial updates with Dask (`sum(...)` over the delayed `_update`
  * results, xpysom.py:545-558).  With one process per GPU that is ONE sum of the exact accumulators

@@ -95,6 +95,10 @@ def test_config_scale_teacher_forced_parity(name):
         # GPU: BMUs for W_t, then one epoch from W_t
         bmu_gpu = som.predict(x_dev)
         som.train(x_dev, T_SCHEDULE, iter_beg=t, iter_end=t + 1)
+        # the BMUs the training epoch itself used (same W_t).  On long rows they come from the one-pass filter + exact fp64
+        # refinement, which may settle a near-tie differently from predict()'s three-pass kernel
+        if getattr(som, "_bmu_last", None) is not None:
+            bmu_gpu = som._bmu_last.cpu().numpy()
         w_gpu = som._weights.copy()
         som._weights = w_in.copy()                     # later t continue from the SAME trajectory
         # oracle: the reference's epoch from the same W_t, its BMUs and its top-2 gaps

@@ -583,3 +583,71 @@ def test_errors_cross_the_abi_as_codes(eng):
     small = torch.empty(16, dtype=torch.uint8, device="cuda")
     assert lib.som_b200_prepare_codebook(eng._p(w), 16, 8, 0, 2.0, eng._p(small), 16, None) == -3
     assert lib.som_b200_prepare_codebook(eng._p(w), 16, 8, 99, 2.0, eng._p(small), 16, None) == -1
+
+
+# ---- long rows: one tensor-core pass + refinement (csrc/bmu_filter.cuh) ---------------------------------------------
+def _filter_bmus(eng, xd, wd, seed_bmu=None):
+    n, d = xd.shape
+    K = wd.shape[0]
+    assert eng.filter_eligible(xd, K, 0)
+    fws = eng.filter_workspace(xd, K)
+    bmu = torch.full((n,), -1, dtype=torch.int32, device="cuda") if seed_bmu is None else seed_bmu.clone()
+    eng.bmu_filter(xd, wd, fws, bmu)
+    ovf, evals = eng.filter_stats(fws, n, K, d)
+    return bmu, ovf, evals
+
+
+@pytest.mark.parametrize("n,d,gx,gy", [(4500, 256, 32, 32), (5000, 784, 40, 50), (4099, 300, 33, 32), (6000, 1024, 32, 33)])
+def test_bmu_filter_matches_oracle(eng, n, d, gx, gy):
+    """The filter + refine path picks, on every row, a neuron inside the stated band of the reference's minimum; run
+    unseeded (no previous BMUs), seeded with its own result, and seeded with arbitrary neurons (any neuron's score is a
+    valid upper bound): the same BMUs every time."""
+    x = U.blobs(n, d, seed=n + d)
+    spec = so.SomSpec(gx=gx, gy=gy, dim=d, random_seed=d)
+    w = so.init_weights(spec).astype(np.float32) * 0.5 + 0.5 * U.uniform(gx * gy, d, 3).reshape(gx, gy, d)
+    xd, wd = torch.from_numpy(x).cuda(), torch.from_numpy(w.reshape(gx * gy, d)).cuda()
+    bmu, ovf, evals = _filter_bmus(eng, xd, wd)
+    assert ovf == 0 and int((bmu < 0).sum()) == 0
+    r = U.bmu_parity(spec, x, w, bmu.cpu().numpy())
+    print("\n[filter n=%d d=%d K=%d] near-tie rate %.2e, raw mismatch %.2e, %.2f candidates re-scored per row"
+          % (n, d, gx * gy, r["near_tie_rate"], r["mismatch_rate"], evals / n))
+    assert r["bad"] == 0, r
+    again, _, evals2 = _filter_bmus(eng, xd, wd, seed_bmu=bmu)
+    assert torch.equal(again, bmu) and evals2 <= evals
+    junk = torch.randint(0, gx * gy, (n,), dtype=torch.int32, device="cuda")
+    assert torch.equal(_filter_bmus(eng, xd, wd, seed_bmu=junk)[0], bmu)
+
+
+def test_bmu_filter_overflow_rows_are_marked_and_training_fixes_them_up(eng):
+    """A very smooth map (every neuron within 1e-4 of a plane through the data mean) has more live candidates than a
+    list holds: those rows come back as -1 from the C entry, XPySom re-does them with the three-pass kernel (or skips the
+    filter for the epoch), and the epoch still matches the oracle's update from its own BMUs."""
+    from xpysom_dask_b200 import XPySom
+    n, d, gx, gy = 6000, 512, 40, 40
+    rng = np.random.RandomState(5)
+    x = rng.random_sample((n, d)).astype(np.float32)
+    u = np.linspace(-1, 1, gx, dtype=np.float32)
+    a, b = rng.randn(d).astype(np.float32) * 0.02, rng.randn(d).astype(np.float32) * 0.02
+    w = (0.5 + u[:, None, None] * a + u[None, :, None] * b + 1e-4 * rng.randn(gx, gy, d)).astype(np.float32)
+    xd, wd = torch.from_numpy(x).cuda(), torch.from_numpy(w.reshape(gx * gy, d)).cuda()
+    bmu, ovf, evals = _filter_bmus(eng, xd, wd)
+    assert ovf == int((bmu < 0).sum())
+    spec = so.SomSpec(gx=gx, gy=gy, dim=d, random_seed=0)
+    keep = (bmu >= 0).cpu().numpy()
+    r = U.bmu_parity(spec, x[keep], w, bmu.cpu().numpy()[keep])
+    assert r["bad"] == 0, r
+    for max_cand in (1e9, 12.0):                   # filter forced on (fix-up of the overflowed rows) / normal policy
+        som = XPySom(gx, gy, d, random_seed=0)
+        som._FILTER_MAX_CANDIDATES, som._FILTER_MAX_OVERFLOW = max_cand, (1.0 if max_cand > 1e6 else 0.005)
+        som._weights = w.copy()
+        som.train(xd, 10, iter_beg=4, iter_end=5)
+        used = som._bmu_last.cpu().numpy()
+        assert (used >= 0).all()
+        assert U.bmu_parity(spec, x, w, used)["bad"] == 0
+        S, c = so.sums_by_bmu(used, x, spec.K)
+        sig = float(so.decay_value(spec.decay_function, spec.sigma, spec.sigmaN, 4, 10))
+        H = so.neighborhood_table(spec, sig).astype(np.float64)
+        num, den = H.T @ S, H.T @ c
+        w_same = np.where(den[:, None] != 0, num / den[:, None], w.reshape(spec.K, -1)).reshape(w.shape)
+        assert U.codebook_rel_err(som._weights, w_same) < 1e-5, max_cand
+        assert som.stats.get("filter_epochs", 0) > 0        # (no probe on so few rows: the filter runs, then judges itself)

@@ -14,6 +14,7 @@
 #include "accumulate.cuh"
 #include "neigh.cuh"
 #include "peer.cuh"
+#include "bmu_filter.cuh"
 #include "misc.cuh"
 #include "epoch_tail.cuh"
 
@@ -325,6 +326,44 @@ int som_b200_top2(const float *x_dev, int64_t n, int d, int64_t ldx, const float
     row_sq_kernel<<<(unsigned)ceil_div(k, 8), 256, 0, (cudaStream_t)stream>>>(w_dev, k, d, wsq);
     if ((rc = check_cuda(cudaGetLastError(), "row_sq_kernel launch"))) return rc;
     return launch_top2_simt(x_dev, n, d, ldx, w_dev, k, wsq, top2_dev, di.sm, (cudaStream_t)stream);
+}
+
+/* ---- one-pass filter + exact refine (bmu_filter.cuh) ---- */
+int som_b200_filter_eligible(const float *x_dev, int64_t n, int d, int64_t ldx, int k, int dist_kind) {
+    return flt::filter_eligible(x_dev, n, d, ldx, k, dist_kind) ? 1 : 0;
+}
+
+size_t som_b200_filter_workspace_bytes(int64_t n, int k, int d) {
+    if (n <= 0 || k <= 0 || d <= 0) return 0;
+    return flt::filter_layout(n, k, d).total;
+}
+
+size_t som_b200_filter_overflow_offset(int64_t n, int k, int d) {
+    if (n <= 0 || k <= 0 || d <= 0) return 0;
+    return flt::filter_layout(n, k, d).ovf_off;
+}
+
+int som_b200_filter_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, void *fws_dev, size_t fws_bytes, void *stream) {
+    SOM_REQUIRE(x_dev && fws_dev && n > 0 && d > 0 && ldx >= d, SOM_E_BADARG, "filter_prepare_samples: bad argument");
+    SOM_REQUIRE(flt::filter_eligible(x_dev, n, d, ldx, 1 << 20, SOM_DIST_EUCLIDEAN), SOM_E_SHAPE,
+                "filter_prepare_samples: shape not eligible (needs 256 <= d <= 1024, d %% 4 == 0, 16-byte aligned rows, n >= 4096)");
+    SOM_REQUIRE(fws_bytes >= flt::filter_layout(n, 1, d).cand_off, SOM_E_WORKSPACE, "filter_prepare_samples: workspace too small");
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    return flt::filter_prepare_samples(x_dev, n, d, ldx, static_cast<uint8_t *>(fws_dev), di.sm, (cudaStream_t)stream);
+}
+
+int som_b200_bmu_filter(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int32_t *bmu_dev,
+                        void *fws_dev, size_t fws_bytes, void *stream) {
+    SOM_REQUIRE(x_dev && w_dev && bmu_dev && fws_dev, SOM_E_BADARG, "bmu_filter: NULL pointer");
+    SOM_REQUIRE(flt::filter_eligible(x_dev, n, d, ldx, k, SOM_DIST_EUCLIDEAN), SOM_E_SHAPE, "bmu_filter: shape not eligible");
+    SOM_REQUIRE(fws_bytes >= flt::filter_layout(n, k, d).total, SOM_E_WORKSPACE, "bmu_filter: workspace %zu < %zu bytes", fws_bytes,
+                flt::filter_layout(n, k, d).total);
+    DevInfo di;
+    int rc = device_info(di);
+    if (rc) return rc;
+    return flt::launch_bmu_filter(x_dev, n, d, ldx, w_dev, k, static_cast<uint8_t *>(fws_dev), bmu_dev, di.sm, (cudaStream_t)stream);
 }
 
 int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const int32_t *bmu_dev, int k,

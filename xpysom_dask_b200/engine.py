@@ -171,6 +171,38 @@ class CudaEngine:
                        "som_b200_epoch_accumulate")
         self.launches += 1
 
+    # -- long rows: one tensor-core pass + exact refinement (csrc/bmu_filter.cuh) ---------------------------------
+    def filter_eligible(self, x, k, dist_kind):
+        n, d = x.shape
+        return bool(self.lib.som_b200_filter_eligible(self._p(x), n, d, x.stride(0), int(k), int(dist_kind)))
+
+    def filter_workspace(self, x, k):
+        """Workspace of the filter path for the samples x (prepared: centre, fp16 copy, row statistics)."""
+        n, d = x.shape
+        fws = torch.empty(self.lib.som_b200_filter_workspace_bytes(n, int(k), d), dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_filter_prepare_samples(self._p(x), n, d, x.stride(0), self._p(fws), fws.numel(),
+                                                                self._stream()), "som_b200_filter_prepare_samples")
+        self.launches += 3
+        return fws
+
+    def filter_stats(self, fws, n, k, d):
+        """(rows whose candidate lists overflowed -- their bmu is -1 --, candidates re-scored) of the last bmu_filter call.
+        Synchronises."""
+        off = self.lib.som_b200_filter_overflow_offset(int(n), int(k), int(d))
+        v = fws[off:off + 16].view(torch.int64).cpu()
+        return int(v[0].item()) & 0xffffffff, int(v[1].item())
+
+    def bmu_filter(self, x, w, fws, bmu_out=None):
+        n, d = x.shape
+        if bmu_out is None:
+            bmu_out = self.empty(n, dtype=torch.int32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_bmu_filter(self._p(x), n, d, x.stride(0), self._p(w), w.shape[0], self._p(bmu_out),
+                                                    self._p(fws), fws.numel(), self._stream()), "som_b200_bmu_filter")
+        self.launches += 3
+        return bmu_out
+
     def neigh_apply(self, s, c, gx, gy, d, topology, neigh_kind, sigma, eta, std_coeff, compact, num, den, tables):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.som_b200_neigh_apply(self._p(s), self._p(c), gx, gy, d, topology, neigh_kind,

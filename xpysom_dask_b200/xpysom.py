@@ -275,6 +275,63 @@ class XPySom:
                              if cache_key is not None else None)
         return stats
 
+    # ---- long rows: one tensor-core pass + exact refinement (csrc/bmu_filter.cuh) -------------------------------
+    _FILTER_PROBE_ROWS = 8192
+    _FILTER_MAX_CANDIDATES = 12.0      # re-scored candidates per row above which the three-pass kernel is cheaper
+    _FILTER_MAX_OVERFLOW = 0.005       # fraction of rows whose candidate lists may overflow
+
+    def _filter_state(self, eng, x, K, dist_kind, cache_key=None):
+        """Workspaces of the filter path for the resident samples x (None when the shape is not eligible or another
+        kernel was asked for): the prepared samples, and a prepared slice of them on which every epoch that is not
+        sure the filter pays first PROBES the current codebook (candidates per row, overflowed lists)."""
+        if (self._algo != 'auto' or getattr(eng, 'name', '') != 'cuda' or x.shape[0] == 0
+                or os.environ.get('SOM_B200_FILTER', '1') == '0' or not eng.filter_eligible(x, K, dist_kind)):
+            return None
+        cached = getattr(self, '_filter_cache', None)
+        if (cache_key is not None and cached is not None and cached[0]() is cache_key and cached[1] == cache_key._version
+                and cached[2] == K):
+            return cached[3]
+        n = x.shape[0]
+        npr = min(n, self._FILTER_PROBE_ROWS)
+        st = {'fws': eng.filter_workspace(x, K), 'n_probe': npr, 'on': None,
+              'probe': eng.filter_workspace(x[:npr], K) if npr < n else None,
+              'probe_bmu': torch.full((npr,), -1, dtype=torch.int32, device=eng.device)}
+        self._filter_cache = (weakref.ref(cache_key), cache_key._version, K, st) if cache_key is not None else None
+        return st
+
+    def _filter_good(self, ovf, evals, rows):
+        return ovf <= self._FILTER_MAX_OVERFLOW * rows and evals <= self._FILTER_MAX_CANDIDATES * max(rows - ovf, 1)
+
+    def _filter_epoch(self, eng, st, x, w, bmu, ws, dist_kind, p, xscale):
+        """BMUs of all rows of x through the filter path, into ``bmu``; False when this epoch should take the three-pass
+        kernel instead (the probe, or the previous epoch, found the candidate lists too long for the current map)."""
+        n, d = x.shape
+        K = w.shape[0]
+        if not st['on'] and st['probe'] is not None:
+            if st.get('skip', 0) > 0:            # the last probe was far from paying: do not even probe this epoch
+                st['skip'] -= 1
+                return False
+            npr = st['n_probe']
+            eng.bmu_filter(x[:npr], w, st['probe'], st['probe_bmu'])
+            ovf, ev = eng.filter_stats(st['probe'], npr, K, d)
+            st['on'] = self._filter_good(ovf, ev, npr)
+            self.stats['filter_probe'] = (ovf / npr, ev / max(npr - ovf, 1))
+            if not st['on']:
+                if ev > 2.0 * self._FILTER_MAX_CANDIDATES * max(npr - ovf, 1) or ovf > 4 * self._FILTER_MAX_OVERFLOW * npr:
+                    st['skip'] = 2
+                return False
+        eng.bmu_filter(x, w, st['fws'], bmu)
+        ovf, ev = eng.filter_stats(st['fws'], n, K, d)
+        if ovf:            # rows whose lists overflowed: the three-pass kernel on just those rows
+            rows = torch.nonzero(bmu < 0).squeeze(1)
+            xg = x.index_select(0, rows)
+            xs_g = eng.prepare_samples(xg, True)[0]
+            bmu.index_copy_(0, rows, eng.bmu(xg, w, dist_kind, p, _lib.ALGO['tc16'], ws, xscale=xs_g))
+        st['on'] = self._filter_good(ovf, ev, n)
+        self.stats['filter_epochs'] = self.stats.get('filter_epochs', 0) + 1
+        self.stats['filter_last'] = (ovf / n, ev / max(n - ovf, 1))
+        return True
+
     def _device_budget(self, eng, nbytes=None):
         """Bytes of samples this process may keep resident (the rest of the job streams through two block buffers).
         With ``nbytes`` given the answer only has to be right about ``nbytes <= budget``: a matrix below 1/8 of what
@@ -371,6 +428,7 @@ class XPySom:
             bmu = eng.empty(n, dtype=torch.int32)
             if n_ep > 0:
                 eng.prepare_codebook(w, dist_kind, p, ws)
+                bmu.fill_(-1)               # 'no BMU yet' (the filter path seeds its bounds with the previous epoch's)
             first = iter_beg
             if chunks is not None:
                 # first epoch: every chunk is searched and accumulated as it lands, with its own column scales, and
@@ -435,12 +493,15 @@ class XPySom:
                 # The sum over the shards: on one node and small maps the accumulators live in NVLink peer memory and
                 # the tail's finalize phase reads all of them itself (peer.py); otherwise NCCL all-reduces the integers.
                 pacc = self._peer_accumulator(eng, group, acc.numel()) if (group is not None and first < iter_end) else None
+                flt = self._filter_state(eng, x, K, dist_kind, cache_key=x if x is data else None) if first < iter_end else None
                 for t in range(first, iter_end):
                     a = pacc.current() if pacc is not None else acc
                     if prof is not None:
                         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                         ev[0].record()
-                    if n > 0:               # a rank may hold an EMPTY shard: it still joins the exchange and the tail
+                    if n > 0 and flt is not None and self._filter_epoch(eng, flt, x, w, bmu, ws, dist_kind, p, xscale):
+                        eng.accumulate(x, bmu, K, qscale, a)           # BMUs from the one-pass filter + exact refinement
+                    elif n > 0:             # a rank may hold an EMPTY shard: it still joins the exchange and the tail
                         eng.epoch_accumulate(x, w, dist_kind, p, algo, qscale, a, ws, bmu_out=bmu, xscale=xscale)
                     if prof is not None:
                         ev[1].record()
@@ -450,6 +511,7 @@ class XPySom:
                     tail(t, a, qinv)
                 if pacc is not None:
                     pacc.fence()            # nobody is still reading this rank's accumulators when train() returns
+                self._bmu_last = bmu if (first < iter_end and n > 0) else None     # BMUs of the last epoch (device)
 
         self._weights = w.cpu().numpy().reshape(gx, gy, d)      # synchronises; fp32 like xpysom.py:580-583
         if verbose:
@@ -699,6 +761,8 @@ class XPySom:
         state['_process_group'] = None if self._process_group in (None, False) else _UNPICKLED_SHARDED
         state.pop('_stats_cache', None)
         state.pop('_peer_cache', None)
+        state.pop('_filter_cache', None)
+        state.pop('_bmu_last', None)
         state['_profile_events'] = []
         state['xp'] = None
         return state
