@@ -455,14 +455,37 @@ class GpuBench:
         rec = None
         if self.rank == 0:
             step_ms = ms / steps
-            rec = {"workload": wl["name"] + (" -- 64-blob Gaussian mixture (hot BMUs)" if blobs else ""),
+            rec = {"workload": wl["name"] + (" -- 64-blob Gaussian mixture (hot BMUs)" if blobs else "")
+                               + (" -- epochs %d..%d of the %d-epoch schedule" % (warmup, warmup + steps - 1, TOTAL_EPOCHS)
+                                  if warmup > 3 else ""),
                    "value": n * self.world * steps / (ms * 1e-3), "unit": "samples*epochs/s", "n_gpus": self.world,
                    "rows_per_gpu": n, "steps": steps, "warmup": warmup, "ms_per_step": step_ms,
                    "block_ms": blocks, "gpu_launches": launches,
                    "roofline": self.roofline(wl, n, bmu_ms, step_ms, eager_ms / steps, key)}
+            self.note_filter(som, rec)
         del som, x_dev
         torch.cuda.empty_cache()
         return rec
+
+    @staticmethod
+    def note_filter(som, rec):
+        """Long rows (D >= 256) may take the one-pass filter + refinement path (csrc/bmu_filter.cuh) when a probe of the
+        current codebook says it pays: say how many of the epochs run so far did, and what the kernel time covers then."""
+        st = getattr(som, "stats", {})
+        if "filter_probe" not in st and "filter_last" not in st:
+            return
+        rec["filter_path"] = {"epochs_on_it_so_far": st.get("filter_epochs", 0),
+                              "last_full_run_overflow_frac_and_candidates_per_row": st.get("filter_last"),
+                              "last_probe_overflow_frac_and_candidates_per_row": st.get("filter_probe"),
+                              "policy": "used when <= 12 candidates per row survive the one-pass bounds and <= 0.5 % of the "
+                                        "rows overflow their lists (probe on 8192 rows, or the previous epoch)"}
+        if st.get("filter_epochs", 0):
+            r = rec["roofline"]
+            r["kernel"] = ("bmu_filter_kernel (tcgen05 kind::f16, ONE pass on centred fp16 operands, interval epilogue) + "
+                           "bmu_refine_kernel + accumulate_kernel on the epochs that took the filter path; " + r["kernel"] +
+                           " on the others")
+            r["note"] += ("; kernel_ms here spans seed + filter + refine + the host's read of the statistics + exact "
+                          "accumulate on filter epochs, whose ceiling is frac 1.0 (one tensor pass)")
 
     def replica_check(self, som, wl, x_dev):
         """N > 1 (row G of SURVEY 8a, reference semantics xpysom.py:546-558: any chunking gives the same sum):
@@ -552,6 +575,7 @@ class GpuBench:
         clocks = sampler.stop() if rank == 0 else None
 
         replica = self.replica_check(som, wl, x_dev) if world > 1 else None
+        self._top_som_stats = type("S", (), {"stats": dict(som.stats)})()
         del som
         subs = {}
         if not args.no_extra:
@@ -561,6 +585,8 @@ class GpuBench:
                 heavy = w2["gx"] * w2["gy"] * w2["d"] > 4_000_000
                 subs[k] = self.sub_record(k, w2, False, 5 if heavy else min(args.steps, 20), 3, 0.0 if heavy else 0.1)
             subs[wl_key + "_blobs"] = self.sub_record(wl_key, wl, True, min(args.steps, 20), 3, 0.1)
+            if wl_key != "c4":     # the north-star shape later in the schedule, where the map has differentiated
+                subs["c4_late"] = self.sub_record("c4", WORKLOADS["c4"], False, 5, 40, 0.0)
 
         if rank != 0:
             return
@@ -591,6 +617,7 @@ class GpuBench:
             "roofline": roof,
             "workloads": subs,
         }
+        self.note_filter(self._top_som_stats, line) if getattr(self, "_top_som_stats", None) is not None else None
         if replica is not None:
             line["replica_check"] = replica
         if world == 1 and not args.no_cpu:

@@ -58,6 +58,9 @@ class OracleEngine:
     def accumulator(self, k, d):
         return torch.zeros(k * ((d + 1) // 2 * 2) + k, dtype=torch.int64)
 
+    def accum_one_copy(self, acc, k, d):
+        return acc                                                  # (one copy here: nothing to fold)
+
     def bmu(self, x, w, dist_kind, p, algo, ws, bmu_out=None, best_out=None, xscale=None):
         k, d = w.shape
         spec = so.SomSpec(gx=k, gy=1, dim=d, activation_distance="euclidean", p=p)

@@ -108,6 +108,19 @@ __global__ void accum_fold_kernel(unsigned long long *__restrict__ Si, int reps,
     }
 }
 
+// replicas 1.. of a local accumulator added into replica 0 and cleared (before an all-reduce: one copy travels)
+__global__ void accum_fold_replicas_kernel(unsigned long long *__restrict__ Si, int reps, size_t rep_words, int64_t all) {
+    pdl_wait(); pdl_trigger();
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < all; e += (int64_t)gridDim.x * blockDim.x) {
+        unsigned long long u = 0ull;
+        for (int r = 1; r < reps; ++r) {
+            const unsigned long long w = Si[(size_t)r * rep_words + e];
+            if (w) { u += w; Si[(size_t)r * rep_words + e] = 0ull; }
+        }
+        if (u) Si[e] += u;
+    }
+}
+
 // running fp64 sums -> fp32 S, c; the doubles are cleared
 __global__ void accum_finalize_f64_kernel(double *__restrict__ Sd, double *__restrict__ cd, int k, int d,
                                           float *__restrict__ S, float *__restrict__ c) {

@@ -101,6 +101,17 @@ class CudaEngine:
         """Zeroed exact accumulator [S | counts] of som_b200_accum_words(k, d) 64-bit words."""
         return self.zeros(self.lib.som_b200_accum_words(int(k), int(d)), dtype=torch.int64)
 
+    def accum_one_copy(self, acc, k, d):
+        """The part of a local accumulator that has to travel in an all-reduce: its replicas folded into the first."""
+        reps = self.lib.som_b200_accum_replicas(int(k), int(d))
+        if reps <= 1:
+            return acc
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_accum_fold_replicas(self._p(acc), int(k), int(d), self._stream()),
+                       "som_b200_accum_fold_replicas")
+        self.launches += 1
+        return acc[:acc.numel() // reps]
+
     def accum_finalize(self, acc, qinv, k, d, s, c):
         with torch.cuda.device(self.device):
             _lib.check(self.lib.som_b200_accum_finalize(self._p(acc), self._p(qinv), k, d, self._p(s), self._p(c),

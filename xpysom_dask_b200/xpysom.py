@@ -471,7 +471,7 @@ class XPySom:
                     eng.prepare_codebook(w, dist_kind, p, ws)
                     if n > 0:
                         eng.epoch_accumulate(x, w, dist_kind, p, algo, qscale, acc, ws, bmu_out=bmu, xscale=xscale)
-                    all_reduce(acc)
+                    all_reduce(eng.accum_one_copy(acc, K, d))
                     eng.accum_finalize(acc, qinv, K, d, S, c)
                     eng.neigh_apply_sched(S, c, gx, gy, d, topo, neigh, sched, epoch_idx, self._std_coeff,
                                           self.compact_support, num, den, tables)
@@ -492,7 +492,8 @@ class XPySom:
                 # -> everything else (eng.epoch_tail: finalize, apply, merge, preparation of the new codebook).
                 # The sum over the shards: on one node and small maps the accumulators live in NVLink peer memory and
                 # the tail's finalize phase reads all of them itself (peer.py); otherwise NCCL all-reduces the integers.
-                pacc = self._peer_accumulator(eng, group, acc.numel()) if (group is not None and first < iter_end) else None
+                pacc = (self._peer_accumulator(eng, group, acc.numel() // max(1, eng.lib.som_b200_accum_replicas(K, d)))
+                        if (group is not None and first < iter_end and cuda) else None)
                 flt = self._filter_state(eng, x, K, dist_kind, cache_key=x if x is data else None) if first < iter_end else None
                 for t in range(first, iter_end):
                     a = pacc.current() if pacc is not None else acc
@@ -506,8 +507,8 @@ class XPySom:
                     if prof is not None:
                         ev[1].record()
                         prof.append(ev)
-                    if pacc is None:
-                        all_reduce(acc)
+                    if pacc is None and group is not None:
+                        all_reduce(eng.accum_one_copy(acc, K, d))
                     tail(t, a, qinv)
                 if pacc is not None:
                     pacc.fence()            # nobody is still reading this rank's accumulators when train() returns
