@@ -53,7 +53,7 @@ constexpr int NUM_BARS = 2 * NST + 2 * NACC;
 constexpr int SMEM_BYTES = NST * STAGE_BYTES + NEPI_WARPS * EPI_STAGE_FLOATS * 4 + 2 * BM * 4 + NUM_BARS * 8 + 64 + 1024;
 static_assert(SMEM_BYTES <= 227 * 1024, "shared memory of the filter kernel");
 
-constexpr int CAPH = 64;                                 // candidate entries per row and column half
+constexpr int CAPH = 128;                                // candidate entries per row and column half
 constexpr int CAND_PER_ROW = 2 * CAPH;
 constexpr int MU_ROWS = 65536;                           // rows the centre is estimated from
 

@@ -277,8 +277,9 @@ class XPySom:
 
     # ---- long rows: one tensor-core pass + exact refinement (csrc/bmu_filter.cuh) -------------------------------
     _FILTER_PROBE_ROWS = 8192
-    _FILTER_MAX_CANDIDATES = 12.0      # re-scored candidates per row above which the three-pass kernel is cheaper
-    _FILTER_MAX_OVERFLOW = 0.005       # fraction of rows whose candidate lists may overflow
+    # re-scored candidates per row above which the three-pass kernel is cheaper / fraction of rows whose lists may overflow
+    _FILTER_MAX_CANDIDATES = float(os.environ.get('SOM_B200_FILTER_MAXC', '12'))
+    _FILTER_MAX_OVERFLOW = float(os.environ.get('SOM_B200_FILTER_MAXO', '0.005'))
 
     def _filter_state(self, eng, x, K, dist_kind, cache_key=None):
         """Workspaces of the filter path for the resident samples x (None when the shape is not eligible or another
