@@ -583,10 +583,10 @@ class GpuBench:
             for k in others:
                 w2 = WORKLOADS[k]
                 heavy = w2["gx"] * w2["gy"] * w2["d"] > 4_000_000
-                subs[k] = self.sub_record(k, w2, False, 5 if heavy else min(args.steps, 20), 3, 0.0 if heavy else 0.1)
+                subs[k] = self.sub_record(k, w2, False, 10 if heavy else min(args.steps, 20), 3, 0.0 if heavy else 0.1)
             subs[wl_key + "_blobs"] = self.sub_record(wl_key, wl, True, min(args.steps, 20), 3, 0.1)
             if wl_key != "c4":     # the north-star shape later in the schedule, where the map has differentiated
-                subs["c4_late"] = self.sub_record("c4", WORKLOADS["c4"], False, 5, 40, 0.0)
+                subs["c4_late"] = self.sub_record("c4", WORKLOADS["c4"], False, 10, 40, 0.0)
 
         if rank != 0:
             return

@@ -236,17 +236,20 @@ int som_b200_epoch_tail(uint64_t *acc_dev, const float *qinv_dev, float *s_dev, 
  * BMU; the few survivors are re-scored exactly (fp64 sum of squared differences of the caller's fp32 arrays) and the
  * first minimum wins.  Replaces _winner / _activate (xpysom.py:336-354,410-417) for those shapes.
  *   som_b200_filter_prepare_samples   once per upload: centre, fp16 copy of the samples, per-row statistics
- *   som_b200_bmu_filter               BMUs of all rows (the codebook side is prepared inside, every call)
+ *   som_b200_bmu_filter               BMUs of all rows (the codebook side is prepared inside, every call); bmu_dev holds the
+ *                                     previous epoch's BMUs on entry (seeds of the bounds; -1 = none); with acc_dev /
+ *                                     qscale_dev non-NULL the refine also adds every row it resolved to the exact accumulator
  * After som_b200_bmu_filter the workspace holds, at byte som_b200_filter_overflow_offset: int32 = rows whose candidate
  * lists overflowed (their bmu is -1: the caller re-does them with som_b200_bmu), and at +8 a uint64 = candidates
  * re-scored in that call (long lists make the refinement dearer than the two tensor passes it saves: the caller's
- * policy input).  An epoch is then: som_b200_bmu_filter, fix the overflowed rows up, som_b200_accumulate. */
+ * policy input).  An epoch is then: som_b200_bmu_filter with the accumulator, then som_b200_bmu + som_b200_accumulate on
+ * the overflowed rows only. */
 int    som_b200_filter_eligible(const float *x_dev, int64_t n, int d, int64_t ldx, int k, int dist_kind);
 size_t som_b200_filter_workspace_bytes(int64_t n, int k, int d);
 size_t som_b200_filter_overflow_offset(int64_t n, int k, int d);
 int    som_b200_filter_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, void *fws_dev, size_t fws_bytes, void *stream);
 int    som_b200_bmu_filter(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int32_t *bmu_dev,
-                           void *fws_dev, size_t fws_bytes, void *stream);
+                           const float *qscale_dev, uint64_t *acc_dev, void *fws_dev, size_t fws_bytes, void *stream);
 
 /* ---- sharded path: the one exchange step, fused into the epoch tail ---------------------------
  * The reference sums the per-block partial updates with Dask (`sum(...)` over the delayed `_update`

@@ -38,7 +38,7 @@ SIGNATURES = {
     "som_b200_filter_prepare_samples": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_void_p,
                                                        ctypes.c_size_t, ctypes.c_void_p]),
     "som_b200_bmu_filter": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, c_f32p, ctypes.c_int, c_i32p,
-                                           ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
+                                           c_f32p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t, ctypes.c_void_p]),
     "som_b200_accum_finalize": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int, ctypes.c_int, c_f32p, c_f32p,
                                                ctypes.c_void_p]),
     "som_b200_accum_fold": (ctypes.c_int, [ctypes.c_void_p, c_f32p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,

@@ -367,7 +367,7 @@ int som_b200_filter_prepare_samples(const float *x_dev, int64_t n, int d, int64_
 }
 
 int som_b200_bmu_filter(const float *x_dev, int64_t n, int d, int64_t ldx, const float *w_dev, int k, int32_t *bmu_dev,
-                        void *fws_dev, size_t fws_bytes, void *stream) {
+                        const float *qscale_dev, uint64_t *acc_dev, void *fws_dev, size_t fws_bytes, void *stream) {
     SOM_REQUIRE(x_dev && w_dev && bmu_dev && fws_dev, SOM_E_BADARG, "bmu_filter: NULL pointer");
     SOM_REQUIRE(flt::filter_eligible(x_dev, n, d, ldx, k, SOM_DIST_EUCLIDEAN), SOM_E_SHAPE, "bmu_filter: shape not eligible");
     SOM_REQUIRE(fws_bytes >= flt::filter_layout(n, k, d).total, SOM_E_WORKSPACE, "bmu_filter: workspace %zu < %zu bytes", fws_bytes,
@@ -375,7 +375,11 @@ int som_b200_bmu_filter(const float *x_dev, int64_t n, int d, int64_t ldx, const
     DevInfo di;
     int rc = device_info(di);
     if (rc) return rc;
-    return flt::launch_bmu_filter(x_dev, n, d, ldx, w_dev, k, static_cast<uint8_t *>(fws_dev), bmu_dev, di.sm, (cudaStream_t)stream);
+    SOM_REQUIRE((acc_dev == nullptr) == (qscale_dev == nullptr), SOM_E_BADARG, "bmu_filter: accumulator and scales go together");
+    SOM_REQUIRE(acc_dev == nullptr || ((reinterpret_cast<uintptr_t>(acc_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(qscale_dev) & 15) == 0),
+                SOM_E_SHAPE, "bmu_filter: the accumulator and the scales must be 16-byte aligned");
+    const AccTarget T = acc_dev ? acc_target(acc_dev, qscale_dev, k, d) : AccTarget();
+    return flt::launch_bmu_filter(x_dev, n, d, ldx, w_dev, k, static_cast<uint8_t *>(fws_dev), bmu_dev, T, di.sm, (cudaStream_t)stream);
 }
 
 int som_b200_accumulate(const float *x_dev, int64_t n, int d, int64_t ldx, const int32_t *bmu_dev, int k,

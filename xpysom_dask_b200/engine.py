@@ -204,13 +204,16 @@ class CudaEngine:
         v = fws[off:off + 16].view(torch.int64).cpu()
         return int(v[0].item()) & 0xffffffff, int(v[1].item())
 
-    def bmu_filter(self, x, w, fws, bmu_out=None):
+    def bmu_filter(self, x, w, fws, bmu_out=None, qscale=None, acc=None):
+        """BMUs through the one-pass filter + refinement; bmu_out holds the previous epoch's BMUs on entry (-1: none).
+        With qscale / acc the refine also adds every resolved row to the exact accumulator (overflowed rows, -1, not)."""
         n, d = x.shape
         if bmu_out is None:
-            bmu_out = self.empty(n, dtype=torch.int32)
+            bmu_out = torch.full((n,), -1, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.som_b200_bmu_filter(self._p(x), n, d, x.stride(0), self._p(w), w.shape[0], self._p(bmu_out),
-                                                    self._p(fws), fws.numel(), self._stream()), "som_b200_bmu_filter")
+                                                    self._p(qscale), self._p(acc), self._p(fws), fws.numel(), self._stream()),
+                       "som_b200_bmu_filter")
         self.launches += 3
         return bmu_out
 

@@ -303,7 +303,7 @@ class XPySom:
     def _filter_good(self, ovf, evals, rows):
         return ovf <= self._FILTER_MAX_OVERFLOW * rows and evals <= self._FILTER_MAX_CANDIDATES * max(rows - ovf, 1)
 
-    def _filter_epoch(self, eng, st, x, w, bmu, ws, dist_kind, p, xscale):
+    def _filter_epoch(self, eng, st, x, w, bmu, ws, dist_kind, p, xscale, qscale, acc):
         """BMUs of all rows of x through the filter path, into ``bmu``; False when this epoch should take the three-pass
         kernel instead (the probe, or the previous epoch, found the candidate lists too long for the current map)."""
         n, d = x.shape
@@ -321,13 +321,15 @@ class XPySom:
                 if ev > 2.0 * self._FILTER_MAX_CANDIDATES * max(npr - ovf, 1) or ovf > 4 * self._FILTER_MAX_OVERFLOW * npr:
                     st['skip'] = 2
                 return False
-        eng.bmu_filter(x, w, st['fws'], bmu)
+        eng.bmu_filter(x, w, st['fws'], bmu, qscale=qscale, acc=acc)      # (the refine accumulates the rows it resolves)
         ovf, ev = eng.filter_stats(st['fws'], n, K, d)
-        if ovf:            # rows whose lists overflowed: the three-pass kernel on just those rows
+        if ovf:            # rows whose lists overflowed: the three-pass kernel and the accumulate on just those rows
             rows = torch.nonzero(bmu < 0).squeeze(1)
             xg = x.index_select(0, rows)
             xs_g = eng.prepare_samples(xg, True)[0]
-            bmu.index_copy_(0, rows, eng.bmu(xg, w, dist_kind, p, _lib.ALGO['tc16'], ws, xscale=xs_g))
+            bmu_g = eng.bmu(xg, w, dist_kind, p, _lib.ALGO['tc16'], ws, xscale=xs_g)
+            eng.accumulate(xg, bmu_g, K, qscale, acc)
+            bmu.index_copy_(0, rows, bmu_g)
         st['on'] = self._filter_good(ovf, ev, n)
         self.stats['filter_epochs'] = self.stats.get('filter_epochs', 0) + 1
         self.stats['filter_last'] = (ovf / n, ev / max(n - ovf, 1))
@@ -501,8 +503,8 @@ class XPySom:
                     if prof is not None:
                         ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
                         ev[0].record()
-                    if n > 0 and flt is not None and self._filter_epoch(eng, flt, x, w, bmu, ws, dist_kind, p, xscale):
-                        eng.accumulate(x, bmu, K, qscale, a)           # BMUs from the one-pass filter + exact refinement
+                    if n > 0 and flt is not None and self._filter_epoch(eng, flt, x, w, bmu, ws, dist_kind, p, xscale, qscale, a):
+                        pass                # BMUs from the one-pass filter + refinement, accumulated by the refine kernel
                     elif n > 0:             # a rank may hold an EMPTY shard: it still joins the exchange and the tail
                         eng.epoch_accumulate(x, w, dist_kind, p, algo, qscale, a, ws, bmu_out=bmu, xscale=xscale)
                     if prof is not None:
