@@ -173,3 +173,20 @@ def test_training_is_bit_reproducible_and_streaming_matches_resident():
     res.train(data, 6, iter_beg=1, iter_end=3)
     assert U.codebook_rel_err(ooc._weights, res._weights) < 2e-3       # free-running: last-bit differences amplify
     assert ooc.quantization_error(data) == pytest.approx(res.quantization_error(data), rel=1e-3)
+
+
+@pytest.mark.gpu
+def test_sharded_training_equals_one_gpu_bitwise_on_two_gpus():
+    """Row G of SURVEY 8a on hardware (needs >= 2 GPUs in the box, skipped otherwise): tools/peer_check.py --quick trains
+    five map types on 2 ranks with the exchange fused into the epoch tail (accumulators in NVLink peer memory) and with
+    the NCCL all-reduce of the integer accumulator, and requires both to equal ONE GPU training on all the rows, bit for bit."""
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29533", os.path.join(root, "tools", "peer_check.py"), "--quick"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=500, cwd=root)
+    assert out.returncode == 0 and "PEER CHECK PASSED" in out.stdout, out.stdout[-3000:] + out.stderr[-2000:]
