@@ -317,7 +317,7 @@ inline SliceGeom neigh_slice_geom(int K, int d, int sm_count) {
     const bool big = d > 64 && K >= 512;                         // 128 x 128 tiles, 8 x 8 per thread
     g.tm = big ? 128 : 64; g.tn = big ? 128 : 64;
     const int gxy = (int)(ceil_div(K, g.tm) * ceil_div(d, g.tn));
-    int slices = (2 * sm_count + gxy - 1) / gxy;
+    int slices = (2 * sm_count) / gxy;                            // ONE wave of 2 CTAs per SM (rounding up left a 4-CTA second wave at config 5)
     const int max_slices = (int)ceil_div(K, 4 * 16);
     if (slices > max_slices) slices = max_slices;
     if (slices < 1) slices = 1;
