@@ -294,9 +294,13 @@ class XPySom:
             return cached[3]
         n = x.shape[0]
         npr = min(n, self._FILTER_PROBE_ROWS)
-        st = {'fws': eng.filter_workspace(x, K), 'n_probe': npr, 'on': None,
-              'probe': eng.filter_workspace(x[:npr], K) if npr < n else None,
-              'probe_bmu': torch.full((npr,), -1, dtype=torch.int32, device=eng.device)}
+        try:               # ~3.8 KB of workspace per row (fp16 copy of the samples, candidate lists)
+            st = {'fws': eng.filter_workspace(x, K), 'n_probe': npr, 'on': None,
+                  'probe': eng.filter_workspace(x[:npr], K) if npr < n else None,
+                  'probe_bmu': torch.full((npr,), -1, dtype=torch.int32, device=eng.device)}
+        except torch.cuda.OutOfMemoryError:
+            torch.cuda.empty_cache()
+            return None    # no room for it: the three-pass kernel needs no extra memory
         self._filter_cache = (weakref.ref(cache_key), cache_key._version, K, st) if cache_key is not None else None
         return st
 
