@@ -113,9 +113,11 @@ int som_b200_prepare_samples(const float *x_dev, int64_t n, int d, int64_t ldx, 
 int    som_b200_accum_scales(const float *colmax_dev, int d, double n_total, float *qscale_dev, float *qinv_dev, void *stream);
 size_t som_b200_accum_words(int k, int d);
 int    som_b200_accum_replicas(int k, int d);
-/* Sharded runs that all-reduce the accumulator themselves: add replicas 1.. into replica 0 (and clear them) first, then
- * all-reduce only the first som_b200_accum_words(k, d) / som_b200_accum_replicas(k, d) words. */
-int    som_b200_accum_fold_replicas(uint64_t *acc_dev, int k, int d, void *stream);
+/* Sharded runs: dst_dev == NULL adds replicas 1.. into replica 0 (and clears them) -- then all-reduce only the first
+ * som_b200_accum_words(k, d) / som_b200_accum_replicas(k, d) words; dst_dev = a peer accumulator
+ * (som_b200_peer_accumulator) adds ALL replicas into it and clears them: on data with hot BMUs, accumulate into a local
+ * replicated accumulator, fold it into the peer accumulator, then som_b200_epoch_tail on the peer accumulator. */
+int    som_b200_accum_fold_replicas(uint64_t *acc_dev, uint64_t *dst_dev, int k, int d, void *stream);
 
 /* Exact accumulator -> fp32 S (k, d) and c (k), one rounding per element; the accumulator is cleared. */
 int som_b200_accum_finalize(uint64_t *acc_dev, const float *qinv_dev, int k, int d, float *s_dev, float *c_dev, void *stream);

@@ -49,15 +49,17 @@ for gx, gy, d, n, kw in CASES:
     rng = np.random.RandomState(100 + rank)
     shard = torch.from_numpy(rng.random_sample((n + 37 * rank, d)).astype(np.float32)).to(dev)    # ragged shards
     res = {}
-    for mode in ("peer", "nccl"):
+    for mode in ("peer", "peer_hot", "nccl"):
         os.environ["SOM_B200_PEER"] = "0" if mode == "nccl" else "1"
         som = XPySom(gx, gy, d, random_seed=4, device=dev, process_group=True, **kw)
+        som._hot_bmus = mode == "peer_hot"       # forced: accumulate into local replicas, fold into the peer accumulator
         som.train(shard, 7)
+        som._hot_bmus = mode == "peer_hot"
         som.train(shard, 12, iter_beg=7, iter_end=12)            # a second call on the same communicator
         res[mode] = torch.as_tensor(som.get_weights()).to(dev)
         used = getattr(som, "_peer_cache", None)
         active = used is not None and used[1].active
-        if mode == "peer" and not active:
+        if mode != "nccl" and not active:
             log("  peer accumulators NOT active (IPC unavailable?)")
             ok = False
         if used is not None:
@@ -71,11 +73,11 @@ for gx, gy, d, n, kw in CASES:
     single.train(torch.cat(parts), 7)
     single.train(torch.cat(parts), 12, iter_beg=7, iter_end=12)
     one = torch.as_tensor(single.get_weights()).to(dev)
-    a = torch.equal(res["peer"], res["nccl"])
+    a = torch.equal(res["peer"], res["nccl"]) and torch.equal(res["peer_hot"], res["nccl"])
     b = same_everywhere(res["peer"])
     c = torch.equal(res["peer"], one)
     rel = float((res["peer"] - one).abs().max() / one.abs().max())
-    log("%2dx%-2d d=%-3d %s: peer == NCCL bitwise %s | identical on all ranks %s | == one GPU on all rows %s (rel %.1e)"
+    log("%2dx%-2d d=%-3d %s: peer == peer via local replicas == NCCL bitwise %s | identical on all ranks %s | == one GPU on all rows %s (rel %.1e)"
         % (gx, gy, d, kw or "", a, b, c, rel))
     if not (a and b and c):
         ok = False

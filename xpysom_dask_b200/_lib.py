@@ -31,7 +31,7 @@ SIGNATURES = {
     "som_b200_accum_scales": (ctypes.c_int, [c_f32p, ctypes.c_int, ctypes.c_double, c_f32p, c_f32p, ctypes.c_void_p]),
     "som_b200_accum_words": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int]),
     "som_b200_accum_replicas": (ctypes.c_int, [ctypes.c_int, ctypes.c_int]),
-    "som_b200_accum_fold_replicas": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
+    "som_b200_accum_fold_replicas": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p]),
     "som_b200_filter_eligible": (ctypes.c_int, [c_f32p, ctypes.c_int64, ctypes.c_int, ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "som_b200_filter_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),
     "som_b200_filter_overflow_offset": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int, ctypes.c_int]),

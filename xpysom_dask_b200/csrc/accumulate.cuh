@@ -108,16 +108,20 @@ __global__ void accum_fold_kernel(unsigned long long *__restrict__ Si, int reps,
     }
 }
 
-// replicas 1.. of a local accumulator added into replica 0 and cleared (before an all-reduce: one copy travels)
-__global__ void accum_fold_replicas_kernel(unsigned long long *__restrict__ Si, int reps, size_t rep_words, int64_t all) {
+// the replicas of a local accumulator folded into ONE copy and cleared: dst == Si: replicas 1.. added into replica 0
+// (before an all-reduce: one copy travels); dst != Si: all replicas summed into dst (a peer-memory accumulator, zero
+// before) -- the sharded path on hot data: scatter into local replicas, fold into the mailbox, exchange
+__global__ void accum_fold_replicas_kernel(unsigned long long *__restrict__ Si, int reps, size_t rep_words, int64_t all,
+                                           unsigned long long *__restrict__ dst) {
     pdl_wait(); pdl_trigger();
+    const int r0 = dst == Si ? 1 : 0;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < all; e += (int64_t)gridDim.x * blockDim.x) {
         unsigned long long u = 0ull;
-        for (int r = 1; r < reps; ++r) {
+        for (int r = r0; r < reps; ++r) {
             const unsigned long long w = Si[(size_t)r * rep_words + e];
             if (w) { u += w; Si[(size_t)r * rep_words + e] = 0ull; }
         }
-        if (u) Si[e] += u;
+        if (u) dst[e] += u;
     }
 }
 

@@ -247,16 +247,17 @@ int som_b200_accum_finalize(uint64_t *acc_dev, const float *qinv_dev, int k, int
                       "accum_finalize_kernel launch");
 }
 
-int som_b200_accum_fold_replicas(uint64_t *acc_dev, int k, int d, void *stream) {
+int som_b200_accum_fold_replicas(uint64_t *acc_dev, uint64_t *dst_dev, int k, int d, void *stream) {
     SOM_REQUIRE(acc_dev && k > 0 && d > 0, SOM_E_BADARG, "accum_fold_replicas: bad argument");
     const AccTarget T = acc_target(acc_dev, nullptr, k, d);
-    if (T.reps <= 1) return 0;
+    unsigned long long *dst = dst_dev ? reinterpret_cast<unsigned long long *>(dst_dev) : T.S;
+    if (T.reps <= 1 && dst == T.S) return 0;
     DevInfo di;
     int rc = device_info(di);
     if (rc) return rc;
     const int64_t all = (int64_t)k * acc_ld(d) + k;
     return check_cuda(launch_pdl(accum_fold_replicas_kernel, dim3(grid_for(all, di.sm)), dim3(256), 0, (cudaStream_t)stream, T.S,
-                                 T.reps, T.rep_words, all), "accum_fold_replicas_kernel launch");
+                                 T.reps, T.rep_words, all, dst), "accum_fold_replicas_kernel launch");
 }
 
 int som_b200_accum_fold(uint64_t *acc_dev, const float *qinv_dev, int k, int d, double *sd_dev, void *stream) {

@@ -107,10 +107,17 @@ class CudaEngine:
         if reps <= 1:
             return acc
         with torch.cuda.device(self.device):
-            _lib.check(self.lib.som_b200_accum_fold_replicas(self._p(acc), int(k), int(d), self._stream()),
+            _lib.check(self.lib.som_b200_accum_fold_replicas(self._p(acc), None, int(k), int(d), self._stream()),
                        "som_b200_accum_fold_replicas")
         self.launches += 1
         return acc[:acc.numel() // reps]
+
+    def accum_fold_into(self, acc, dst, k, d):
+        """All replicas of the local accumulator added into dst (a peer accumulator) and cleared."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.som_b200_accum_fold_replicas(self._p(acc), self._p(dst), int(k), int(d), self._stream()),
+                       "som_b200_accum_fold_replicas")
+        self.launches += 1
 
     def accum_finalize(self, acc, qinv, k, d, s, c):
         with torch.cuda.device(self.device):
