@@ -477,7 +477,7 @@ class GpuBench:
         rec["filter_path"] = {"epochs_on_it_so_far": st.get("filter_epochs", 0),
                               "last_full_run_overflow_frac_and_candidates_per_row": st.get("filter_last"),
                               "last_probe_overflow_frac_and_candidates_per_row": st.get("filter_probe"),
-                              "policy": "used when <= 12 candidates per row survive the one-pass bounds and <= 0.5 % of the "
+                              "policy": "used when <= 24 candidates per row survive the one-pass bounds and <= 0.5 % of the "
                                         "rows overflow their lists (probe on 8192 rows, or the previous epoch)"}
         if st.get("filter_epochs", 0):
             r = rec["roofline"]

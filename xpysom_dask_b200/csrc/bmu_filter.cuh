@@ -477,7 +477,7 @@ filter_seed_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, c
 // clock and SM.)
 // one warp per row.  A row whose list overflowed gets bmu = -1 and is counted in ovf[0] (the caller re-does those rows
 // with the three-pass kernel); ovf[2..3] (one uint64) = candidates re-scored in this launch (the caller's policy input)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 bmu_refine_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, const float *W, int k,
                   const int2 *__restrict__ cand, const int2 *__restrict__ meta, int32_t *__restrict__ bmu, int *__restrict__ ovf,
                   const ExactAcc A0) {
@@ -503,17 +503,20 @@ bmu_refine_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, co
             const int c4 = lane + 32 * i;
             x[i] = c4 < d4 ? __ldg(xr + c4) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
-        auto dist2 = [&](int kk) -> float {
+        auto load_w = [&](int kk, float4 (&w)[MAXV]) {
             const float4 *wr = reinterpret_cast<const float4 *>(W + (size_t)kk * d);
-            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
             for (int i = 0; i < MAXV; ++i) {
                 const int c4 = lane + 32 * i;
-                if (c4 < d4) {
-                    const float4 w = wr[c4];
-                    const float a = x[i].x - w.x, b = x[i].y - w.y, c = x[i].z - w.z, e = x[i].w - w.w;
-                    s0 = fmaf(a, a, s0); s1 = fmaf(b, b, s1); s2 = fmaf(c, c, s2); s3 = fmaf(e, e, s3);
-                }
+                w[i] = c4 < d4 ? wr[c4] : x[i];                 // (difference 0 past the end)
+            }
+        };
+        auto dist2 = [&](const float4 (&w)[MAXV]) -> float {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) {
+                const float a = x[i].x - w[i].x, b = x[i].y - w[i].y, c = x[i].z - w[i].z, e = x[i].w - w[i].w;
+                s0 = fmaf(a, a, s0); s1 = fmaf(b, b, s1); s2 = fmaf(c, c, s2); s3 = fmaf(e, e, s3);
             }
             return warp_sum((s0 + s1) + (s2 + s3));    // (xor butterfly: every lane holds the same bits)
         };
@@ -525,16 +528,31 @@ bmu_refine_kernel(const float *__restrict__ X, int64_t n, int d, int64_t ldx, co
             if (lane == 0) bmu[r] = -1;
             continue;
         }
-        for (int half = 0; half < 2; ++half) {
-            const int cn = half ? m1.x : m0.x;
-            const int2 *list = cand + r * CAND_PER_ROW + half * CAPH;
-            for (int i = 0; i < cn; ++i) {
-                const int2 e = list[i];
-                if (!(__int_as_float(e.y) <= U) || e.x >= k) continue;         // pruned by the final bound
-                const float v = dist2(e.x);
-                n_eval += 1;
-                if (v < best || (v == best && e.x < bidx)) { best = v; bidx = e.x; }
+        // The surviving entries of both halves, software-pipelined: the next candidate's codebook row is in flight while
+        // this one is reduced (the re-scoring is bound by L2 latency / bandwidth: 4 D bytes per candidate).
+        const int2 *list0 = cand + r * CAND_PER_ROW;
+        const int total = m0.x + m1.x;
+        auto next_live = [&](int i) -> int {           // first entry >= i that survives the final bound; its neuron in nk
+            for (; i < total; ++i) {
+                const int2 e = i < m0.x ? list0[i] : list0[CAPH + (i - m0.x)];
+                if (__int_as_float(e.y) <= U && e.x < k) return i;
             }
+            return total;
+        };
+        auto unit_of = [&](int i) -> int { return (i < m0.x ? list0[i] : list0[CAPH + (i - m0.x)]).x; };
+        int cur = next_live(0);
+        float4 wa[MAXV], wb[MAXV];
+        if (cur < total) load_w(unit_of(cur), wa);
+        while (cur < total) {
+            const int ku = unit_of(cur);
+            const int nxt = next_live(cur + 1);
+            if (nxt < total) load_w(unit_of(nxt), wb);
+            const float v = dist2(wa);
+            n_eval += 1;
+            if (v < best || (v == best && ku < bidx)) { best = v; bidx = ku; }
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i) wa[i] = wb[i];
+            cur = nxt;
         }
         if (bidx == 0x7fffffff) bidx = 0;
         if (lane == 0) bmu[r] = bidx;

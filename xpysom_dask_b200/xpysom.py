@@ -278,7 +278,7 @@ class XPySom:
     # ---- long rows: one tensor-core pass + exact refinement (csrc/bmu_filter.cuh) -------------------------------
     _FILTER_PROBE_ROWS = 8192
     # re-scored candidates per row above which the three-pass kernel is cheaper / fraction of rows whose lists may overflow
-    _FILTER_MAX_CANDIDATES = float(os.environ.get('SOM_B200_FILTER_MAXC', '12'))
+    _FILTER_MAX_CANDIDATES = float(os.environ.get('SOM_B200_FILTER_MAXC', '24'))
     _FILTER_MAX_OVERFLOW = float(os.environ.get('SOM_B200_FILTER_MAXO', '0.005'))
 
     def _filter_state(self, eng, x, K, dist_kind, cache_key=None):
